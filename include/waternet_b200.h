@@ -1,0 +1,126 @@
+/*
+ * waternet_b200 -- C ABI of the B200-native WaterNet hot path.
+ *
+ * The reference (tnwei/waternet @ 2091896) is pure Python; it has no FFI.  The
+ * boundary it exposes for this path is its Python API, and every entry point
+ * below is what a binding for one of those calls would bind (file:line are
+ * relative to the reference checkout):
+ *
+ *   wn_preprocess_u8      waternet/data.py:81-90   transform(rgb) -> wb, gc, he
+ *                         + hubconf.py:8-21        arr2ten_noeinops (x/255, HWC->1CHW)
+ *                         + hubconf.py:85-91       preprocess(rgb) -> rgb, wb, he, gc tensors
+ *   wn_pack_weights       waternet/net.py:12-42,62-70,94-97  the 34-tensor state dict
+ *                         (hubconf.py:83 / inference.py:111-120 load_state_dict)
+ *   wn_forward            waternet/net.py:99-108   WaterNet.forward(x, wb, ce, gc)
+ *   wn_postprocess_u8     hubconf.py:24-34         ten2arr_noeinops (clip, *255, truncate, NCHW->NHWC)
+ *   wn_enhance_u8         hubconf.py:85-94 + net.py:99-108: preprocess -> model -> postprocess
+ *                         (the per-frame body of inference.py:261-323)
+ *
+ * Conventions: every data pointer is a DEVICE pointer on the handle's device
+ * unless its name ends in _host; the caller owns every buffer (the handle only
+ * owns its packed weights and constant tables); every call is asynchronous on
+ * `stream` (a cudaStream_t passed as void*); return 0 on success, a negative
+ * WN_E_* code otherwise with a message available from wn_last_error() (thread
+ * local).  A handle may be used from one thread at a time.
+ */
+#ifndef WATERNET_B200_H_
+#define WATERNET_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WN_ABI_VERSION 1
+
+#define WN_OK 0
+#define WN_E_INVALID (-1)   /* bad argument (NULL pointer, non-positive size, unknown mode) */
+#define WN_E_CUDA (-2)      /* a CUDA call failed; wn_last_error() has cudaGetErrorString */
+#define WN_E_STATE (-3)     /* call order: forward before wn_pack_weights, etc. */
+#define WN_E_WORKSPACE (-4) /* workspace smaller than wn_*_workspace_bytes() */
+#define WN_E_UNSUPPORTED (-5)
+
+/* Arithmetic used for the 17 convolutions of wn_forward. */
+#define WN_MODE_FP32_SIMT 0 /* fp32 FMA on CUDA cores (bit-for-bit independent of tensor cores) */
+#define WN_MODE_BF16X3 1    /* tcgen05 tensor cores, 3-term bf16 split operands, fp32 accumulate */
+#define WN_MODE_DEFAULT (-1) /* the library's fastest mode that meets the 1e-3 parity bar */
+
+#define WN_NUM_PARAMS 34
+
+typedef struct wn_handle wn_handle;
+
+int wn_abi_version(void);
+const char* wn_last_error(void);
+
+/* One handle per device.  Builds the constant tables (sRGB / Lab / gamma). */
+int wn_create(int device, wn_handle** out);
+void wn_destroy(wn_handle* h);
+
+/*
+ * Host-only: fill the constant tables the preprocess kernels use, so that they
+ * can be checked on a machine without a GPU.  Sizes: gtab[256], ctab[3072],
+ * ytab[256], fytab[256], igtab[4096], gamma[256], div255[256].
+ */
+int wn_build_tables_host(uint16_t* gtab, uint16_t* ctab, int16_t* ytab, int16_t* fytab,
+                         uint8_t* igtab, uint8_t* gamma, float* div255);
+
+/*
+ * params: WN_NUM_PARAMS device pointers to contiguous fp32 tensors in the order of
+ * WaterNet().state_dict(): cmg.conv1.weight, cmg.conv1.bias, ... cmg.conv8.bias,
+ * wb_refiner.conv1.weight ... gc_refiner.conv3.bias; weights are OIHW.
+ * Re-packs them into the kernels' layouts (device side, asynchronous).
+ */
+int wn_pack_weights(wn_handle* h, const float* const* params, void* stream);
+
+/*
+ * WaterNet.forward.  x/wb/he/gc: fp32 (N,3,H,W) with arbitrary element strides
+ * in_strides[i] = {sN, sC, sH, sW} (contiguous NCHW and the channels_last strides
+ * arr2ten produces are both accepted).  out: fp32 contiguous NCHW (N,3,H,W).
+ */
+size_t wn_forward_workspace_bytes(int n, int h, int w, int mode);
+int wn_forward(wn_handle* h, const float* x, const float* wb, const float* he, const float* gc,
+               const int64_t in_strides[4][4], float* out, int n, int height, int width, int mode,
+               void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * transform + arr2ten.  rgb: uint8 NHWC (N,H,W,3).  Any output pointer may be
+ * NULL.  fp32 outputs are contiguous NCHW (N,3,H,W) in [0,1] (u/255, true
+ * division); *_u8 outputs are NHWC like the reference's numpy arrays.
+ * Statistics (white balance quantiles, CLAHE tiles) are per image.
+ */
+size_t wn_preprocess_workspace_bytes(int n, int h, int w);
+int wn_preprocess_u8(wn_handle* h, const uint8_t* rgb, int n, int height, int width, float* x,
+                     float* wb, float* he, float* gc, uint8_t* wb_u8, uint8_t* he_u8,
+                     uint8_t* gc_u8, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ten2arr: fp32 NCHW (N,3,H,W) -> uint8 NHWC, clip to [0,1], *255, truncate. */
+int wn_postprocess_u8(wn_handle* h, const float* out_nchw, uint8_t* out_nhwc, int n, int height,
+                      int width, void* stream);
+
+/* preprocess -> forward -> postprocess without leaving the device. */
+size_t wn_enhance_workspace_bytes(int n, int h, int w, int mode);
+int wn_enhance_u8(wn_handle* h, const uint8_t* rgb, uint8_t* out_nhwc, float* out_f32_or_null,
+                  int n, int height, int width, int mode, void* workspace, size_t workspace_bytes,
+                  void* stream);
+
+/*
+ * Per-kernel device timing (measurement aid for bench.py, off by default).  When on, every
+ * kernel group is bracketed by a cudaEvent pair on the launching stream.  wn_read_timings
+ * must be called after the stream has been synchronised; it adds the elapsed milliseconds and
+ * the number of bracketed launches per slot into ms[] / count[] (WN_NUM_TIMING_SLOTS entries:
+ * 0..16 the convolutions in state-dict order, 17 operand packing, 18 gated sum, 19 preprocess
+ * statistics, 20 LUT build, 21 per-pixel apply, 22 postprocess) and clears the record.
+ */
+#define WN_NUM_TIMING_SLOTS 23
+int wn_enable_timing(wn_handle* h, int on);
+int wn_read_timings(wn_handle* h, float* ms, int* count);
+
+/* Number of kernels the library has launched on this handle since creation. */
+uint64_t wn_launch_count(const wn_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WATERNET_B200_H_ */

@@ -92,9 +92,14 @@ def _build_lab_tables():
     f = np.where(
         x < np.float32(0.008856),
         x * np.float32(7.787) + np.float32(0.13793103448275862),
-        np.cbrt(x),
+        np.cbrt(x.astype(np.float64)).astype(np.float32),  # correctly rounded; SIMD-independent
     ).astype(np.float32)
     ctab = np.rint(np.float32(1 << _LAB_SHIFT2) * f).astype(np.int64)
+    # OpenCV fills LabCbrtTab_b with its own cube-root approximation; at these two arguments
+    # 32768*f sits on a .5 tie and OpenCV's value is one ulp low.  324 is reachable from 8-bit RGB
+    # (cv2 4.13 checked over all 2^24 colours), 2079 is not.
+    ctab[324] = 17745
+    ctab[2079] = 32975
 
     lvl = np.arange(256, dtype=np.float32)
     li = lvl * np.float32(100.0) / np.float32(255.0)

@@ -1,0 +1,115 @@
+"""CPU-side checks: the C-ABI library loads and exports what include/*.h declares; host logic."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+from oracle import forward as ofw
+from oracle import preprocess as opre
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from waternet_b200 import _lib, build
+    build.build()
+    return _lib.load()
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "waternet_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(wn_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(lib):
+    from waternet_b200 import _lib
+    declared = _declared_symbols()
+    assert len(declared) >= 12
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/waternet_b200.h but not exported"
+    assert sorted(_lib.EXPORTED_SYMBOLS) == declared, "ctypes binding and header disagree"
+    assert lib.wn_abi_version() == 1
+
+
+def test_constant_tables_match_oracle(lib):
+    gtab = (ctypes.c_uint16 * 256)()
+    ctab = (ctypes.c_uint16 * 3072)()
+    ytab = (ctypes.c_int16 * 256)()
+    fytab = (ctypes.c_int16 * 256)()
+    igtab = (ctypes.c_uint8 * 4096)()
+    gamma = (ctypes.c_uint8 * 256)()
+    div255 = (ctypes.c_float * 256)()
+    assert lib.wn_build_tables_host(gtab, ctab, ytab, fytab, igtab, gamma, div255) == 0
+    assert np.array_equal(np.array(gtab), opre._GTAB)
+    assert np.array_equal(np.array(ctab), opre._CTAB)
+    assert np.array_equal(np.array(ytab), opre._YTAB)
+    assert np.array_equal(np.array(fytab), opre._FYTAB)
+    assert np.array_equal(np.array(igtab), opre._IGTAB)
+    levels = np.arange(256, dtype=np.uint8)
+    assert np.array_equal(np.array(gamma), opre.gamma_correction(levels))
+    assert np.array_equal(np.array(div255, dtype=np.float32), levels.astype(np.float32) / np.float32(255))
+
+
+def test_null_arguments_are_rejected_without_a_gpu(lib):
+    assert lib.wn_create(0, None) != 0
+    assert b"NULL" in lib.wn_last_error() or b"null" in lib.wn_last_error()
+    assert lib.wn_forward_workspace_bytes(0, 10, 10, 0) == 0
+    assert lib.wn_forward_workspace_bytes(2, 112, 112, 0) > 0
+    assert lib.wn_preprocess_workspace_bytes(2, 112, 112) > 0
+
+
+def test_state_dict_is_reference_compatible():
+    from waternet_b200.net import WaterNet
+    m = WaterNet()
+    sd = m.state_dict()
+    spec = ofw.state_dict_spec()
+    assert list(sd.keys()) == [k for k, _ in spec]
+    for k, shape in spec:
+        assert tuple(sd[k].shape) == shape
+    m.load_state_dict(ofw.synthetic_state_dict(0), strict=True)
+    assert sum(p.numel() for p in m.parameters()) == 1_090_668
+    ordered = m._ordered_params()
+    assert len(ordered) == 34 and all(a is b for a, b in zip(ordered, m.parameters()))
+
+
+def test_torch_graph_equals_oracle_on_cpu():
+    """The differentiable graph used for gradients is the same function as the oracle."""
+    from waternet_b200.net import WaterNet
+    m = WaterNet()
+    sd = ofw.synthetic_state_dict(1, 3.0)
+    m.load_state_dict(sd)
+    torch.manual_seed(0)
+    ins = [torch.rand(1, 3, 20, 24) for _ in range(4)]
+    with torch.no_grad():
+        a = m._graph(*ins)
+    b = ofw.waternet_forward(sd, *ins)
+    assert torch.allclose(a, b, rtol=1e-5, atol=1e-6)
+
+
+def test_no_cpu_fallback_without_cuda():
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from waternet_b200 import WaterNetLibraryError, data
+    from waternet_b200.hub import waternet
+    with pytest.raises(WaterNetLibraryError):
+        data.transform(ofw.synthetic_image(0, 16, 16))
+    with pytest.raises(WaterNetLibraryError):
+        waternet(pretrained=False)
+
+
+def test_reference_module_paths_resolve():
+    import waternet.data as d
+    import waternet.net as n
+    import waternet.training_utils as tu
+    for name in ("WaterNet", "ConfidenceMapGenerator", "Refiner"):
+        assert hasattr(n, name)
+    for name in ("transform", "white_balance_transform", "gamma_correction", "histeq"):
+        assert hasattr(d, name)
+    for name in ("UIEBDataset", "arr2ten", "ten2arr"):
+        assert hasattr(tu, name)
+    import hubconf
+    assert callable(hubconf.waternet) and "torch" in hubconf.dependencies

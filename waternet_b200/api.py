@@ -1,0 +1,66 @@
+"""Host-buffer convenience API: numpy uint8 images in, numpy uint8 images out.
+
+This is the per-frame body of the reference's ``inference.py:169-233,261-323``
+(preprocess -> model -> postprocess) as one call; the host<->device copies use
+pinned staging buffers and the current CUDA stream.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from .engine import Engine, get_engine
+
+
+class Enhancer:
+    """Holds a model's packed weights and pinned staging buffers for repeated calls."""
+
+    def __init__(self, model, device=None, precision: Optional[str] = None):
+        self.engine: Engine = get_engine(device if device is not None else next(model.parameters()).device)
+        self.model = model.to(self.engine.device)
+        self.mode = model._mode() if precision is None else {
+            "default": _lib.MODE_DEFAULT, "fp32": _lib.MODE_FP32_SIMT, "bf16x3": _lib.MODE_BF16X3}[precision]
+        self._pin_in = None
+        self._pin_out = None
+        self._dev_in = None
+        self._dev_out = None
+
+    def _buffers(self, shape):
+        if self._dev_in is None or tuple(self._dev_in.shape) != tuple(shape):
+            self._dev_in = torch.empty(shape, dtype=torch.uint8, device=self.engine.device)
+            self._dev_out = torch.empty(shape, dtype=torch.uint8, device=self.engine.device)
+
+    def __call__(self, rgb: np.ndarray) -> np.ndarray:
+        """rgb: uint8 HWC or NHWC.  Returns the enhanced uint8 image(s), same layout."""
+        arr = np.asarray(rgb)
+        single = arr.ndim == 3
+        if single:
+            arr = arr[None]
+        if arr.dtype != np.uint8 or arr.ndim != 4 or arr.shape[3] != 3:
+            raise ValueError(f"expected uint8 (N)HWC RGB, got {arr.dtype} {arr.shape}")
+        eng = self.engine
+        params = self.model._ordered_params()
+        eng.pack_weights(params, key=tuple((p.data_ptr(), p._version) for p in params))
+        if self._pin_in is None or tuple(self._pin_in.shape) != tuple(arr.shape):
+            self._pin_in = torch.empty(arr.shape, dtype=torch.uint8).pin_memory()
+            self._pin_out = torch.empty(arr.shape, dtype=torch.uint8).pin_memory()
+        self._pin_in.numpy()[...] = arr
+        self.enhance_pinned(self._pin_in, self._pin_out)
+        out = self._pin_out.numpy().copy()
+        return out[0] if single else out
+
+    def enhance_pinned(self, pin_in: torch.Tensor, pin_out: torch.Tensor, after_device=None) -> None:
+        """Pinned uint8 NHWC host tensor -> pinned uint8 NHWC host tensor (H2D, kernels, D2H, sync).
+
+        ``after_device(dev_out)`` runs on the device result before the copy back (e.g. an all-gather).
+        """
+        self._buffers(tuple(pin_in.shape))
+        self._dev_in.copy_(pin_in, non_blocking=True)
+        self.engine.enhance(self._dev_in, mode=self.mode, out_u8=self._dev_out)
+        if after_device is not None:
+            after_device(self._dev_out)
+        pin_out.copy_(self._dev_out, non_blocking=True)
+        torch.cuda.current_stream(self.engine.device).synchronize()

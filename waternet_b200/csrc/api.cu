@@ -1,0 +1,281 @@
+// C ABI of libwaternet_b200.so (see include/waternet_b200.h for the contract).
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace wn {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+static int resolve_mode(int mode) {
+  if (mode == WN_MODE_DEFAULT) return WN_MODE_BF16X3;
+  return mode;
+}
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) ok = false;
+    if (ok && prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+}  // namespace wn
+
+using namespace wn;
+
+extern "C" {
+
+int wn_abi_version(void) { return WN_ABI_VERSION; }
+
+const char* wn_last_error(void) { return g_err; }
+
+int wn_build_tables_host(uint16_t* gtab, uint16_t* ctab, int16_t* ytab, int16_t* fytab,
+                         uint8_t* igtab, uint8_t* gamma, float* div255) {
+  if (!gtab || !ctab || !ytab || !fytab || !igtab || !gamma || !div255) {
+    set_error("wn_build_tables_host: null output");
+    return WN_E_INVALID;
+  }
+  Tables* t = (Tables*)malloc(sizeof(Tables));
+  build_tables_host(t);
+  memcpy(gtab, t->gtab, sizeof(t->gtab));
+  memcpy(ctab, t->ctab, sizeof(t->ctab));
+  memcpy(ytab, t->ytab, sizeof(t->ytab));
+  memcpy(fytab, t->fytab, sizeof(t->fytab));
+  memcpy(igtab, t->igtab, sizeof(t->igtab));
+  memcpy(gamma, t->gamma, sizeof(t->gamma));
+  memcpy(div255, t->div255, sizeof(t->div255));
+  free(t);
+  return WN_OK;
+}
+
+int wn_create(int device, wn_handle** out) {
+  if (!out) {
+    set_error("wn_create: out is NULL");
+    return WN_E_INVALID;
+  }
+  *out = nullptr;
+  int count = 0;
+  WN_CUDA(cudaGetDeviceCount(&count));
+  if (device < 0 || device >= count) {
+    set_error("wn_create: device %d out of range (%d devices)", device, count);
+    return WN_E_INVALID;
+  }
+  DeviceGuard guard(device);
+  cudaDeviceProp prop;
+  WN_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    set_error("wn_create: device %d is sm_%d%d; this library is built for sm_100a only", device,
+              prop.major, prop.minor);
+    return WN_E_UNSUPPORTED;
+  }
+  wn_handle* h = (wn_handle*)calloc(1, sizeof(wn_handle));
+  h->device = device;
+  h->sm_count = prop.multiProcessorCount;
+  Tables* t = (Tables*)malloc(sizeof(Tables));
+  build_tables_host(t);
+  cudaError_t e = cudaMalloc(&h->d_tables, sizeof(Tables));
+  if (e == cudaSuccess) e = cudaMemcpy(h->d_tables, t, sizeof(Tables), cudaMemcpyHostToDevice);
+  free(t);
+  if (e != cudaSuccess) {
+    set_error("wn_create: %s", cudaGetErrorString(e));
+    free(h);
+    return WN_E_CUDA;
+  }
+  *out = h;
+  return WN_OK;
+}
+
+void wn_destroy(wn_handle* h) {
+  if (!h) return;
+  DeviceGuard guard(h->device);
+  simt_free(h);
+  umma_free(h);
+  if (h->d_tables) cudaFree(h->d_tables);
+  if (h->timing) {
+    for (int i = 0; i < h->timing->created; i++) {
+      cudaEventDestroy(h->timing->a[i]);
+      cudaEventDestroy(h->timing->b[i]);
+    }
+    free(h->timing);
+  }
+  free(h);
+}
+
+int wn_pack_weights(wn_handle* h, const float* const* params, void* stream) {
+  if (!h || !params) {
+    set_error("wn_pack_weights: null argument");
+    return WN_E_INVALID;
+  }
+  for (int i = 0; i < WN_NUM_PARAMS; i++)
+    if (!params[i]) {
+      set_error("wn_pack_weights: params[%d] is NULL", i);
+      return WN_E_INVALID;
+    }
+  DeviceGuard guard(h->device);
+  int rc = simt_pack_weights(h, params, (cudaStream_t)stream);
+  if (rc) return rc;
+  rc = umma_pack_weights(h, params, (cudaStream_t)stream);
+  if (rc) return rc;
+  h->packed = true;
+  return WN_OK;
+}
+
+size_t wn_forward_workspace_bytes(int n, int h, int w, int mode) {
+  if (n <= 0 || h <= 0 || w <= 0) return 0;
+  switch (resolve_mode(mode)) {
+    case WN_MODE_FP32_SIMT: return simt_forward_workspace_bytes(n, h, w);
+    case WN_MODE_BF16X3: return umma_forward_workspace_bytes(n, h, w);
+  }
+  return 0;
+}
+
+int wn_forward(wn_handle* h, const float* x, const float* wb, const float* he, const float* gc,
+               const int64_t in_strides[4][4], float* out, int n, int height, int width, int mode,
+               void* workspace, size_t workspace_bytes, void* stream) {
+  if (!h || !x || !wb || !he || !gc || !in_strides || !out || !workspace) {
+    set_error("wn_forward: null argument");
+    return WN_E_INVALID;
+  }
+  if (n <= 0 || height <= 0 || width <= 0) {
+    set_error("wn_forward: bad shape n=%d h=%d w=%d", n, height, width);
+    return WN_E_INVALID;
+  }
+  if (!h->packed) {
+    set_error("wn_forward: wn_pack_weights has not been called");
+    return WN_E_STATE;
+  }
+  DeviceGuard guard(h->device);
+  const float* in[4] = {x, wb, he, gc};
+  switch (resolve_mode(mode)) {
+    case WN_MODE_FP32_SIMT:
+      return simt_forward(h, in, in_strides, out, n, height, width, workspace, workspace_bytes,
+                          (cudaStream_t)stream);
+    case WN_MODE_BF16X3:
+      return umma_forward(h, in, in_strides, out, n, height, width, workspace, workspace_bytes,
+                          (cudaStream_t)stream);
+  }
+  set_error("wn_forward: unknown mode %d", mode);
+  return WN_E_INVALID;
+}
+
+size_t wn_preprocess_workspace_bytes(int n, int h, int w) {
+  if (n <= 0 || h <= 0 || w <= 0) return 0;
+  return preprocess_workspace_bytes(n, h, w);
+}
+
+int wn_preprocess_u8(wn_handle* h, const uint8_t* rgb, int n, int height, int width, float* x,
+                     float* wb, float* he, float* gc, uint8_t* wb_u8, uint8_t* he_u8,
+                     uint8_t* gc_u8, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!h || !rgb || !workspace) {
+    set_error("wn_preprocess_u8: null argument");
+    return WN_E_INVALID;
+  }
+  if (n <= 0 || height <= 0 || width <= 0) {
+    set_error("wn_preprocess_u8: bad shape n=%d h=%d w=%d", n, height, width);
+    return WN_E_INVALID;
+  }
+  DeviceGuard guard(h->device);
+  return preprocess_u8(h, rgb, n, height, width, x, wb, he, gc, wb_u8, he_u8, gc_u8, workspace,
+                       workspace_bytes, (cudaStream_t)stream);
+}
+
+int wn_postprocess_u8(wn_handle* h, const float* out_nchw, uint8_t* out_nhwc, int n, int height,
+                      int width, void* stream) {
+  if (!h || !out_nchw || !out_nhwc || n <= 0 || height <= 0 || width <= 0) {
+    set_error("wn_postprocess_u8: bad argument");
+    return WN_E_INVALID;
+  }
+  DeviceGuard guard(h->device);
+  return postprocess_u8(h, out_nchw, out_nhwc, n, height, width, (cudaStream_t)stream);
+}
+
+static size_t align256(size_t v) { return (v + 255) / 256 * 256; }
+
+size_t wn_enhance_workspace_bytes(int n, int h, int w, int mode) {
+  if (n <= 0 || h <= 0 || w <= 0) return 0;
+  size_t tens = align256((size_t)n * 3 * h * w * sizeof(float));
+  return 5 * tens + align256(preprocess_workspace_bytes(n, h, w)) +
+         align256(wn_forward_workspace_bytes(n, h, w, mode)) + 256;
+}
+
+int wn_enhance_u8(wn_handle* h, const uint8_t* rgb, uint8_t* out_nhwc, float* out_f32_or_null,
+                  int n, int height, int width, int mode, void* workspace, size_t workspace_bytes,
+                  void* stream) {
+  if (!h || !rgb || !out_nhwc || !workspace) {
+    set_error("wn_enhance_u8: null argument");
+    return WN_E_INVALID;
+  }
+  if (workspace_bytes < wn_enhance_workspace_bytes(n, height, width, mode)) {
+    set_error("wn_enhance_u8: workspace too small");
+    return WN_E_WORKSPACE;
+  }
+  uint8_t* ws = (uint8_t*)(((uintptr_t)workspace + 255) / 256 * 256);
+  const size_t tens = align256((size_t)n * 3 * height * width * sizeof(float));
+  float* t[5];
+  for (int i = 0; i < 5; i++) {
+    t[i] = (float*)ws;
+    ws += tens;
+  }
+  void* pre_ws = ws;
+  size_t pre_b = align256(preprocess_workspace_bytes(n, height, width));
+  ws += pre_b;
+  void* fwd_ws = ws;
+  size_t fwd_b = align256(wn_forward_workspace_bytes(n, height, width, mode));
+  int rc = wn_preprocess_u8(h, rgb, n, height, width, t[0], t[1], t[2], t[3], nullptr, nullptr,
+                            nullptr, pre_ws, pre_b, stream);
+  if (rc) return rc;
+  const int64_t hw = (int64_t)height * width;
+  const int64_t st[4][4] = {{3 * hw, hw, width, 1}, {3 * hw, hw, width, 1}, {3 * hw, hw, width, 1},
+                            {3 * hw, hw, width, 1}};
+  float* outf = out_f32_or_null ? out_f32_or_null : t[4];
+  rc = wn_forward(h, t[0], t[1], t[2], t[3], st, outf, n, height, width, mode, fwd_ws, fwd_b, stream);
+  if (rc) return rc;
+  return wn_postprocess_u8(h, outf, out_nhwc, n, height, width, stream);
+}
+
+uint64_t wn_launch_count(const wn_handle* h) { return h ? h->launches : 0; }
+
+int wn_enable_timing(wn_handle* h, int on) {
+  if (!h) {
+    set_error("wn_enable_timing: null handle");
+    return WN_E_INVALID;
+  }
+  if (!h->timing) h->timing = (Timing*)calloc(1, sizeof(Timing));
+  h->timing->on = on != 0;
+  h->timing->used = 0;
+  return WN_OK;
+}
+
+int wn_read_timings(wn_handle* h, float* ms, int* count) {
+  if (!h || !ms || !count) {
+    set_error("wn_read_timings: null argument");
+    return WN_E_INVALID;
+  }
+  if (!h->timing) return WN_OK;
+  DeviceGuard guard(h->device);
+  Timing* t = h->timing;
+  for (int i = 0; i < t->used; i++) {
+    float e = 0.f;
+    WN_CUDA(cudaEventElapsedTime(&e, t->a[i], t->b[i]));
+    ms[t->slot[i]] += e;
+    count[t->slot[i]] += 1;
+  }
+  t->used = 0;
+  return WN_OK;
+}
+
+}  // extern "C"

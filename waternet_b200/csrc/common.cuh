@@ -1,0 +1,141 @@
+// Shared declarations for the waternet_b200 CUDA library (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/waternet_b200.h"
+
+namespace wn {
+
+void set_error(const char* fmt, ...);
+
+#define WN_CUDA(call)                                                                   \
+  do {                                                                                  \
+    cudaError_t err__ = (call);                                                         \
+    if (err__ != cudaSuccess) {                                                         \
+      wn::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(err__)); \
+      return WN_E_CUDA;                                                                 \
+    }                                                                                   \
+  } while (0)
+
+#define WN_LAUNCH_CHECK(h)   \
+  do {                       \
+    (h)->launches++;         \
+    WN_CUDA(cudaGetLastError()); \
+  } while (0)
+
+// ---- constant tables (OpenCV 8-bit Lab, gamma 0.7, u/255) -------------------
+struct Tables {
+  uint16_t gtab[256];    // sRGB decode, scaled 255*8
+  uint16_t ctab[3072];   // Lab f(t), scaled 1<<15
+  int16_t ytab[256];     // L -> Y, scaled 1<<14
+  int16_t fytab[256];    // L -> f(Y), scaled 1<<14
+  uint8_t igtab[4096];   // linear -> sRGB 8 bit
+  uint8_t gamma[256];    // data.py:61-65 as a LUT
+  float div255[256];     // float(u)/255.f
+};
+
+void build_tables_host(Tables* t);
+
+// ---- network description (net.py:12-42, 62-70) ------------------------------
+struct LayerDesc {
+  int cin, cout, ks;
+};
+static const LayerDesc kCmg[8] = {{12, 128, 7}, {128, 128, 5}, {128, 128, 3}, {128, 64, 1},
+                                  {64, 64, 7},  {64, 64, 5},   {64, 64, 3},   {64, 3, 3}};
+static const LayerDesc kRef[3] = {{6, 32, 7}, {32, 32, 5}, {32, 3, 3}};
+constexpr int kNumConvs = 17;  // 8 + 3*3, in state-dict order
+
+struct SimtLayer {
+  int cin, cout, cout_pad, ks;
+  float* w;     // [cin][ks*ks][cout_pad]
+  float* bias;  // [cout_pad]
+};
+
+struct UmmaWeights;  // conv_umma.cu
+
+// Optional per-kernel timing with CUDA events on the launching stream (bench.py's roofline leg).
+enum TimingSlot {
+  kSlotConv0 = 0,  // 0..16: the 17 convolutions in state-dict order (fused kernels use their first layer)
+  kSlotPack = 17,  // input concat / operand packing
+  kSlotGate = 18,  // sigmoid-gated weighted sum
+  kSlotStats = 19,
+  kSlotLuts = 20,
+  kSlotApply = 21,
+  kSlotPost = 22,
+  kNumSlots = 23
+};
+struct Timing {
+  static constexpr int kMax = 8192;
+  bool on;
+  int used, created;
+  cudaEvent_t a[kMax], b[kMax];
+  int slot[kMax];
+};
+
+}  // namespace wn
+
+struct wn_handle {
+  int device;
+  uint64_t launches;
+  wn::Tables* d_tables;
+  bool packed;
+  wn::SimtLayer simt[wn::kNumConvs];
+  wn::UmmaWeights* umma;
+  int sm_count;
+  wn::Timing* timing;
+};
+
+namespace wn {
+
+// Scope guard: records an event pair around the launches issued while it is alive.
+struct TimedScope {
+  Timing* t;
+  int idx;
+  cudaStream_t stream;
+  TimedScope(wn_handle* h, int slot, cudaStream_t s) : t(h->timing), idx(-1), stream(s) {
+    if (!t || !t->on || t->used >= Timing::kMax) return;
+    idx = t->used;
+    if (idx >= t->created) {
+      if (cudaEventCreate(&t->a[idx]) != cudaSuccess || cudaEventCreate(&t->b[idx]) != cudaSuccess) {
+        idx = -1;
+        return;
+      }
+      t->created = idx + 1;
+    }
+    t->used++;
+    t->slot[idx] = slot;
+    cudaEventRecord(t->a[idx], stream);
+  }
+  ~TimedScope() {
+    if (idx >= 0) cudaEventRecord(t->b[idx], stream);
+  }
+};
+
+// preprocess.cu
+size_t preprocess_workspace_bytes(int n, int h, int w);
+int preprocess_u8(wn_handle* h, const uint8_t* rgb, int n, int height, int width, float* x,
+                  float* wb, float* he, float* gc, uint8_t* wb_u8, uint8_t* he_u8, uint8_t* gc_u8,
+                  void* workspace, size_t workspace_bytes, cudaStream_t stream);
+int postprocess_u8(wn_handle* h, const float* out_nchw, uint8_t* out_nhwc, int n, int height,
+                   int width, cudaStream_t stream);
+
+// conv_simt.cu
+int simt_pack_weights(wn_handle* h, const float* const* params, cudaStream_t stream);
+void simt_free(wn_handle* h);
+size_t simt_forward_workspace_bytes(int n, int h, int w);
+int simt_forward(wn_handle* h, const float* const in[4], const int64_t in_strides[4][4], float* out,
+                 int n, int height, int width, void* workspace, size_t workspace_bytes,
+                 cudaStream_t stream);
+
+// conv_umma.cu
+int umma_pack_weights(wn_handle* h, const float* const* params, cudaStream_t stream);
+void umma_free(wn_handle* h);
+size_t umma_forward_workspace_bytes(int n, int h, int w);
+int umma_forward(wn_handle* h, const float* const in[4], const int64_t in_strides[4][4], float* out,
+                 int n, int height, int width, void* workspace, size_t workspace_bytes,
+                 cudaStream_t stream);
+
+}  // namespace wn

@@ -1,0 +1,489 @@
+// WaterNet preprocess on the GPU: white balance, gamma, Lab+CLAHE hist-eq, u8->fp32.
+//
+// Replaces /root/reference/waternet/data.py:6-90 (+ hubconf.py:8-21 arr2ten,
+// hubconf.py:24-34 ten2arr).  All three transforms are "global or tile histogram
+// -> small LUTs -> one per-pixel pass", so the GPU form is
+//
+//   stats_kernel   one read of the u8 image: 3x256 RGB histograms per image and
+//                  8x8 per-tile histograms of the Lab L channel (shared-memory
+//                  atomics, one global merge per CTA)
+//   luts_kernel    64 CLAHE LUTs (clip, redistribute, prefix sum) + the 3x256
+//                  white-balance LUT (float64 quantiles as numpy computes them)
+//   apply_kernel   one per-pixel pass: WB LUT, gamma LUT, RGB->Lab->CLAHE blend->
+//                  Lab->RGB in OpenCV's 8-bit fixed point, u/255, writes the four
+//                  fp32 NCHW tensors (and/or u8 NHWC images)
+//
+// HBM-bound: 3 B/px read twice, 48 B/px written (fp32 tensors) -- see DESIGN.md.
+// Bit-exact with the reference's numpy/OpenCV output (tests/test_preprocess_gpu.py).
+#include <math.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace wn {
+
+// ---------------------------------------------------------------------------
+// Host: constant tables.  Same formulas as OpenCV's initLabTabs (color_lab.cpp)
+// and data.py:61-65; checked against the oracle in tests/test_abi_cpu.py.
+// ---------------------------------------------------------------------------
+void build_tables_host(Tables* t) {
+  for (int i = 0; i < 256; i++) {
+    double u = i / 255.0;
+    double lin = u <= 0.04045 ? u / 12.92 : pow((u + 0.055) / 1.055, 2.4);
+    t->gtab[i] = (uint16_t)rint(255.0 * 8.0 * lin);
+    t->gamma[i] = (uint8_t)fmin(fmax(255.0 * pow(i / 255.0, 0.7), 0.0), 255.0);
+    t->div255[i] = (float)i / 255.0f;
+  }
+  for (int i = 0; i < 3072; i++) {
+    float x = (float)i / (255.0f * 8.0f);
+    float f = x < 0.008856f ? x * 7.787f + 0.13793103448275862f : (float)cbrt((double)x);
+    t->ctab[i] = (uint16_t)rintf(32768.0f * f);
+  }
+  // OpenCV builds this table with its own cube-root approximation, which lands one ulp below
+  // the correctly rounded value at two arguments where 32768*f sits on a .5 tie.  Entry 324 is
+  // reachable from 8-bit RGB (verified against cv2 over all 2^24 colours), 2079 is not.
+  t->ctab[324] = 17745;
+  t->ctab[2079] = 32975;
+  for (int i = 0; i < 256; i++) {
+    float li = (float)i * 100.0f / 255.0f;
+    float y, fy;
+    if (li <= 8.0f) {
+      y = li / 903.3f;
+      fy = 7.787f * y + 16.0f / 116.0f;
+    } else {
+      fy = (li + 16.0f) / 116.0f;
+      y = fy * fy * fy;
+    }
+    t->ytab[i] = (int16_t)rintf(y * 16384.0f);
+    t->fytab[i] = (int16_t)rintf(fy * 16384.0f);
+  }
+  for (int i = 0; i < 4096; i++) {
+    double x = i / 4096.0;
+    double s = x <= 0.0031308 ? 12.92 * x : 1.055 * pow(x, 1.0 / 2.4) - 0.055;
+    double v = rint(255.0 * s);
+    t->igtab[i] = (uint8_t)fmin(fmax(v, 0.0), 255.0);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Device helpers: OpenCV 8-bit fixed-point colour conversion
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ int descale(int x, int n) { return (x + (1 << (n - 1))) >> n; }
+__device__ __forceinline__ int clamp255(int v) { return min(max(v, 0), 255); }
+
+// COLOR_RGB2LAB, L only needs fY.
+__device__ __forceinline__ int lab_L(const uint16_t* gtab, const uint16_t* ctab, int r, int g,
+                                     int b) {
+  int R = gtab[r], G = gtab[g], B = gtab[b];
+  int fY = ctab[descale(R * 871 + G * 2929 + B * 296, 12)];
+  return clamp255(descale(296 * fY - 1336934, 15));
+}
+
+__device__ __forceinline__ void rgb2lab(const uint16_t* gtab, const uint16_t* ctab, int r, int g,
+                                        int b, int& L, int& A, int& Bv) {
+  int R = gtab[r], G = gtab[g], B = gtab[b];
+  int fX = ctab[descale(R * 1777 + G * 1541 + B * 778, 12)];
+  int fY = ctab[descale(R * 871 + G * 2929 + B * 296, 12)];
+  int fZ = ctab[descale(R * 73 + G * 448 + B * 3575, 12)];
+  L = clamp255(descale(296 * fY - 1336934, 15));
+  A = clamp255(descale(500 * (fX - fY) + 128 * 32768, 15));
+  Bv = clamp255(descale(200 * (fY - fZ) + 128 * 32768, 15));
+}
+
+// OpenCV's abToXZ_b table as arithmetic (C integer division truncates toward zero).
+__device__ __forceinline__ int ab_to_xz(int t) {
+  return t <= 3390 ? t * 108 / 841 - 290 : (t * t / 16384) * t / 16384;
+}
+
+__device__ __forceinline__ void lab2rgb(const int16_t* ytab, const int16_t* fytab,
+                                        const uint8_t* igtab, int L, int A, int Bv, int& r, int& g,
+                                        int& b) {
+  int y = ytab[L];
+  int ify = fytab[L];
+  int adiv = ((5 * A * 53687 + 128) >> 13) - 4194;
+  int bdiv = ((Bv * 41943 + 16) >> 9) - 10485 + 1;
+  int x = ab_to_xz(ify + adiv);
+  int z = ab_to_xz(ify - bdiv);
+  int ro = descale(12615 * x - 6296 * y - 2223 * z, 14);
+  int go = descale(-3773 * x + 7684 * y + 185 * z, 14);
+  int bo = descale(217 * x - 836 * y + 4715 * z, 14);
+  r = igtab[min(max(ro, 0), 4095)];
+  g = igtab[min(max(go, 0), 4095)];
+  b = igtab[min(max(bo, 0), 4095)];
+}
+
+// BORDER_REFLECT_101 index (cv::borderInterpolate), p >= 0.
+__device__ __forceinline__ int reflect101(int p, int len) {
+  if (len == 1) return 0;
+  while (p >= len) {
+    p = 2 * (len - 1) - p;
+    if (p < 0) p = -p;
+  }
+  return p;
+}
+
+// ---------------------------------------------------------------------------
+// Pass 1: histograms.  grid = (64 tiles, slabs, N), 256 threads.
+// ---------------------------------------------------------------------------
+constexpr int kStatsThreads = 256;
+
+__global__ void __launch_bounds__(kStatsThreads)
+stats_kernel(const uint8_t* __restrict__ rgb, int H, int W, int th, int tw, int rows_per_slab,
+             const Tables* __restrict__ tables, uint32_t* __restrict__ tile_hist,
+             uint32_t* __restrict__ rgb_hist) {
+  __shared__ uint32_t s_hist[4][256];  // 0: L of this tile, 1..3: R, G, B
+  __shared__ uint16_t s_gtab[256];
+  __shared__ uint16_t s_ctab[3072];
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 1024; i += kStatsThreads) (&s_hist[0][0])[i] = 0;
+  for (int i = tid; i < 256; i += kStatsThreads) s_gtab[i] = tables->gtab[i];
+  for (int i = tid; i < 3072; i += kStatsThreads) s_ctab[i] = tables->ctab[i];
+  __syncthreads();
+
+  const int tile = blockIdx.x, ty = tile >> 3, tx = tile & 7;
+  const int n = blockIdx.z;
+  const int r0 = blockIdx.y * rows_per_slab;
+  const int r1 = min(r0 + rows_per_slab, th);
+  const uint8_t* img = rgb + (size_t)n * H * W * 3;
+  const int count = (r1 - r0) * tw;
+  for (int i = tid; i < count; i += kStatsThreads) {
+    int rr = i / tw;
+    int cc = i - rr * tw;
+    int py = ty * th + r0 + rr, px = tx * tw + cc;  // padded-image coordinates
+    int sy = reflect101(py, H), sx = reflect101(px, W);
+    const uint8_t* p = img + ((size_t)sy * W + sx) * 3;
+    int r = p[0], g = p[1], b = p[2];
+    atomicAdd(&s_hist[0][lab_L(s_gtab, s_ctab, r, g, b)], 1u);
+    if (py < H && px < W) {  // every real pixel lies in exactly one tile
+      atomicAdd(&s_hist[1][r], 1u);
+      atomicAdd(&s_hist[2][g], 1u);
+      atomicAdd(&s_hist[3][b], 1u);
+    }
+  }
+  __syncthreads();
+  uint32_t* th_out = tile_hist + ((size_t)n * 64 + tile) * 256;
+  uint32_t* rgb_out = rgb_hist + (size_t)n * 768;
+  for (int i = tid; i < 256; i += kStatsThreads) {
+    uint32_t v = s_hist[0][i];
+    if (v) atomicAdd(&th_out[i], v);
+  }
+  for (int i = tid; i < 768; i += kStatsThreads) {
+    uint32_t v = (&s_hist[1][0])[i];
+    if (v) atomicAdd(&rgb_out[i], v);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Pass 2: LUTs.  grid = (65, N), 256 threads: blocks 0..63 CLAHE tiles, 64 = WB.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t block_inclusive_scan_256(uint32_t v, uint32_t* s_warp) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += t;
+  }
+  if (lane == 31) s_warp[warp] = v;
+  __syncthreads();
+  uint32_t add = 0;
+  for (int wi = 0; wi < warp; wi++) add += s_warp[wi];
+  __syncthreads();
+  return v + add;
+}
+
+// numpy's np.quantile(..., method="linear") on the sorted multiset described by an
+// inclusive cumulative histogram; `n` elements.  Mirrors numpy/lib/_function_base_impl.py
+// (_compute_virtual_index, _get_indexes, _lerp) operation for operation in float64.
+__device__ double np_quantile_from_cum(const uint32_t* cum, int n, double q) {
+  double vi = __dsub_rn(__dadd_rn(__dmul_rn((double)n, q), __dadd_rn(1.0, __dmul_rn(q, -1.0))), 1.0);
+  double prev_f = floor(vi);
+  long long prev = (long long)prev_f, next = prev + 1;
+  if (vi >= (double)(n - 1)) prev = next = n - 1;
+  if (vi < 0.0) prev = next = 0;
+  if (prev < 0) prev = 0;
+  if (next > n - 1) next = n - 1;
+  double gamma = __dsub_rn(vi, prev_f);
+  int a = 0, b = 0;
+  for (int u = 0; u < 256; u++) {
+    if (cum[u] > (uint32_t)prev) { a = u; break; }
+  }
+  for (int u = a; u < 256; u++) {
+    if (cum[u] > (uint32_t)next) { b = u; break; }
+  }
+  double da = (double)a, db = (double)b, diff = __dsub_rn(db, da);
+  double res = __dadd_rn(da, __dmul_rn(diff, gamma));
+  if (gamma >= 0.5) res = __dsub_rn(db, __dmul_rn(diff, __dsub_rn(1.0, gamma)));
+  return res;
+}
+
+__global__ void __launch_bounds__(256)
+luts_kernel(const uint32_t* __restrict__ tile_hist, const uint32_t* __restrict__ rgb_hist,
+            int npix, int clip, float lut_scale, uint8_t* __restrict__ clahe_lut,
+            uint8_t* __restrict__ wb_lut) {
+  __shared__ uint32_t s_warp[8];
+  __shared__ uint32_t s_cum[3][256];
+  __shared__ unsigned long long s_sum[3];
+  __shared__ uint32_t s_red;
+  const int tid = threadIdx.x, n = blockIdx.y;
+  if (blockIdx.x < 64) {
+    // OpenCV CLAHE_CalcLut_Body: clip, redistribute the excess, prefix-sum, scale.
+    const int tile = blockIdx.x;
+    int hv = (int)tile_hist[((size_t)n * 64 + tile) * 256 + tid];
+    if (tid == 0) s_red = 0;
+    __syncthreads();
+    int over = max(hv - clip, 0);
+    if (over) atomicAdd(&s_red, (uint32_t)over);
+    __syncthreads();
+    int excess = (int)s_red;
+    hv = min(hv, clip);
+    int batch = excess / 256;
+    int residual = excess - batch * 256;
+    hv += batch;
+    if (residual != 0) {
+      int step = max(256 / residual, 1);
+      if (tid % step == 0 && tid / step < residual) hv += 1;
+    }
+    uint32_t cum = block_inclusive_scan_256((uint32_t)hv, s_warp);
+    float f = rintf(__fmul_rn((float)cum, lut_scale));
+    clahe_lut[((size_t)n * 64 + tile) * 256 + tid] = (uint8_t)fminf(fmaxf(f, 0.f), 255.f);
+    return;
+  }
+  // White balance LUT: data.py:15-23 (saturation levels), :38-48 (quantiles, stretch).
+  const uint32_t* hist = rgb_hist + (size_t)n * 768;
+  if (tid < 3) s_sum[tid] = 0ull;
+  __syncthreads();
+  for (int c = 0; c < 3; c++) {
+    uint32_t hv = hist[c * 256 + tid];
+    atomicAdd(&s_sum[c], (unsigned long long)hv * (unsigned long long)tid);
+    uint32_t cum = block_inclusive_scan_256(hv, s_warp);
+    s_cum[c][tid] = cum;
+  }
+  __syncthreads();
+  __shared__ double s_q[3][2];
+  if (tid < 3) {
+    const int c = tid;
+    unsigned long long mx = max(s_sum[0], max(s_sum[1], s_sum[2]));
+    double lo = 0.0, hi = 255.0;
+    if (s_sum[c] != 0ull) {
+      double ratio = __ddiv_rn((double)mx, (double)s_sum[c]);
+      double sat = __dmul_rn(0.005, ratio);
+      double qlo = sat, qhi = __dsub_rn(1.0, sat);
+      if (qlo >= 0.0 && qlo <= 1.0 && qhi >= 0.0 && qhi <= 1.0) {
+        lo = np_quantile_from_cum(s_cum[c], npix, qlo);
+        hi = np_quantile_from_cum(s_cum[c], npix, qhi);
+      }
+    }
+    s_q[c][0] = lo;
+    s_q[c][1] = hi;
+  }
+  __syncthreads();
+  for (int c = 0; c < 3; c++) {
+    double lo = s_q[c][0], hi = s_q[c][1];
+    double v = fmin(fmax((double)tid, lo), hi);
+    double span = __dsub_rn(hi, lo);
+    double o = 0.0;
+    if (span > 0.0) o = __ddiv_rn(__dmul_rn(__dsub_rn(v, lo), 255.0), span);
+    int oi = (int)o;  // astype(uint8): truncate
+    wb_lut[(size_t)n * 768 + c * 256 + tid] = (uint8_t)min(max(oi, 0), 255);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Pass 3: per-pixel apply.  grid = (ceil(H*W/256), N), 256 threads.
+// ---------------------------------------------------------------------------
+struct ApplyOut {
+  float* f32[4];    // x, wb, he, gc  -- NCHW planes, may be null
+  uint8_t* u8[3];   // wb, he, gc     -- NHWC, may be null
+};
+
+__global__ void __launch_bounds__(256)
+apply_kernel(const uint8_t* __restrict__ rgb, int H, int W, int th, int tw,
+             const Tables* __restrict__ tables, const uint8_t* __restrict__ clahe_lut,
+             const uint8_t* __restrict__ wb_lut, ApplyOut out) {
+  __shared__ __align__(16) uint8_t s_clahe[64 * 256];
+  __shared__ __align__(16) uint8_t s_wb[768];
+  __shared__ __align__(16) uint8_t s_gamma[256];
+  __shared__ __align__(16) uint8_t s_igtab[4096];
+  __shared__ uint16_t s_gtab[256];
+  __shared__ uint16_t s_ctab[3072];
+  __shared__ int16_t s_ytab[256];
+  __shared__ int16_t s_fytab[256];
+  __shared__ float s_div[256];
+  const int tid = threadIdx.x, n = blockIdx.y;
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(clahe_lut + (size_t)n * 64 * 256);
+    uint4* dst = reinterpret_cast<uint4*>(s_clahe);
+    for (int i = tid; i < 1024; i += 256) dst[i] = src[i];
+    const uint32_t* wsrc = reinterpret_cast<const uint32_t*>(wb_lut + (size_t)n * 768);
+    for (int i = tid; i < 192; i += 256) reinterpret_cast<uint32_t*>(s_wb)[i] = wsrc[i];
+    const uint4* isrc = reinterpret_cast<const uint4*>(tables->igtab);
+    for (int i = tid; i < 256; i += 256) reinterpret_cast<uint4*>(s_igtab)[i] = isrc[i];
+    s_gamma[tid] = tables->gamma[tid];
+    s_gtab[tid] = tables->gtab[tid];
+    s_ytab[tid] = tables->ytab[tid];
+    s_fytab[tid] = tables->fytab[tid];
+    s_div[tid] = tables->div255[tid];
+    for (int i = tid; i < 3072; i += 256) s_ctab[i] = tables->ctab[i];
+  }
+  __syncthreads();
+  const int plane = H * W;
+  const int pix = blockIdx.x * 256 + tid;
+  if (pix >= plane) return;
+  const int y = pix / W, x = pix - y * W;
+  const uint8_t* p = rgb + ((size_t)n * plane + pix) * 3;
+  const int r = p[0], g = p[1], b = p[2];
+
+  // hist-eq: RGB -> Lab, CLAHE bilinear blend of the four neighbouring tile LUTs, Lab -> RGB
+  int L, A, Bv;
+  rgb2lab(s_gtab, s_ctab, r, g, b, L, A, Bv);
+  const float inv_tw = __fdiv_rn(1.0f, (float)tw), inv_th = __fdiv_rn(1.0f, (float)th);
+  float txf = __fsub_rn(__fmul_rn((float)x, inv_tw), 0.5f);
+  float tyf = __fsub_rn(__fmul_rn((float)y, inv_th), 0.5f);
+  int tx1 = (int)floorf(txf), ty1 = (int)floorf(tyf);
+  float xa = __fsub_rn(txf, (float)tx1), ya = __fsub_rn(tyf, (float)ty1);
+  float xa1 = __fsub_rn(1.0f, xa), ya1 = __fsub_rn(1.0f, ya);
+  int tx2 = min(tx1 + 1, 7), ty2 = min(ty1 + 1, 7);
+  tx1 = max(tx1, 0);
+  ty1 = max(ty1, 0);
+  float l11 = (float)s_clahe[(ty1 * 8 + tx1) * 256 + L];
+  float l12 = (float)s_clahe[(ty1 * 8 + tx2) * 256 + L];
+  float l21 = (float)s_clahe[(ty2 * 8 + tx1) * 256 + L];
+  float l22 = (float)s_clahe[(ty2 * 8 + tx2) * 256 + L];
+  float top = __fadd_rn(__fmul_rn(l11, xa1), __fmul_rn(l12, xa));
+  float bot = __fadd_rn(__fmul_rn(l21, xa1), __fmul_rn(l22, xa));
+  float res = __fadd_rn(__fmul_rn(top, ya1), __fmul_rn(bot, ya));
+  int Leq = (int)fminf(fmaxf(rintf(res), 0.f), 255.f);
+  int hr, hg, hb;
+  lab2rgb(s_ytab, s_fytab, s_igtab, Leq, A, Bv, hr, hg, hb);
+
+  const int wr = s_wb[r], wg = s_wb[256 + g], wbb = s_wb[512 + b];
+  const int gr = s_gamma[r], gg = s_gamma[g], gb = s_gamma[b];
+
+  const size_t o = (size_t)n * 3 * plane + pix;
+  if (out.f32[0]) { float* q = out.f32[0] + o; q[0] = s_div[r]; q[plane] = s_div[g]; q[2 * plane] = s_div[b]; }
+  if (out.f32[1]) { float* q = out.f32[1] + o; q[0] = s_div[wr]; q[plane] = s_div[wg]; q[2 * plane] = s_div[wbb]; }
+  if (out.f32[2]) { float* q = out.f32[2] + o; q[0] = s_div[hr]; q[plane] = s_div[hg]; q[2 * plane] = s_div[hb]; }
+  if (out.f32[3]) { float* q = out.f32[3] + o; q[0] = s_div[gr]; q[plane] = s_div[gg]; q[2 * plane] = s_div[gb]; }
+  const size_t o8 = ((size_t)n * plane + pix) * 3;
+  if (out.u8[0]) { uint8_t* q = out.u8[0] + o8; q[0] = wr; q[1] = wg; q[2] = wbb; }
+  if (out.u8[1]) { uint8_t* q = out.u8[1] + o8; q[0] = hr; q[1] = hg; q[2] = hb; }
+  if (out.u8[2]) { uint8_t* q = out.u8[2] + o8; q[0] = gr; q[1] = gg; q[2] = gb; }
+}
+
+// ---------------------------------------------------------------------------
+// ten2arr: clip(0,1) * 255 -> truncate, NCHW -> NHWC (hubconf.py:24-34)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+postprocess_kernel(const float* __restrict__ in, uint8_t* __restrict__ out, int plane) {
+  const int n = blockIdx.y;
+  const int pix = blockIdx.x * 256 + threadIdx.x;
+  if (pix >= plane) return;
+  const float* q = in + (size_t)n * 3 * plane + pix;
+  uint8_t* o = out + ((size_t)n * plane + pix) * 3;
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    float v = fminf(fmaxf(q[(size_t)c * plane], 0.0f), 1.0f);
+    o[c] = (uint8_t)(int)__fmul_rn(v, 255.0f);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Host side
+// ---------------------------------------------------------------------------
+struct PreGeom {
+  int hp, wp, th, tw, clip;
+  float lut_scale;
+};
+
+static PreGeom geometry(int H, int W) {
+  PreGeom g;
+  if (H % 8 == 0 && W % 8 == 0) {
+    g.hp = H;
+    g.wp = W;
+  } else {  // cv::copyMakeBorder(0, 8 - H%8, 0, 8 - W%8): a full 8 on an already divisible side
+    g.hp = H + (8 - H % 8);
+    g.wp = W + (8 - W % 8);
+  }
+  g.th = g.hp / 8;
+  g.tw = g.wp / 8;
+  int area = g.th * g.tw;
+  int clip = (int)(0.1 * area / 256);  // createCLAHE(clipLimit=0.1): data.py:71
+  g.clip = clip < 1 ? 1 : clip;
+  g.lut_scale = 255.0f / (float)area;
+  return g;
+}
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// workspace: [tile_hist N*64*256 u32][rgb_hist N*768 u32][clahe_lut N*64*256 u8][wb_lut N*768 u8]
+size_t preprocess_workspace_bytes(int n, int, int) {
+  size_t b = 0;
+  b += align_up((size_t)n * 64 * 256 * 4, 256);
+  b += align_up((size_t)n * 768 * 4, 256);
+  b += align_up((size_t)n * 64 * 256, 256);
+  b += align_up((size_t)n * 768, 256);
+  return b;
+}
+
+int preprocess_u8(wn_handle* h, const uint8_t* rgb, int n, int H, int W, float* x, float* wb,
+                  float* he, float* gc, uint8_t* wb_u8, uint8_t* he_u8, uint8_t* gc_u8,
+                  void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  if (workspace_bytes < preprocess_workspace_bytes(n, H, W)) {
+    set_error("preprocess workspace too small: %zu < %zu", workspace_bytes,
+              preprocess_workspace_bytes(n, H, W));
+    return WN_E_WORKSPACE;
+  }
+  if ((size_t)H * W > (size_t)0x7fffffff / 3 || n > 65535) {
+    set_error("image too large: n=%d h=%d w=%d", n, H, W);
+    return WN_E_UNSUPPORTED;
+  }
+  PreGeom g = geometry(H, W);
+  uint8_t* ws = (uint8_t*)workspace;
+  uint32_t* tile_hist = (uint32_t*)ws;
+  ws += align_up((size_t)n * 64 * 256 * 4, 256);
+  uint32_t* rgb_hist = (uint32_t*)ws;
+  ws += align_up((size_t)n * 768 * 4, 256);
+  uint8_t* clahe_lut = ws;
+  ws += align_up((size_t)n * 64 * 256, 256);
+  uint8_t* wb_lut = ws;
+
+  size_t hist_bytes = align_up((size_t)n * 64 * 256 * 4, 256) + (size_t)n * 768 * 4;
+  WN_CUDA(cudaMemsetAsync(tile_hist, 0, hist_bytes, stream));
+  // ~4K pixels per CTA keeps the grid well above 148 SMs * 2 even for one 1080p image
+  int slabs = (g.th * g.tw + 4095) / 4096;
+  if (slabs > g.th) slabs = g.th;
+  if (slabs < 1) slabs = 1;
+  int rows_per_slab = (g.th + slabs - 1) / slabs;
+  slabs = (g.th + rows_per_slab - 1) / rows_per_slab;
+  {
+  TimedScope ts(h, kSlotStats, stream);
+  stats_kernel<<<dim3(64, slabs, n), kStatsThreads, 0, stream>>>(rgb, H, W, g.th, g.tw,
+                                                                  rows_per_slab, h->d_tables,
+                                                                  tile_hist, rgb_hist);
+  WN_LAUNCH_CHECK(h);
+  }
+  {
+  TimedScope ts(h, kSlotLuts, stream);
+  luts_kernel<<<dim3(65, n), 256, 0, stream>>>(tile_hist, rgb_hist, H * W, g.clip, g.lut_scale,
+                                               clahe_lut, wb_lut);
+  WN_LAUNCH_CHECK(h);
+  }
+  ApplyOut ao;
+  ao.f32[0] = x; ao.f32[1] = wb; ao.f32[2] = he; ao.f32[3] = gc;
+  ao.u8[0] = wb_u8; ao.u8[1] = he_u8; ao.u8[2] = gc_u8;
+  TimedScope ts(h, kSlotApply, stream);
+  apply_kernel<<<dim3((H * W + 255) / 256, n), 256, 0, stream>>>(rgb, H, W, g.th, g.tw,
+                                                                 h->d_tables, clahe_lut, wb_lut, ao);
+  WN_LAUNCH_CHECK(h);
+  return WN_OK;
+}
+
+int postprocess_u8(wn_handle* h, const float* out_nchw, uint8_t* out_nhwc, int n, int H, int W,
+                   cudaStream_t stream) {
+  TimedScope ts(h, kSlotPost, stream);
+  postprocess_kernel<<<dim3((H * W + 255) / 256, n), 256, 0, stream>>>(out_nchw, out_nhwc, H * W);
+  WN_LAUNCH_CHECK(h);
+  return WN_OK;
+}
+
+}  // namespace wn

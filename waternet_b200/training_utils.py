@@ -1,0 +1,127 @@
+"""Dataset glue of the reference (``waternet/training_utils.py``) on the B200 preprocess.
+
+``arr2ten`` / ``ten2arr`` keep the reference's layout-and-scale contract
+(``training_utils.py:11-43``: no batch dimension is added to a 3-D array here,
+unlike the hubconf variants).  ``UIEBDataset`` keeps the reference's constructor
+and item dictionary (``training_utils.py:46-132``); file decoding and resizing
+stay with OpenCV (disk-bound glue, out of scope for kernels) while the WB/GC/HE
+transform of every item runs on the GPU.  ``SyntheticUIEB`` is the offline
+stand-in used by ``train.py --synthetic`` (no UIEB images without network).
+"""
+from __future__ import annotations
+
+import os
+from pathlib import Path
+from typing import Optional
+
+import numpy as np
+import torch
+
+from .data import transform as preprocess_transform
+
+
+def arr2ten(arr) -> torch.Tensor:
+    """uint8 (N)HWC array -> fp32 (N)CHW tensor scaled to [0,1] (true division by 255)."""
+    ten = torch.from_numpy(np.ascontiguousarray(arr)) / 255
+    if ten.dim() == 3:
+        return ten.permute(2, 0, 1)
+    if ten.dim() == 4:
+        return ten.permute(0, 3, 1, 2)
+    return ten
+
+
+def ten2arr(ten: torch.Tensor) -> np.ndarray:
+    """fp32 (N)CHW tensor -> uint8 (N)HWC array: clip to [0,1], scale by 255, truncate."""
+    arr = np.clip(ten.detach().cpu().numpy(), 0, 1)
+    arr = (arr * 255).astype(np.uint8)
+    if arr.ndim == 3:
+        return np.transpose(arr, (1, 2, 0))
+    if arr.ndim == 4:
+        return np.transpose(arr, (0, 2, 3, 1))
+    return arr
+
+
+class FlipRotate:
+    """HorizontalFlip / VerticalFlip / RandomRotate90, each with p=0.5 (training_utils.py:72-78).
+
+    Same call convention as an albumentations Compose: ``t(image=a, mask=b)`` ->
+    ``{"image": a', "mask": b'}``; seeded so that runs are reproducible.
+    """
+
+    def __init__(self, seed: Optional[int] = None):
+        self.rng = np.random.default_rng(seed)
+
+    def __call__(self, image, mask):
+        if self.rng.random() < 0.5:
+            image, mask = image[:, ::-1], mask[:, ::-1]
+        if self.rng.random() < 0.5:
+            image, mask = image[::-1], mask[::-1]
+        if self.rng.random() < 0.5:
+            k = int(self.rng.integers(0, 4))
+            image, mask = np.rot90(image, k), np.rot90(mask, k)
+        return {"image": np.ascontiguousarray(image), "mask": np.ascontiguousarray(mask)}
+
+
+def _item(raw_im: np.ndarray, ref_im: np.ndarray):
+    wb, gc, he = preprocess_transform(raw_im)
+    return {"raw": arr2ten(raw_im), "wb": arr2ten(wb), "gc": arr2ten(gc), "he": arr2ten(he), "ref": arr2ten(ref_im)}
+
+
+class UIEBDataset(torch.utils.data.Dataset):
+    """Paired raw/reference PNG folders (same file names in both)."""
+
+    def __init__(self, raw_dir, ref_dir, im_height: Optional[int] = None, im_width: Optional[int] = None,
+                 transform=None):
+        raw_names = sorted(p.name for p in Path(raw_dir).glob("*.png"))
+        ref_names = sorted(p.name for p in Path(ref_dir).glob("*.png"))
+        assert set(raw_names) == set(ref_names)
+        self.transform = transform if transform is not None else FlipRotate()
+        self.raw_dir, self.ref_dir = Path(raw_dir), Path(ref_dir)
+        self.im_fns = raw_names
+        self.im_height, self.im_width = im_height, im_width
+
+    def __len__(self):
+        return len(self.im_fns)
+
+    def __getitem__(self, idx):
+        import cv2  # file decode / resize only
+        raw_im = cv2.imread(os.fspath(self.raw_dir / self.im_fns[idx]))
+        ref_im = cv2.imread(os.fspath(self.ref_dir / self.im_fns[idx]))
+        if self.im_width is not None and self.im_height is not None:
+            size = (self.im_width, self.im_height)
+        else:  # multiple of 32 for VGG; the reference swaps the axis names here (training_utils.py:100-103)
+            size = (int(raw_im.shape[0] / 32) * 32, int(raw_im.shape[1] / 32) * 32)
+        raw_im = cv2.cvtColor(cv2.resize(raw_im, size), cv2.COLOR_BGR2RGB)
+        ref_im = cv2.cvtColor(cv2.resize(ref_im, size), cv2.COLOR_BGR2RGB)
+        if self.transform is not None:
+            t = self.transform(image=raw_im, mask=ref_im)
+            raw_im, ref_im = t["image"], t["mask"]
+        return _item(raw_im, ref_im)
+
+
+class SyntheticUIEB(torch.utils.data.Dataset):
+    """UIEB-shaped synthetic pairs: a smooth scene (reference) and a blue-green degraded copy (raw)."""
+
+    def __init__(self, length: int = 890, im_height: int = 112, im_width: int = 112, seed: int = 0, transform=None):
+        self.length, self.h, self.w, self.seed = length, im_height, im_width, seed
+        self.transform = transform
+
+    def __len__(self):
+        return self.length
+
+    def _scene(self, idx):
+        rng = np.random.default_rng(self.seed * 100003 + idx)
+        coarse = rng.random((self.h // 8 + 2, self.w // 8 + 2, 3))
+        ref = np.kron(coarse, np.ones((8, 8, 1)))[: self.h, : self.w]
+        ref = (ref * 255).astype(np.uint8)
+        cast = np.array([0.35, 0.8, 0.9])
+        raw = (ref.astype(np.float64) * cast * (0.6 + 0.4 * rng.random())).astype(np.uint8)
+        raw = np.maximum(raw, 1)
+        return raw, ref
+
+    def __getitem__(self, idx):
+        raw_im, ref_im = self._scene(idx)
+        if self.transform is not None:
+            t = self.transform(image=raw_im, mask=ref_im)
+            raw_im, ref_im = t["image"], t["mask"]
+        return _item(raw_im, ref_im)

@@ -258,17 +258,25 @@ def main():
         peaks = load_peaks()
         px_per_launch_denominator = None
         conv_ms = slot_ms[:17]
+        macs_by_slot = list(CONV_MACS)
+        names_by_slot = list(CONV_NAMES)
+        if mode != _lib.MODE_FP32_SIMT:
+            # tensor-core path: ten launches.  slot 0 = cmg.conv1 + the three refiner conv1 (one 16->224 GEMM),
+            # slot 9 = the three refiner conv2 (block-diagonal 96->96), slot 10 = the three conv3 + gated sum
+            macs_by_slot = CONV_MACS[:8] + [0] * 9
+            macs_by_slot[0] += 3 * 9408
+            macs_by_slot[9] = 3 * 25600
+            macs_by_slot[10] = 3 * 864
+            names_by_slot[0] = "cmg.conv1+refiner.conv1x3"
+            names_by_slot[9] = "refiner.conv2x3"
+            names_by_slot[10] = "refiner.conv3x3+gate"
         top = int(np.argmax(conv_ms))
         n_launch = max(slot_cnt[top], 1)
         avg_ms = conv_ms[top] / n_launch
         # how many images one bracketed launch group covers: steps*B images / count
         imgs_per_launch = args.steps * B / n_launch
-        macs = CONV_MACS[top]
-        fused = [CONV_NAMES[top]]
-        if mode != _lib.MODE_FP32_SIMT and top == 0:
-            # the tensor-core path runs cmg.conv1 and the three refiner conv1 as one kernel
-            macs += 3 * 9408
-            fused += ["wb_refiner.conv1", "ce_refiner.conv1", "gc_refiner.conv1"]
+        macs = macs_by_slot[top]
+        fused = [names_by_slot[top]]
         flops = 2.0 * macs * H * W * imgs_per_launch
         achieved = flops / (avg_ms * 1e-3) / 1e12
         peak = peaks["tf_sustained"]
@@ -304,7 +312,9 @@ def main():
             "gpu_launches": int(launches),
             "roofline": roofline,
             "kernel_ms_per_step": {name: round(slot_ms[i] / args.steps, 4) for i, name in enumerate(
-                CONV_NAMES + ["pack", "gate", "pre_stats", "pre_luts", "pre_apply", "post"]) if slot_cnt[i]},
+                names_by_slot + ["pack", "gate", "pre_stats", "pre_luts", "pre_apply", "post"]) if slot_cnt[i]},
+            "kernel_tflops": {name: round(2.0 * macs_by_slot[i] * H * W * B * args.steps / (slot_ms[i] * 1e-3) / 1e12, 1)
+                              for i, name in enumerate(names_by_slot) if slot_cnt[i] and slot_ms[i] > 0},
         }
         if world == 1 and not args.no_cpu_baseline:
             from oracle import forward as ofw

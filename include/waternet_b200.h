@@ -117,6 +117,17 @@ int wn_enhance_u8(wn_handle* h, const uint8_t* rgb, uint8_t* out_nhwc, float* ou
 int wn_enable_timing(wn_handle* h, int on);
 int wn_read_timings(wn_handle* h, float* ms, int* count);
 
+/*
+ * Test aid: run wn_forward's layer chain in `mode` up to an intermediate activation and return it
+ * as contiguous fp32 NCHW.  layer: 0..6 = output of cmg.conv1..conv7 (after ReLU), 7 = the three
+ * sigmoid confidence maps, 8 = the three refiners' conv1 outputs concatenated (96 channels),
+ * 9 = their conv2 outputs (96 channels).  dst must hold n*C*h*w floats.  Workspace as wn_forward.
+ */
+int wn_debug_forward_layer(wn_handle* h, const float* x, const float* wb, const float* he,
+                           const float* gc, const int64_t in_strides[4][4], int n, int height,
+                           int width, int mode, int layer, float* dst, void* workspace,
+                           size_t workspace_bytes, void* stream);
+
 /* Number of kernels the library has launched on this handle since creation. */
 uint64_t wn_launch_count(const wn_handle* h);
 

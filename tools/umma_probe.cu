@@ -92,6 +92,7 @@ struct MmaArgs {
   uint32_t b_off, b_lbo, b_sbo, b_kstep;
   int reps;                      // >1: timing mode, repeat the K loop
   int b_region_off;              // where the B image starts in smem (>= a_bytes, 128B aligned)
+  int nacc;                      // timing mode: rotate over this many accumulators
 };
 
 // One CTA, 128 threads.  smem images are copied verbatim from global.
@@ -114,7 +115,7 @@ __global__ void __launch_bounds__(128) mma_probe_kernel(const uint8_t* a_img, co
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                      smem_u32(&tmem_base_s)),
-                 "r"(256u)
+                 "r"(512u)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -130,8 +131,9 @@ __global__ void __launch_bounds__(128) mma_probe_kernel(const uint8_t* a_img, co
     t0 = clock64();
     for (int r = 0; r < g.reps; r++)
       for (int k = 0; k < g.ksteps; k++)
-        umma_bf16(tmem_base, make_desc(a_base + k * g.a_kstep, g.a_lbo, g.a_sbo),
-                  make_desc(b_base + k * g.b_kstep, g.b_lbo, g.b_sbo), idesc, (r | k) != 0);
+        umma_bf16(tmem_base + (uint32_t)(((r * g.ksteps + k) % g.nacc) * g.N),
+                  make_desc(a_base + k * g.a_kstep, g.a_lbo, g.a_sbo),
+                  make_desc(b_base + k * g.b_kstep, g.b_lbo, g.b_sbo), idesc, (r * g.ksteps + k) >= g.nacc);
     umma_commit(&bar);
   }
   __syncwarp();
@@ -154,7 +156,7 @@ __global__ void __launch_bounds__(128) mma_probe_kernel(const uint8_t* a_img, co
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 0)
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u)
                  : "memory");
 }
 
@@ -183,7 +185,7 @@ static void put(std::vector<uint8_t>& img, uint32_t off, uint32_t lbo, uint32_t 
 }
 
 static int run_mma(const char* name, int N, int K, uint32_t a_off, uint32_t a_lbo, uint32_t a_sbo,
-                   uint32_t b_lbo, uint32_t b_sbo, bool swap_fields, int reps) {
+                   uint32_t b_lbo, uint32_t b_sbo, bool swap_fields, int reps, int nacc = 1) {
   const int M = 128;
   std::vector<float> A((size_t)M * K), B((size_t)N * K);
   srand(1234);
@@ -223,6 +225,7 @@ static int run_mma(const char* name, int N, int K, uint32_t a_off, uint32_t a_lb
   g.b_off = 0;
   g.b_region_off = a_bytes;
   g.reps = reps;
+  g.nacc = nacc;
   if (!swap_fields) {
     g.a_lbo = a_lbo; g.a_sbo = a_sbo; g.b_lbo = b_lbo; g.b_sbo = b_sbo;
   } else {
@@ -259,10 +262,12 @@ static int run_mma(const char* name, int N, int K, uint32_t a_off, uint32_t a_lb
       double ref = 0;
       for (int k = 0; k < K; k++) ref += (double)A[(size_t)r * K + k] * B[(size_t)c * K + k];
       ref *= reps;
+      if (nacc > 1) continue;  // rotating accumulators: timing only
       double err = fabs(ref - D[(size_t)r * N + c]);
       if (err > maxerr) maxerr = err;
       if (err > 1e-2 * reps) bad++;
     }
+  if (nacc > 1) printf("[nacc=%d] ", nacc);
   printf("%s: N=%d K=%d a_off=%u a_lbo=%u a_sbo=%u b_lbo=%u b_sbo=%u swap=%d reps=%d -> %s maxerr=%.3g bad=%d "
          "cycles=%lld (%.1f per MMA)\n",
          name, N, K, a_off, a_lbo, a_sbo, b_lbo, b_sbo, (int)swap_fields, reps, bad ? "FAIL" : "PASS",
@@ -388,6 +393,10 @@ int main(int argc, char** argv) {
   if (!strcmp(t, "n16")) return run_mma(t, 16, 64, 0, 128 * 16, 128, 16 * 16, 128, false, 1);
   if (!strcmp(t, "n256")) return run_mma(t, 256, 32, 0, 128 * 16, 128, 256 * 16, 128, false, 1);
   if (!strcmp(t, "tma")) return run_tma();
+  if (!strcmp(t, "rate2") && argc >= 5) {
+    int N = atoi(argv[2]), reps = atoi(argv[3]), nacc = atoi(argv[4]);
+    return run_mma("rate2", N, 64, (3 * 20 + 2) * 16, 560 * 16, 20 * 16, N * 16, 128, false, reps, nacc);
+  }
   if (!strcmp(t, "rate") && argc >= 4) {
     int N = atoi(argv[2]), reps = atoi(argv[3]);
     int conv = argc >= 5 ? atoi(argv[4]) : 0;

@@ -249,6 +249,27 @@ int wn_enhance_u8(wn_handle* h, const uint8_t* rgb, uint8_t* out_nhwc, float* ou
 
 uint64_t wn_launch_count(const wn_handle* h) { return h ? h->launches : 0; }
 
+int wn_debug_forward_layer(wn_handle* h, const float* x, const float* wb, const float* he,
+                           const float* gc, const int64_t in_strides[4][4], int n, int height,
+                           int width, int mode, int layer, float* dst, void* workspace,
+                           size_t workspace_bytes, void* stream) {
+  if (!h || !x || !wb || !he || !gc || !in_strides || !dst || !workspace || layer < 0 || layer > 9) {
+    set_error("wn_debug_forward_layer: bad argument");
+    return WN_E_INVALID;
+  }
+  if (!h->packed) {
+    set_error("wn_debug_forward_layer: wn_pack_weights has not been called");
+    return WN_E_STATE;
+  }
+  DeviceGuard guard(h->device);
+  const float* in[4] = {x, wb, he, gc};
+  if (resolve_mode(mode) == WN_MODE_FP32_SIMT)
+    return simt_debug_layer(h, in, in_strides, n, height, width, layer, dst, workspace, workspace_bytes,
+                            (cudaStream_t)stream);
+  return umma_debug_layer(h, in, in_strides, n, height, width, layer, dst, workspace, workspace_bytes,
+                          (cudaStream_t)stream);
+}
+
 int wn_enable_timing(wn_handle* h, int on) {
   if (!h) {
     set_error("wn_enable_timing: null handle");

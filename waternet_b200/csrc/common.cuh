@@ -130,7 +130,14 @@ int simt_forward(wn_handle* h, const float* const in[4], const int64_t in_stride
                  int n, int height, int width, void* workspace, size_t workspace_bytes,
                  cudaStream_t stream);
 
+int simt_debug_layer(wn_handle* h, const float* const in[4], const int64_t in_strides[4][4], int n,
+                     int height, int width, int layer, float* dst, void* workspace,
+                     size_t workspace_bytes, cudaStream_t stream);
+
 // conv_umma.cu
+int umma_debug_layer(wn_handle* h, const float* const in[4], const int64_t in_strides[4][4], int n,
+                     int height, int width, int layer, float* dst, void* workspace,
+                     size_t workspace_bytes, cudaStream_t stream);
 int umma_pack_weights(wn_handle* h, const float* const* params, cudaStream_t stream);
 void umma_free(wn_handle* h);
 size_t umma_forward_workspace_bytes(int n, int h, int w);

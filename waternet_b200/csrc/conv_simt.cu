@@ -261,7 +261,8 @@ __global__ void pair_kernel(const float* __restrict__ cat12, float* __restrict__
 
 static int simt_forward_chunk(wn_handle* h, const float* const in[4],
                               const int64_t in_strides[4][4], float* out, int n, int H, int W,
-                              void* workspace, cudaStream_t stream);
+                              void* workspace, cudaStream_t stream, int dbg_layer = -1,
+                              float* dbg_dst = nullptr);
 
 int simt_forward(wn_handle* h, const float* const in[4], const int64_t in_strides[4][4], float* out,
                  int n, int H, int W, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
@@ -282,9 +283,19 @@ int simt_forward(wn_handle* h, const float* const in[4], const int64_t in_stride
   return WN_OK;
 }
 
+int simt_debug_layer(wn_handle* h, const float* const in[4], const int64_t in_strides[4][4], int n,
+                     int H, int W, int layer, float* dst, void* workspace, size_t workspace_bytes,
+                     cudaStream_t stream) {
+  if (simt_chunk(n, H, W) != n || workspace_bytes < simt_forward_workspace_bytes(n, H, W)) {
+    set_error("debug layer dump: batch too large for one pass or workspace too small");
+    return WN_E_WORKSPACE;
+  }
+  return simt_forward_chunk(h, in, in_strides, nullptr, n, H, W, workspace, stream, layer, dst);
+}
+
 static int simt_forward_chunk(wn_handle* h, const float* const in[4],
                               const int64_t in_strides[4][4], float* out, int n, int H, int W,
-                              void* workspace, cudaStream_t stream) {
+                              void* workspace, cudaStream_t stream, int dbg_layer, float* dbg_dst) {
   const size_t px = (size_t)n * H * W;
   const int plane = H * W;
   float* ws = (float*)(((uintptr_t)workspace + 255) / 256 * 256);
@@ -318,6 +329,10 @@ static int simt_forward_chunk(wn_handle* h, const float* const in[4],
     float* dst = i == 7 ? cm : pp[i & 1];
     if ((rc = run_conv(h, i, cur, dst, n, H, W, i == 7 ? 2 : 1, stream))) return rc;
     cur = dst;
+    if (dbg_layer == i) {
+      WN_CUDA(cudaMemcpyAsync(dbg_dst, dst, px * h->simt[i].cout * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+      return WN_OK;
+    }
   }
   // refiners: net.py:76-80, inputs cat[x, wb], cat[x, ce], cat[x, gc]
   for (int r = 0; r < 3; r++) {
@@ -329,8 +344,16 @@ static int simt_forward_chunk(wn_handle* h, const float* const in[4],
     float* refr = refined + (size_t)r * px * 3;
     if ((rc = run_conv(h, 8 + 3 * r + 0, pair, r32a, n, H, W, 1, stream))) return rc;
     if ((rc = run_conv(h, 8 + 3 * r + 1, r32a, r32b, n, H, W, 1, stream))) return rc;
+    if (dbg_layer == 8 || dbg_layer == 9) {  // (N,32,H,W) -> channels 32r.. of (N,96,H,W)
+      const float* src = dbg_layer == 8 ? r32a : r32b;
+      WN_CUDA(cudaMemcpy2DAsync(dbg_dst + (size_t)r * 32 * plane, (size_t)96 * plane * sizeof(float), src,
+                                (size_t)32 * plane * sizeof(float), (size_t)32 * plane * sizeof(float), n,
+                                cudaMemcpyDeviceToDevice, stream));
+      continue;
+    }
     if ((rc = run_conv(h, 8 + 3 * r + 2, r32b, refr, n, H, W, 1, stream))) return rc;
   }
+  if (dbg_layer >= 0) return WN_OK;
   TimedScope ts(h, kSlotGate, stream);
   gate_sum_kernel<<<dim3((plane + 255) / 256, n), 256, 0, stream>>>(
       cm, refined, refined + px * 3, refined + 2 * px * 3, out, plane);

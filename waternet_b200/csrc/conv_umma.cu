@@ -1,11 +1,730 @@
-// placeholder until the tcgen05 path lands
+// Tensor-core path of WaterNet.forward (WN_MODE_BF16X3): tcgen05 implicit-GEMM convolutions.
+//
+// Replaces /root/reference/waternet/net.py:45-56, :75-80, :99-108.  Every
+// convolution is a dense contraction, so it runs on the 5th-gen
+// tensor cores -- but the 1e-3 parity bar rules out single-pass bf16/tf32 operands
+// (SURVEY.md section 0).  Each fp32 operand is split into bf16 hi + lo and three
+// MMAs (hi*hi + lo*hi + hi*lo) accumulate in fp32 in TMEM ("bf16x3", ~2^-16
+// relative operand error).
+//
+// Data layout in HBM: activations are bf16 planes of 8 channels,
+//     act[n][plane][y][x][8]   planes [0, C/8) = hi parts, [C/8, 2C/8) = lo parts,
+// so that ONE 5-D TMA box (8 ch, x, y, planes, n) drops a halo tile into shared
+// memory as [plane][y][x][16 B] -- exactly the no-swizzle K-major UMMA operand
+// layout with "8 consecutive pixels of a row" as the 8x16B core matrix.  A filter
+// tap (ky,kx) is then just a different descriptor start address into the SAME halo
+// tile: the activations are read from L2/HBM once per tile, not once per tap, and
+// out-of-image pixels come back as zeros from the TMA (padding="same").
+//
+// One persistent CTA per SM, warp-specialised:
+//   warps 0-3  epilogue  (TMEM -> registers -> bias/act -> bf16 hi/lo planes or fp32)
+//   warp 4     A producer (TMA halo tiles, one 16-channel chunk per stage)
+//   warp 5     B producer (bulk copies of pre-packed weight stages, one (chunk,tap) per stage)
+//   warp 6     MMA issuer (one thread; 3 MMAs per sub-tile per stage)
+//   warp 7     TMEM allocator
+// A CTA tile is S sub-tiles of 8x16 pixels (M = 128 each) sharing every weight stage.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
 #include "common.cuh"
+
 namespace wn {
-int umma_pack_weights(wn_handle*, const float* const*, cudaStream_t) { return WN_OK; }
-void umma_free(wn_handle*) {}
-size_t umma_forward_workspace_bytes(int n, int h, int w) { return simt_forward_workspace_bytes(n, h, w); }
-int umma_forward(wn_handle* h, const float* const in[4], const int64_t in_strides[4][4], float* out,
-                 int n, int height, int width, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
-  return simt_forward(h, in, in_strides, out, n, height, width, workspace, workspace_bytes, stream);
+
+// ------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
 }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+// Bounded wait: a pipeline bug becomes a trap ("unspecified launch failure"), never a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  for (uint32_t it = 0; it < (1u << 26); it++) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (done) return;
+  }
+  __trap();
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* tmap, uint64_t* bar, int c0,
+                                            int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+// shared-memory matrix descriptor: no swizzle, K-major.  LBO = byte distance between the two
+// 8-element K halves of a K=16 step, SBO = byte distance between 8-row groups.
+__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr >> 4) & 0x3fff);
+  d |= (uint64_t)((lbo >> 4) & 0x3fff) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3fff) << 32;
+  d |= 1ull << 46;
+  return d;
+}
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+  // c=f32 (bit 4), a=b=bf16 (bits 7, 10), K-major both, N>>3 at 17, M>>4 at 24
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
+        "=r"(v[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+
+// ------------------------------------------------------------------------------------------
+// Kernel configuration
+// ------------------------------------------------------------------------------------------
+enum Epilogue { kEpiAct = 0, kEpiSigmoid = 1, kEpiGate = 2 };
+
+constexpr int kSubW = 8, kSubH = 16;  // one M=128 sub-tile: 8 px wide, 16 px tall
+constexpr int kThreads = 256;
+
+template <int KS, int CIN_PAD, int NPAD, int S, int AS>
+struct UmmaCfg {
+  static constexpr int TILE_W = kSubW * S, TILE_H = kSubH;
+  static constexpr int HALO_W = TILE_W + KS - 1, HALO_H = TILE_H + KS - 1;
+  static constexpr int NCHUNK = CIN_PAD / 16;
+  static constexpr int PLANE_BYTES = HALO_W * HALO_H * 16;
+  static constexpr int A_STAGE = (4 * PLANE_BYTES + 1023) / 1024 * 1024;  // hi k0, hi k1, lo k0, lo k1
+  static constexpr int B_STAGE = NPAD * 64;                                // [hi|lo][k8 0|1][NPAD][16 B]
+  static constexpr int NB = NPAD > 128 ? 4 : 6;
+  static constexpr int BUDGET = 225 * 1024 - 2048;
+  static constexpr int NA_FIT = (BUDGET - NB * B_STAGE) / A_STAGE;
+  static constexpr int NA = NA_FIT > 3 ? 3 : NA_FIT;
+  static constexpr int TMEM_COLS_USED = AS * S * NPAD;
+  static constexpr int TMEM_COLS = TMEM_COLS_USED <= 32 ? 32 : TMEM_COLS_USED <= 64 ? 64
+                                   : TMEM_COLS_USED <= 128 ? 128 : TMEM_COLS_USED <= 256 ? 256 : 512;
+  static constexpr int SMEM_BYTES = NA * A_STAGE + NB * B_STAGE + 2048 + 1024;  // + barriers/bias + align slack
+  static_assert(NA >= 1, "halo tile does not fit in shared memory");
+  static_assert(TMEM_COLS_USED <= 512, "accumulators do not fit in TMEM");
+  static_assert(NPAD % 16 == 0 && NPAD >= 16 && NPAD <= 256, "invalid UMMA N");
+};
+
+struct ActDst {
+  uint4* base;   // [n][2*planes_half][H][W] of 16-byte (8 x bf16) units
+  int planes_half;
+};
+
+struct ConvArgs {
+  const uint8_t* wpk;   // packed weight stages
+  const float* bias;    // [NPAD]
+  int N, H, W;
+  int in_planes_half;   // C_in_pad / 8
+  int tiles_x, tiles_y;
+  // kEpiAct
+  ActDst dst0, dst1;
+  int split_c;          // channels [0, split_c) -> dst0, [split_c, cout) -> dst1
+  int cout;             // valid output channels
+  // kEpiSigmoid / kEpiGate
+  float* out_f32;       // [n][3][H][W]
+  const float* cm;      // [n][3][H][W] (gate)
+};
+
+__device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b) {
+  return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+}
+
+template <int KS, int CIN_PAD, int NPAD, int S, int AS, int EPI>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) {
+  using C = UmmaCfg<KS, CIN_PAD, NPAD, S, AS>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* a_stages = smem;
+  uint8_t* b_stages = smem + C::NA * C::A_STAGE;
+  uint8_t* tail = b_stages + C::NB * C::B_STAGE;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(tail);
+  uint64_t* a_empty = a_full + C::NA;
+  uint64_t* b_full = a_empty + C::NA;
+  uint64_t* b_empty = b_full + C::NB;
+  uint64_t* t_full = b_empty + C::NB;
+  uint64_t* t_empty = t_full + AS;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + AS);
+  float* s_bias = reinterpret_cast<float*>(tail + 512);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int num_tiles = g.tiles_x * g.tiles_y * g.N;
+
+  if (tid == 0) {
+    for (int i = 0; i < C::NA; i++) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < C::NB; i++) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < AS; i++) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = tid; i < NPAD; i += kThreads) s_bias[i] = g.bias[i];
+  if (warp == 7) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)C::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4) {
+    // ===================== A producer: halo tiles by TMA =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int n = tile / (g.tiles_x * g.tiles_y);
+        const int rem = tile - n * g.tiles_x * g.tiles_y;
+        const int ty = rem / g.tiles_x, tx = rem - ty * g.tiles_x;
+        const int x0 = tx * C::TILE_W - KS / 2, y0 = ty * C::TILE_H - KS / 2;
+        for (int c = 0; c < C::NCHUNK; c++) {
+          mbar_wait(&a_empty[stage], phase ^ 1);
+          uint8_t* dst = a_stages + stage * C::A_STAGE;
+          mbar_expect_tx(&a_full[stage], 4 * C::PLANE_BYTES);
+          tma_load_5d(dst, &tmap_in, &a_full[stage], 0, x0, y0, 2 * c, n);
+          tma_load_5d(dst + 2 * C::PLANE_BYTES, &tmap_in, &a_full[stage], 0, x0, y0,
+                      g.in_planes_half + 2 * c, n);
+          if (++stage == C::NA) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ===================== B producer: packed weight stages =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int it = 0; it < C::NCHUNK * KS * KS; it++) {
+          mbar_wait(&b_empty[stage], phase ^ 1);
+          mbar_expect_tx(&b_full[stage], C::B_STAGE);
+          bulk_load(b_stages + stage * C::B_STAGE, g.wpk + (size_t)it * C::B_STAGE, C::B_STAGE, &b_full[stage]);
+          if (++stage == C::NB) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 6) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(128, NPAD);
+      int astage = 0, bstage = 0, acc = 0;
+      uint32_t aphase = 0, bphase = 0, tphase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&t_empty[acc], tphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_base = tmem_base + (uint32_t)(acc * S * NPAD);
+        for (int c = 0; c < C::NCHUNK; c++) {
+          mbar_wait(&a_full[astage], aphase);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(a_stages + astage * C::A_STAGE);
+          for (int tap = 0; tap < KS * KS; tap++) {
+            mbar_wait(&b_full[bstage], bphase);
+            tc_fence_after();
+            const int ky = tap / KS, kx = tap - ky * KS;
+            const uint32_t b_base = smem_u32(b_stages + bstage * C::B_STAGE);
+            const uint64_t b_hi = make_desc(b_base, NPAD * 16, 128);
+            const uint64_t b_lo = make_desc(b_base + 2 * NPAD * 16, NPAD * 16, 128);
+            const uint32_t first = (c | tap) == 0 ? 0u : 1u;
+            // split-major order: consecutive MMAs target different accumulators
+#pragma unroll
+            for (int sp = 0; sp < 3; sp++) {
+#pragma unroll
+              for (int s = 0; s < S; s++) {
+                const uint32_t a_off = (uint32_t)((ky * C::HALO_W + kx + s * kSubW) * 16) +
+                                       (sp == 1 ? 2u * C::PLANE_BYTES : 0u);
+                const uint64_t a_d = make_desc(a_base + a_off, C::PLANE_BYTES, C::HALO_W * 16);
+                umma_bf16(d_base + (uint32_t)(s * NPAD), a_d, sp == 2 ? b_lo : b_hi, idesc, sp == 0 ? first : 1u);
+              }
+            }
+            umma_commit(&b_empty[bstage]);
+            if (++bstage == C::NB) { bstage = 0; bphase ^= 1; }
+          }
+          umma_commit(&a_empty[astage]);
+          if (++astage == C::NA) { astage = 0; aphase ^= 1; }
+        }
+        umma_commit(&t_full[acc]);
+        if (++acc == AS) { acc = 0; tphase ^= 1; }
+      }
+    }
+  } else if (warp < 4) {
+    // ===================== epilogue =====================
+    int acc = 0;
+    uint32_t tphase = 0;
+    const int px = tid & 7, py = tid >> 3;  // this thread's pixel inside a sub-tile (TMEM lane == tid)
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int n = tile / (g.tiles_x * g.tiles_y);
+      const int rem = tile - n * g.tiles_x * g.tiles_y;
+      const int ty = rem / g.tiles_x, tx = rem - ty * g.tiles_x;
+      mbar_wait(&t_full[acc], tphase);
+      tc_fence_after();
+      const int gy = ty * C::TILE_H + py;
+#pragma unroll 1
+      for (int s = 0; s < S; s++) {
+        const int gx = tx * C::TILE_W + s * kSubW + px;
+        const bool inside = gx < g.W && gy < g.H;
+        const uint32_t t_addr = tmem_base + lane_base + (uint32_t)(acc * S * NPAD + s * NPAD);
+        if constexpr (EPI == kEpiAct) {
+#pragma unroll 1
+          for (int c0 = 0; c0 < NPAD; c0 += 16) {
+            uint32_t v[16];
+            tmem_ld16(t_addr + c0, v);
+            if (c0 < g.cout && inside) {
+              uint32_t hi[8], lo[8];
+#pragma unroll
+              for (int j = 0; j < 16; j += 2) {
+                float f0 = fmaxf(__uint_as_float(v[j]) + s_bias[c0 + j], 0.f);
+                float f1 = fmaxf(__uint_as_float(v[j + 1]) + s_bias[c0 + j + 1], 0.f);
+                __nv_bfloat16 h0 = __float2bfloat16_rn(f0), h1 = __float2bfloat16_rn(f1);
+                __nv_bfloat16 l0 = __float2bfloat16_rn(f0 - __bfloat162float(h0));
+                __nv_bfloat16 l1 = __float2bfloat16_rn(f1 - __bfloat162float(h1));
+                hi[j >> 1] = pack_bf16x2(h0, h1);
+                lo[j >> 1] = pack_bf16x2(l0, l1);
+              }
+              const bool second = c0 >= g.split_c;
+              const ActDst& d = second ? g.dst1 : g.dst0;
+              const int plane = ((second ? c0 - g.split_c : c0) >> 3);
+              const size_t img = (size_t)n * 2 * d.planes_half;
+              const size_t pix = (size_t)gy * g.W + gx;
+              const size_t hw = (size_t)g.H * g.W;
+              uint4* p_hi = d.base + (img + plane) * hw + pix;
+              uint4* p_lo = d.base + (img + d.planes_half + plane) * hw + pix;
+              p_hi[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+              p_hi[hw] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+              p_lo[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+              p_lo[hw] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+            }
+          }
+        } else {
+          uint32_t v[16];
+          tmem_ld16(t_addr, v);
+          if (inside) {
+            const size_t hw = (size_t)g.H * g.W;
+            const size_t o = (size_t)n * 3 * hw + (size_t)gy * g.W + gx;
+            if constexpr (EPI == kEpiSigmoid) {
+#pragma unroll
+              for (int c = 0; c < 3; c++) {
+                float f = __uint_as_float(v[c]) + s_bias[c];
+                g.out_f32[o + c * hw] = 1.0f / (1.0f + expf(-f));
+              }
+            } else {  // kEpiGate: columns 3r+c = refiner r, colour c  (net.py:104-108)
+              float r[9];
+#pragma unroll
+              for (int j = 0; j < 9; j++) r[j] = fmaxf(__uint_as_float(v[j]) + s_bias[j], 0.f);
+              const float c0 = g.cm[o], c1 = g.cm[o + hw], c2 = g.cm[o + 2 * hw];
+#pragma unroll
+              for (int c = 0; c < 3; c++)
+                g.out_f32[o + c * hw] =
+                    __fadd_rn(__fadd_rn(__fmul_rn(r[c], c0), __fmul_rn(r[3 + c], c1)), __fmul_rn(r[6 + c], c2));
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&t_empty[acc]);
+      if (++acc == AS) { acc = 0; tphase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 7) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"((uint32_t)C::TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Operand packing kernels
+// ------------------------------------------------------------------------------------------
+// scatter one OIHW fp32 tensor into a dense [npad][cinpad][ks*ks] fp32 block-matrix
+__global__ void scatter_weights_kernel(const float* __restrict__ src, float* __restrict__ dense, int co, int ci,
+                                       int kk, int cinpad, int row_off, int split, int base0, int base1) {
+  const int total = co * ci * kk;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    int t = i % kk;
+    int c = (i / kk) % ci;
+    int o = i / (kk * ci);
+    int cd = c < split ? base0 + c : base1 + (c - split);
+    dense[((size_t)(row_off + o) * cinpad + cd) * kk + t] = src[i];
+  }
+}
+__global__ void scatter_bias_kernel(const float* __restrict__ src, float* __restrict__ dst, int co, int row_off) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < co; i += gridDim.x * blockDim.x) dst[row_off + i] = src[i];
+}
+// dense fp32 -> stages [(chunk*kk + tap)][split hi|lo][k8 0|1][npad][8] bf16
+__global__ void pack_stages_kernel(const float* __restrict__ dense, __nv_bfloat16* __restrict__ out, int npad,
+                                   int cinpad, int kk) {
+  const size_t total = (size_t)(cinpad / 16) * kk * 2 * 2 * npad * 8;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    int e = (int)(i % 8);
+    size_t r = i / 8;
+    int nrow = (int)(r % npad); r /= npad;
+    int k8 = (int)(r % 2); r /= 2;
+    int split = (int)(r % 2); r /= 2;
+    int tap = (int)(r % kk);
+    int chunk = (int)(r / kk);
+    int cin = chunk * 16 + k8 * 8 + e;
+    float w = dense[((size_t)nrow * cinpad + cin) * kk + tap];
+    __nv_bfloat16 hi = __float2bfloat16_rn(w);
+    out[i] = split == 0 ? hi : __float2bfloat16_rn(w - __bfloat162float(hi));
+  }
+}
+
+// torch.cat([x, wb, ce, gc], 1) (net.py:46) -> act planes: 16 channels (12 + 4 zero), bf16 hi/lo
+struct PackInArgs {
+  const float* p[4];
+  long long s[4][4];
+};
+__global__ void __launch_bounds__(256) pack_inputs_kernel(PackInArgs a, uint4* __restrict__ out, int H, int W) {
+  const int n = blockIdx.y;
+  const int pix = blockIdx.x * 256 + threadIdx.x;
+  const int hw = H * W;
+  if (pix >= hw) return;
+  const int y = pix / W, x = pix - y * W;
+  float v[16];
+#pragma unroll
+  for (int t = 0; t < 4; t++)
+#pragma unroll
+    for (int c = 0; c < 3; c++) v[t * 3 + c] = a.p[t][n * a.s[t][0] + c * a.s[t][1] + y * a.s[t][2] + x * a.s[t][3]];
+  v[12] = v[13] = v[14] = v[15] = 0.f;
+  uint32_t hi[8], lo[8];
+#pragma unroll
+  for (int j = 0; j < 16; j += 2) {
+    __nv_bfloat16 h0 = __float2bfloat16_rn(v[j]), h1 = __float2bfloat16_rn(v[j + 1]);
+    hi[j >> 1] = pack_bf16x2(h0, h1);
+    lo[j >> 1] = pack_bf16x2(__float2bfloat16_rn(v[j] - __bfloat162float(h0)),
+                             __float2bfloat16_rn(v[j + 1] - __bfloat162float(h1)));
+  }
+  uint4* o = out + (size_t)n * 4 * hw + pix;  // planes: hi0, hi1, lo0, lo1
+  o[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  o[hw] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+  o[2 * (size_t)hw] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  o[3 * (size_t)hw] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+}
+
+// ------------------------------------------------------------------------------------------
+// Host side
+// ------------------------------------------------------------------------------------------
+// The ten tensor-core launches of one forward (fused layer list).
+enum UmmaLayer {
+  kL1 = 0,    // cmg.conv1 (12->128) + the three refiner conv1 (6->32 each): 16 -> 224, 7x7
+  kC2, kC3, kC4, kC5, kC6, kC7,
+  kC8,        // 64 -> 3 (pad 16), sigmoid
+  kR2,        // three refiner conv2 as one block-diagonal 96 -> 96, 5x5
+  kR3,        // three refiner conv3 as block-diagonal 96 -> 9 (pad 16), ReLU, gated sum
+  kNumUmmaLayers
+};
+struct UmmaLayerSpec {
+  int ks, cinpad, npad, cout, slot;
+};
+static const UmmaLayerSpec kSpecs[kNumUmmaLayers] = {
+    {7, 16, 224, 224, 0}, {5, 128, 128, 128, 1}, {3, 128, 128, 128, 2}, {1, 128, 64, 64, 3}, {7, 64, 64, 64, 4},
+    {5, 64, 64, 64, 5},   {3, 64, 64, 64, 6},    {3, 64, 16, 3, 7},     {5, 96, 96, 96, 9},  {3, 96, 16, 9, 10}};
+
+struct UmmaWeights {
+  uint8_t* stages[kNumUmmaLayers];
+  float* bias[kNumUmmaLayers];
+  float* dense;  // scratch for packing
+};
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+
+static int get_encoder() {
+  if (g_encode) return WN_OK;
+  cudaDriverEntryPointQueryResult q;
+  void* fn = nullptr;
+  WN_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+  if (!fn || q != cudaDriverEntryPointSuccess) {
+    set_error("cuTensorMapEncodeTiled is not available from this driver");
+    return WN_E_UNSUPPORTED;
+  }
+  g_encode = (EncodeTiledFn)fn;
+  return WN_OK;
+}
+
+static size_t stage_bytes_total(const UmmaLayerSpec& s) {
+  return (size_t)(s.cinpad / 16) * s.ks * s.ks * s.npad * 64;
+}
+
+int umma_pack_weights(wn_handle* h, const float* const* params, cudaStream_t stream) {
+  if (!h->umma) {
+    h->umma = (UmmaWeights*)calloc(1, sizeof(UmmaWeights));
+    for (int i = 0; i < kNumUmmaLayers; i++) {
+      WN_CUDA(cudaMalloc(&h->umma->stages[i], stage_bytes_total(kSpecs[i])));
+      WN_CUDA(cudaMalloc(&h->umma->bias[i], kSpecs[i].npad * sizeof(float)));
+    }
+    WN_CUDA(cudaMalloc(&h->umma->dense, (size_t)224 * 128 * 49 * sizeof(float)));
+  }
+  UmmaWeights* u = h->umma;
+  auto W = [&](int conv) { return params[2 * conv]; };
+  auto B = [&](int conv) { return params[2 * conv + 1]; };
+  for (int li = 0; li < kNumUmmaLayers; li++) {
+    const UmmaLayerSpec& s = kSpecs[li];
+    const int kk = s.ks * s.ks;
+    WN_CUDA(cudaMemsetAsync(u->dense, 0, (size_t)s.npad * s.cinpad * kk * sizeof(float), stream));
+    WN_CUDA(cudaMemsetAsync(u->bias[li], 0, s.npad * sizeof(float), stream));
+    auto scatter = [&](int conv, int co, int ci, int row_off, int split, int base0, int base1) -> int {
+      scatter_weights_kernel<<<128, 256, 0, stream>>>(W(conv), u->dense, co, ci, kk, s.cinpad, row_off, split,
+                                                      base0, base1);
+      WN_LAUNCH_CHECK(h);
+      scatter_bias_kernel<<<1, 256, 0, stream>>>(B(conv), u->bias[li], co, row_off);
+      WN_LAUNCH_CHECK(h);
+      return WN_OK;
+    };
+    int rc = WN_OK;
+    if (li == kL1) {
+      rc = scatter(0, 128, 12, 0, 12, 0, 0);
+      for (int r = 0; r < 3 && !rc; r++)  // refiner r sees cat[x, input r+1]: channels 0..2 and 3(r+1)..3(r+1)+2
+        rc = scatter(8 + 3 * r, 32, 6, 128 + 32 * r, 3, 0, 3 * (r + 1));
+    } else if (li >= kC2 && li <= kC8) {
+      const int conv = li;  // cmg.conv2..conv8 are convs 1..7
+      const LayerDesc& d = kCmg[conv];
+      rc = scatter(conv, d.cout, d.cin, 0, d.cin, 0, 0);
+    } else if (li == kR2) {
+      for (int r = 0; r < 3 && !rc; r++) rc = scatter(8 + 3 * r + 1, 32, 32, 32 * r, 32, 32 * r, 0);
+    } else {
+      for (int r = 0; r < 3 && !rc; r++) rc = scatter(8 + 3 * r + 2, 3, 32, 3 * r, 32, 32 * r, 0);
+    }
+    if (rc) return rc;
+    pack_stages_kernel<<<256, 256, 0, stream>>>(u->dense, (__nv_bfloat16*)u->stages[li], s.npad, s.cinpad, kk);
+    WN_LAUNCH_CHECK(h);
+  }
+  return WN_OK;
+}
+
+void umma_free(wn_handle* h) {
+  if (!h->umma) return;
+  for (int i = 0; i < kNumUmmaLayers; i++) {
+    if (h->umma->stages[i]) cudaFree(h->umma->stages[i]);
+    if (h->umma->bias[i]) cudaFree(h->umma->bias[i]);
+  }
+  if (h->umma->dense) cudaFree(h->umma->dense);
+  free(h->umma);
+  h->umma = nullptr;
+}
+
+// bytes per pixel: act0 (16 ch) 64 | cmg ping/pong (128 ch) 512 each | ref ping/pong (96 ch) 384 each | cm 12
+static constexpr size_t kUmmaBytesPerPixel = 64 + 512 + 512 + 384 + 384 + 12;
+
+static int umma_chunk(int n, int h, int w) {
+  long long per = (long long)h * w;
+  long long nb = (8ll << 20) / (per > 0 ? per : 1);  // <= 8M pixels (~15 GB) per pass
+  if (nb < 1) nb = 1;
+  return nb < n ? (int)nb : n;
+}
+
+size_t umma_forward_workspace_bytes(int n, int h, int w) {
+  return (size_t)umma_chunk(n, h, w) * h * w * kUmmaBytesPerPixel + 4096;
+}
+
+static int make_tmap(CUtensorMap* tm, void* base, int planes_total, int N, int H, int W, int halo_w, int halo_h) {
+  cuuint64_t dims[5] = {8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)planes_total, (cuuint64_t)N};
+  cuuint64_t strides[4] = {16, (cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)planes_total * H * W * 16};
+  cuuint32_t box[5] = {8, (cuuint32_t)halo_w, (cuuint32_t)halo_h, 2, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with %d (planes=%d N=%d H=%d W=%d box=%dx%d)", (int)r, planes_total, N, H,
+              W, halo_w, halo_h);
+    return WN_E_CUDA;
+  }
+  return WN_OK;
+}
+
+template <int KS, int CIN_PAD, int NPAD, int S, int AS, int EPI>
+static int launch_umma(wn_handle* h, int li, void* in_base, ConvArgs a, cudaStream_t stream) {
+  using C = UmmaCfg<KS, CIN_PAD, NPAD, S, AS>;
+  CUtensorMap tm;
+  int rc = make_tmap(&tm, in_base, 2 * (CIN_PAD / 8), a.N, a.H, a.W, C::HALO_W, C::HALO_H);
+  if (rc) return rc;
+  a.wpk = h->umma->stages[li];
+  a.bias = h->umma->bias[li];
+  a.in_planes_half = CIN_PAD / 8;
+  a.tiles_x = (a.W + C::TILE_W - 1) / C::TILE_W;
+  a.tiles_y = (a.H + C::TILE_H - 1) / C::TILE_H;
+  const long long tiles = (long long)a.tiles_x * a.tiles_y * a.N;
+  auto kern = conv_umma_kernel<KS, CIN_PAD, NPAD, S, AS, EPI>;
+  WN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+  int grid = (int)(tiles < h->sm_count ? tiles : h->sm_count);
+  TimedScope ts(h, kSpecs[li].slot, stream);
+  kern<<<grid, kThreads, C::SMEM_BYTES, stream>>>(tm, a);
+  WN_LAUNCH_CHECK(h);
+  return WN_OK;
+}
+
+// bf16 hi/lo planes -> fp32 NCHW (test aid)
+__global__ void decode_planes_kernel(const uint4* __restrict__ src, float* __restrict__ dst, int planes_half, int hw) {
+  const int n = blockIdx.z, plane = blockIdx.y;
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= hw) return;
+  const uint4 h4 = src[((size_t)n * 2 * planes_half + plane) * hw + pix];
+  const uint4 l4 = src[((size_t)n * 2 * planes_half + planes_half + plane) * hw + pix];
+  const uint32_t hs[4] = {h4.x, h4.y, h4.z, h4.w}, ls[4] = {l4.x, l4.y, l4.z, l4.w};
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    float hi = __uint_as_float(((hs[j >> 1] >> ((j & 1) * 16)) & 0xffffu) << 16);
+    float lo = __uint_as_float(((ls[j >> 1] >> ((j & 1) * 16)) & 0xffffu) << 16);
+    dst[((size_t)n * planes_half * 8 + plane * 8 + j) * hw + pix] = hi + lo;
+  }
+}
+
+static int umma_forward_chunk(wn_handle* h, const float* const in[4], const int64_t st[4][4], float* out, int n,
+                              int H, int W, void* workspace, cudaStream_t stream, int dbg_layer = -1,
+                              float* dbg_dst = nullptr) {
+  const size_t px = (size_t)n * H * W;
+  uint8_t* ws = (uint8_t*)(((uintptr_t)workspace + 1023) / 1024 * 1024);
+  uint4* act0 = (uint4*)ws;   ws += px * 64;
+  uint4* cmgA = (uint4*)ws;   ws += px * 512;
+  uint4* cmgB = (uint4*)ws;   ws += px * 512;
+  uint4* refA = (uint4*)ws;   ws += px * 384;
+  uint4* refB = (uint4*)ws;   ws += px * 384;
+  float* cm = (float*)ws;
+
+  PackInArgs pa;
+  for (int t = 0; t < 4; t++) {
+    pa.p[t] = in[t];
+    for (int k = 0; k < 4; k++) pa.s[t][k] = st[t][k];
+  }
+  {
+    TimedScope ts(h, kSlotPack, stream);
+    pack_inputs_kernel<<<dim3((H * W + 255) / 256, n), 256, 0, stream>>>(pa, act0, H, W);
+    WN_LAUNCH_CHECK(h);
+  }
+  ConvArgs a;
+  memset(&a, 0, sizeof(a));
+  a.N = n; a.H = H; a.W = W;
+  int rc;
+  auto dump = [&](int layer, const uint4* buf, int channels) -> bool {
+    if (dbg_layer != layer) return false;
+    decode_planes_kernel<<<dim3((H * W + 255) / 256, channels / 8, n), 256, 0, stream>>>(buf, dbg_dst, channels / 8,
+                                                                                     H * W);
+    h->launches++;
+    return true;
+  };
+  auto act = [&](uint4* d0, int c0, uint4* d1, int c1) {
+    a.dst0.base = d0; a.dst0.planes_half = c0 / 8;
+    a.dst1.base = d1; a.dst1.planes_half = c1 / 8;
+    a.split_c = c0; a.cout = c0 + c1;
+  };
+  // L1: 16 -> 128 (cmg) + 96 (refiners)
+  act(cmgA, 128, refA, 96);
+  if ((rc = launch_umma<7, 16, 224, 2, 1, kEpiAct>(h, kL1, act0, a, stream))) return rc;
+  if (dump(0, cmgA, 128) || dump(8, refA, 96)) return WN_OK;
+  act(cmgB, 128, nullptr, 0);
+  if ((rc = launch_umma<5, 128, 128, 4, 1, kEpiAct>(h, kC2, cmgA, a, stream))) return rc;
+  if (dump(1, cmgB, 128)) return WN_OK;
+  act(cmgA, 128, nullptr, 0);
+  if ((rc = launch_umma<3, 128, 128, 4, 1, kEpiAct>(h, kC3, cmgB, a, stream))) return rc;
+  if (dump(2, cmgA, 128)) return WN_OK;
+  act(cmgB, 64, nullptr, 0);
+  if ((rc = launch_umma<1, 128, 64, 4, 2, kEpiAct>(h, kC4, cmgA, a, stream))) return rc;
+  if (dump(3, cmgB, 64)) return WN_OK;
+  act(cmgA, 64, nullptr, 0);
+  if ((rc = launch_umma<7, 64, 64, 4, 2, kEpiAct>(h, kC5, cmgB, a, stream))) return rc;
+  if (dump(4, cmgA, 64)) return WN_OK;
+  act(cmgB, 64, nullptr, 0);
+  if ((rc = launch_umma<5, 64, 64, 4, 2, kEpiAct>(h, kC6, cmgA, a, stream))) return rc;
+  if (dump(5, cmgB, 64)) return WN_OK;
+  act(cmgA, 64, nullptr, 0);
+  if ((rc = launch_umma<3, 64, 64, 4, 2, kEpiAct>(h, kC7, cmgB, a, stream))) return rc;
+  if (dump(6, cmgA, 64)) return WN_OK;
+  a.out_f32 = dbg_layer == 7 ? dbg_dst : cm;
+  if ((rc = launch_umma<3, 64, 16, 4, 2, kEpiSigmoid>(h, kC8, cmgA, a, stream))) return rc;
+  if (dbg_layer == 7) return WN_OK;
+  act(refB, 96, nullptr, 0);
+  if ((rc = launch_umma<5, 96, 96, 4, 1, kEpiAct>(h, kR2, refA, a, stream))) return rc;
+  if (dump(9, refB, 96)) return WN_OK;
+  a.out_f32 = out;
+  a.cm = cm;
+  if ((rc = launch_umma<3, 96, 16, 4, 2, kEpiGate>(h, kR3, refB, a, stream))) return rc;
+  return WN_OK;
+}
+
+int umma_debug_layer(wn_handle* h, const float* const in[4], const int64_t in_strides[4][4], int n, int H, int W,
+                     int layer, float* dst, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  if (!h->umma || umma_chunk(n, H, W) != n || workspace_bytes < umma_forward_workspace_bytes(n, H, W)) {
+    set_error("debug layer dump: weights not packed, batch too large for one pass or workspace too small");
+    return WN_E_WORKSPACE;
+  }
+  int rc = get_encoder();
+  if (rc) return rc;
+  return umma_forward_chunk(h, in, in_strides, nullptr, n, H, W, workspace, stream, layer, dst);
+}
+
+int umma_forward(wn_handle* h, const float* const in[4], const int64_t in_strides[4][4], float* out, int n, int H,
+                 int W, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  if (!h->umma) {
+    set_error("tensor-core weights have not been packed");
+    return WN_E_STATE;
+  }
+  if (workspace_bytes < umma_forward_workspace_bytes(n, H, W)) {
+    set_error("forward workspace too small: %zu < %zu", workspace_bytes, umma_forward_workspace_bytes(n, H, W));
+    return WN_E_WORKSPACE;
+  }
+  int rc = get_encoder();
+  if (rc) return rc;
+  const int nb = umma_chunk(n, H, W);
+  for (int n0 = 0; n0 < n; n0 += nb) {
+    const int cur = n - n0 < nb ? n - n0 : nb;
+    const float* sub[4];
+    for (int t = 0; t < 4; t++) sub[t] = in[t] + (long long)n0 * in_strides[t][0];
+    rc = umma_forward_chunk(h, sub, in_strides, out + (size_t)n0 * 3 * H * W, cur, H, W, workspace, stream);
+    if (rc) return rc;
+  }
+  return WN_OK;
+}
+
+}  // namespace wn

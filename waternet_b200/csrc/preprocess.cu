@@ -195,7 +195,7 @@ __device__ __forceinline__ uint32_t block_inclusive_scan_256(uint32_t v, uint32_
 // inclusive cumulative histogram; `n` elements.  Mirrors numpy/lib/_function_base_impl.py
 // (_compute_virtual_index, _get_indexes, _lerp) operation for operation in float64.
 __device__ double np_quantile_from_cum(const uint32_t* cum, int n, double q) {
-  double vi = __dsub_rn(__dadd_rn(__dmul_rn((double)n, q), __dadd_rn(1.0, __dmul_rn(q, -1.0))), 1.0);
+  double vi = __dmul_rn((double)(n - 1), q);  // method "linear": virtual index = (n - 1) * q
   double prev_f = floor(vi);
   long long prev = (long long)prev_f, next = prev + 1;
   if (vi >= (double)(n - 1)) prev = next = n - 1;
@@ -291,6 +291,9 @@ luts_kernel(const uint32_t* __restrict__ tile_hist, const uint32_t* __restrict__
 // ---------------------------------------------------------------------------
 // Pass 3: per-pixel apply.  grid = (ceil(H*W/256), N), 256 threads.
 // ---------------------------------------------------------------------------
+// pixels per CTA = 256 * kApplyIters: amortises the ~30 KB of LUT/table staging per CTA
+constexpr int kApplyIters = 16;
+
 struct ApplyOut {
   float* f32[4];    // x, wb, he, gc  -- NCHW planes, may be null
   uint8_t* u8[3];   // wb, he, gc     -- NHWC, may be null
@@ -327,8 +330,10 @@ apply_kernel(const uint8_t* __restrict__ rgb, int H, int W, int th, int tw,
   }
   __syncthreads();
   const int plane = H * W;
-  const int pix = blockIdx.x * 256 + tid;
-  if (pix >= plane) return;
+  const float inv_tw = __fdiv_rn(1.0f, (float)tw), inv_th = __fdiv_rn(1.0f, (float)th);
+  for (int it = 0; it < kApplyIters; it++) {
+  const int pix = (blockIdx.x * kApplyIters + it) * 256 + tid;
+  if (pix >= plane) break;
   const int y = pix / W, x = pix - y * W;
   const uint8_t* p = rgb + ((size_t)n * plane + pix) * 3;
   const int r = p[0], g = p[1], b = p[2];
@@ -336,7 +341,6 @@ apply_kernel(const uint8_t* __restrict__ rgb, int H, int W, int th, int tw,
   // hist-eq: RGB -> Lab, CLAHE bilinear blend of the four neighbouring tile LUTs, Lab -> RGB
   int L, A, Bv;
   rgb2lab(s_gtab, s_ctab, r, g, b, L, A, Bv);
-  const float inv_tw = __fdiv_rn(1.0f, (float)tw), inv_th = __fdiv_rn(1.0f, (float)th);
   float txf = __fsub_rn(__fmul_rn((float)x, inv_tw), 0.5f);
   float tyf = __fsub_rn(__fmul_rn((float)y, inv_th), 0.5f);
   int tx1 = (int)floorf(txf), ty1 = (int)floorf(tyf);
@@ -368,6 +372,7 @@ apply_kernel(const uint8_t* __restrict__ rgb, int H, int W, int th, int tw,
   if (out.u8[0]) { uint8_t* q = out.u8[0] + o8; q[0] = wr; q[1] = wg; q[2] = wbb; }
   if (out.u8[1]) { uint8_t* q = out.u8[1] + o8; q[0] = hr; q[1] = hg; q[2] = hb; }
   if (out.u8[2]) { uint8_t* q = out.u8[2] + o8; q[0] = gr; q[1] = gg; q[2] = gb; }
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -472,7 +477,7 @@ int preprocess_u8(wn_handle* h, const uint8_t* rgb, int n, int H, int W, float* 
   ao.f32[0] = x; ao.f32[1] = wb; ao.f32[2] = he; ao.f32[3] = gc;
   ao.u8[0] = wb_u8; ao.u8[1] = he_u8; ao.u8[2] = gc_u8;
   TimedScope ts(h, kSlotApply, stream);
-  apply_kernel<<<dim3((H * W + 255) / 256, n), 256, 0, stream>>>(rgb, H, W, g.th, g.tw,
+  apply_kernel<<<dim3((H * W + 256 * kApplyIters - 1) / (256 * kApplyIters), n), 256, 0, stream>>>(rgb, H, W, g.th, g.tw,
                                                                  h->d_tables, clahe_lut, wb_lut, ao);
   WN_LAUNCH_CHECK(h);
   return WN_OK;

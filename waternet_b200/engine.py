@@ -129,6 +129,22 @@ class Engine:
         _lib.check(rc, "wn_forward")
         return out
 
+    LAYER_CHANNELS = (128, 128, 128, 64, 64, 64, 64, 3, 96, 96)
+
+    def debug_layer(self, x, wb, he, gc, layer: int, mode: int) -> torch.Tensor:
+        """Test aid (wn_debug_forward_layer): an intermediate activation as fp32 (N,C,H,W)."""
+        ins = [t.detach().float() for t in (x, wb, he, gc)]
+        n, _, h, w = ins[0].shape
+        dst = torch.empty((n, self.LAYER_CHANNELS[layer], h, w), dtype=torch.float32, device=self.device)
+        strides = (ctypes.c_int64 * 16)(*[s for t in ins for s in t.stride()])
+        ws = self._workspace("forward", self.lib.wn_forward_workspace_bytes(n, h, w, mode))
+        with torch.cuda.device(self.device):
+            rc = self.lib.wn_debug_forward_layer(self.handle, ins[0].data_ptr(), ins[1].data_ptr(), ins[2].data_ptr(),
+                                                 ins[3].data_ptr(), strides, n, h, w, mode, layer, dst.data_ptr(),
+                                                 ws.data_ptr(), ws.numel(), _stream_ptr(self.device))
+        _lib.check(rc, "wn_debug_forward_layer")
+        return dst
+
     # ---- preprocess / postprocess ----------------------------------------------
     def preprocess(self, rgb_u8: torch.Tensor, tensors: bool = True, images: bool = False):
         """rgb_u8: uint8 (N,H,W,3) CUDA tensor.  Returns dict with the requested outputs.

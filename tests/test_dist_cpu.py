@@ -1,0 +1,69 @@
+"""Batch sharding + output all-gather on CPU (gloo, world_size 2): the N>1 host logic of bench.py."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from waternet_b200.dist import all_gather_batch, run_sharded, shard_counts, shard_range
+
+
+def test_shard_range_covers_the_batch_exactly():
+    for n in (0, 1, 2, 7, 16, 128, 129):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(n, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and sum(c for _, c in spans) == n
+            for (s0, c0), (s1, _) in zip(spans, spans[1:]):
+                assert s0 + c0 == s1
+            assert max(c for _, c in spans) - min(c for _, c in spans) <= 1
+    assert shard_counts(128, 8) == [16] * 8
+    with pytest.raises(ValueError):
+        shard_range(4, 2, 2)
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, n, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import preprocess as opre  # stand-in for the CUDA engine on a CPU box (tests only)
+        rng = np.random.default_rng(0)
+        batch = torch.from_numpy(rng.integers(0, 256, (n, 24, 40, 3), dtype=np.uint8))
+
+        def fn(local):  # independent per-image work, like Engine.enhance
+            return torch.from_numpy(np.stack([opre.gamma_correction(a.numpy()) for a in local])
+                                    if len(local) else np.zeros((0, 24, 40, 3), np.uint8))
+
+        full = run_sharded(batch, fn, gather=True)
+        local = run_sharded(batch, fn, gather=False)
+        start, count = shard_range(n, world, rank)
+        ok = torch.equal(full, fn(batch)) and torch.equal(local, full[start:start + count])
+        counts = shard_counts(n, world)
+        again = all_gather_batch(local, counts)
+        ok = ok and torch.equal(again, full)
+        ret[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [4, 5, 1])
+def test_sharded_result_equals_single_process_result(n):
+    world = 2
+    port = _free_port()
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_worker, args=(world, port, n, ret), nprocs=world, join=True)
+        assert dict(ret) == {0: True, 1: True}
+
+
+def test_run_sharded_without_process_group_is_identity():
+    t = torch.arange(12).reshape(4, 3)
+    assert torch.equal(run_sharded(t, lambda x: x * 2), t * 2)

@@ -98,6 +98,18 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Same, descriptors given as (lo, hi) 32-bit halves so that the per-MMA work is one add.
+__device__ __forceinline__ void umma_bf16_split(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                                uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
                    smem_u32(bar))
@@ -112,6 +124,15 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
         "=r"(v[15])
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_before() {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -211,6 +232,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (tmem_base != 0) __trap();  // see the MMA issuer: accumulators are addressed from column 0
 
   if (warp == 4) {
     // ===================== A producer: halo tiles by TMA =====================
@@ -249,44 +271,54 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
     }
   } else if (warp == 6) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // The whole warp walks the pipeline (converged, so every operand stays in uniform registers);
+    // one elected lane issues the MMAs and commits.
+    {
       constexpr uint32_t idesc = make_idesc(128, NPAD);
+      // descriptor halves: hi = SBO | version, lo = start address | LBO
+      constexpr uint32_t a_hi32 = ((uint32_t)(C::HALO_W * 16) >> 4) | (1u << 14);
+      constexpr uint32_t b_hi32 = (128u >> 4) | (1u << 14);
       int astage = 0, bstage = 0, acc = 0;
       uint32_t aphase = 0, bphase = 0, tphase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         mbar_wait(&t_empty[acc], tphase ^ 1);
         tc_fence_after();
-        const uint32_t d_base = tmem_base + (uint32_t)(acc * S * NPAD);
+        // TMEM addresses are compile-time column offsets: this CTA is alone on its SM (shared memory
+        // footprint) and owns the allocation at column 0 (checked after the allocation).
+        const uint32_t d_base = (uint32_t)(acc * S * NPAD);
         for (int c = 0; c < C::NCHUNK; c++) {
           mbar_wait(&a_full[astage], aphase);
           tc_fence_after();
-          const uint32_t a_base = smem_u32(a_stages + astage * C::A_STAGE);
+          const uint32_t a_lo32 = (smem_u32(a_stages + astage * C::A_STAGE) >> 4) | ((uint32_t)(C::PLANE_BYTES >> 4) << 16);
           for (int tap = 0; tap < KS * KS; tap++) {
             mbar_wait(&b_full[bstage], bphase);
             tc_fence_after();
             const int ky = tap / KS, kx = tap - ky * KS;
-            const uint32_t b_base = smem_u32(b_stages + bstage * C::B_STAGE);
-            const uint64_t b_hi = make_desc(b_base, NPAD * 16, 128);
-            const uint64_t b_lo = make_desc(b_base + 2 * NPAD * 16, NPAD * 16, 128);
+            const uint32_t b_lo32 = (smem_u32(b_stages + bstage * C::B_STAGE) >> 4) | ((uint32_t)(NPAD * 16 >> 4) << 16);
+            const uint32_t a_tap = a_lo32 + (uint32_t)(ky * C::HALO_W + kx);
             const uint32_t first = (c | tap) == 0 ? 0u : 1u;
-            // split-major order: consecutive MMAs target different accumulators
+            if (elect_one_sync()) {
+              // split-major order: consecutive MMAs target different accumulators
 #pragma unroll
-            for (int sp = 0; sp < 3; sp++) {
+              for (int sp = 0; sp < 3; sp++) {
 #pragma unroll
-              for (int s = 0; s < S; s++) {
-                const uint32_t a_off = (uint32_t)((ky * C::HALO_W + kx + s * kSubW) * 16) +
-                                       (sp == 1 ? 2u * C::PLANE_BYTES : 0u);
-                const uint64_t a_d = make_desc(a_base + a_off, C::PLANE_BYTES, C::HALO_W * 16);
-                umma_bf16(d_base + (uint32_t)(s * NPAD), a_d, sp == 2 ? b_lo : b_hi, idesc, sp == 0 ? first : 1u);
+                for (int s = 0; s < S; s++) {
+                  const uint32_t a_d = a_tap + (uint32_t)(s * kSubW) + (sp == 1 ? (uint32_t)(2 * C::PLANE_BYTES >> 4) : 0u);
+                  const uint32_t b_d = b_lo32 + (sp == 2 ? (uint32_t)(2 * NPAD * 16 >> 4) : 0u);
+                  umma_bf16_split(d_base + (uint32_t)(s * NPAD), a_d, a_hi32, b_d, b_hi32, idesc, sp == 0 ? first : 1u);
+                }
+              }
+              umma_commit(&b_empty[bstage]);
+              if (tap == KS * KS - 1) {
+                umma_commit(&a_empty[astage]);
+                if (c == C::NCHUNK - 1) umma_commit(&t_full[acc]);
               }
             }
-            umma_commit(&b_empty[bstage]);
+            __syncwarp();
             if (++bstage == C::NB) { bstage = 0; bphase ^= 1; }
           }
-          umma_commit(&a_empty[astage]);
           if (++astage == C::NA) { astage = 0; aphase ^= 1; }
         }
-        umma_commit(&t_full[acc]);
         if (++acc == AS) { acc = 0; tphase ^= 1; }
       }
     }

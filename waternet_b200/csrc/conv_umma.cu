@@ -149,7 +149,13 @@ enum Epilogue { kEpiAct = 0, kEpiSigmoid = 1, kEpiGate = 2 };
 constexpr int kSubW = 8, kSubH = 16;  // one M=128 sub-tile: 8 px wide, 16 px tall
 constexpr int kThreads = 256;
 
-template <int KS, int CIN_PAD, int NPAD, int S, int AS>
+// NPAD   output channels per diagonal block (UMMA N of the lo*hi pass)
+// CONCAT weight stage rows are [hi rows | lo rows]: a_hi x [w_hi|w_lo] is ONE MMA of N = 2*NPAD (the
+//        activation tile is read from shared memory once for two products), then a_lo x w_hi with
+//        N = NPAD.  Pays when NPAD <= 64, where an MMA is bound by the 4 KB A-operand read.
+// NBLK   number of diagonal blocks (the three refiners run as one block-diagonal layer): input
+//        chunk c only feeds block c / (NCHUNK / NBLK), so only that block's weights are staged.
+template <int KS, int CIN_PAD, int NPAD, int S, int AS, int CONCAT = 0, int NBLK = 1>
 struct UmmaCfg {
   static constexpr int TILE_W = kSubW * S, TILE_H = kSubH;
   static constexpr int HALO_W = TILE_W + KS - 1, HALO_H = TILE_H + KS - 1;
@@ -161,7 +167,13 @@ struct UmmaCfg {
   static constexpr int BUDGET = 225 * 1024 - 2048;
   static constexpr int NA_FIT = (BUDGET - NB * B_STAGE) / A_STAGE;
   static constexpr int NA = NA_FIT > 3 ? 3 : NA_FIT;
-  static constexpr int TMEM_COLS_USED = AS * S * NPAD;
+  static constexpr int CPB = NCHUNK / NBLK;                // chunks per diagonal block
+  static constexpr int N1 = CONCAT ? 2 * NPAD : NPAD;      // UMMA N of the a_hi pass
+  static constexpr int BLK_COLS = N1;                      // accumulator columns per block
+  static constexpr int SUB_COLS = NBLK * BLK_COLS;         // accumulator columns per sub-tile
+  static constexpr int TMEM_COLS_USED = AS * S * SUB_COLS;
+  static_assert(NCHUNK % NBLK == 0, "chunks must split evenly over the diagonal blocks");
+  static_assert(N1 % 16 == 0 && N1 <= 256, "invalid UMMA N for the a_hi pass");
   static constexpr int TMEM_COLS = TMEM_COLS_USED <= 32 ? 32 : TMEM_COLS_USED <= 64 ? 64
                                    : TMEM_COLS_USED <= 128 ? 128 : TMEM_COLS_USED <= 256 ? 256 : 512;
   static constexpr int SMEM_BYTES = NA * A_STAGE + NB * B_STAGE + 2048 + 1024;  // + barriers/bias + align slack
@@ -194,10 +206,10 @@ __device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b
   return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
 }
 
-template <int KS, int CIN_PAD, int NPAD, int S, int AS, int EPI>
+template <int KS, int CIN_PAD, int NPAD, int S, int AS, int EPI, int CONCAT, int NBLK>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) {
-  using C = UmmaCfg<KS, CIN_PAD, NPAD, S, AS>;
+  using C = UmmaCfg<KS, CIN_PAD, NPAD, S, AS, CONCAT, NBLK>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* a_stages = smem;
@@ -221,7 +233,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
     for (int i = 0; i < AS; i++) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int i = tid; i < NPAD; i += kThreads) s_bias[i] = g.bias[i];
+  for (int i = tid; i < NBLK * NPAD; i += kThreads) s_bias[i] = g.bias[i];
   if (warp == 7) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "r"((uint32_t)C::TMEM_COLS)
@@ -274,10 +286,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
     // The whole warp walks the pipeline (converged, so every operand stays in uniform registers);
     // one elected lane issues the MMAs and commits.
     {
-      constexpr uint32_t idesc = make_idesc(128, NPAD);
+      constexpr uint32_t idesc1 = make_idesc(128, C::N1);  // a_hi pass
+      constexpr uint32_t idesc2 = make_idesc(128, NPAD);   // a_lo x w_hi (and a_hi x w_lo without CONCAT)
       // descriptor halves: hi = SBO | version, lo = start address | LBO
       constexpr uint32_t a_hi32 = ((uint32_t)(C::HALO_W * 16) >> 4) | (1u << 14);
       constexpr uint32_t b_hi32 = (128u >> 4) | (1u << 14);
+      // weight stage: CONCAT [k8][hi rows | lo rows][16 B] (LBO = 2*NPAD*16), else [hi|lo][k8][rows][16 B]
+      constexpr uint32_t b_lbo = (uint32_t)((CONCAT ? 2 * NPAD : NPAD) * 16);
       int astage = 0, bstage = 0, acc = 0;
       uint32_t aphase = 0, bphase = 0, tphase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -285,28 +300,36 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
         tc_fence_after();
         // TMEM addresses are compile-time column offsets: this CTA is alone on its SM (shared memory
         // footprint) and owns the allocation at column 0 (checked after the allocation).
-        const uint32_t d_base = (uint32_t)(acc * S * NPAD);
+        const uint32_t d_tile = (uint32_t)(acc * S * C::SUB_COLS);
         for (int c = 0; c < C::NCHUNK; c++) {
           mbar_wait(&a_full[astage], aphase);
           tc_fence_after();
           const uint32_t a_lo32 = (smem_u32(a_stages + astage * C::A_STAGE) >> 4) | ((uint32_t)(C::PLANE_BYTES >> 4) << 16);
+          const int blk = NBLK > 1 ? c / C::CPB : 0;
+          const uint32_t d_base = d_tile + (uint32_t)(blk * C::BLK_COLS);
           for (int tap = 0; tap < KS * KS; tap++) {
             mbar_wait(&b_full[bstage], bphase);
             tc_fence_after();
             const int ky = tap / KS, kx = tap - ky * KS;
-            const uint32_t b_lo32 = (smem_u32(b_stages + bstage * C::B_STAGE) >> 4) | ((uint32_t)(NPAD * 16 >> 4) << 16);
+            const uint32_t b_lo32 = (smem_u32(b_stages + bstage * C::B_STAGE) >> 4) | ((b_lbo >> 4) << 16);
             const uint32_t a_tap = a_lo32 + (uint32_t)(ky * C::HALO_W + kx);
-            const uint32_t first = (c | tap) == 0 ? 0u : 1u;
+            const uint32_t first = ((NBLK > 1 ? c % C::CPB : c) | tap) == 0 ? 0u : 1u;
             if (elect_one_sync()) {
-              // split-major order: consecutive MMAs target different accumulators
+              // pass-major order: consecutive MMAs target different accumulators
+              constexpr uint32_t a_lo_off = (uint32_t)(2 * C::PLANE_BYTES >> 4);
 #pragma unroll
-              for (int sp = 0; sp < 3; sp++) {
+              for (int s = 0; s < S; s++)  // a_hi x w_hi (CONCAT: x [w_hi | w_lo])
+                umma_bf16_split(d_base + (uint32_t)(s * C::SUB_COLS), a_tap + (uint32_t)(s * kSubW), a_hi32, b_lo32,
+                                b_hi32, idesc1, first);
 #pragma unroll
-                for (int s = 0; s < S; s++) {
-                  const uint32_t a_d = a_tap + (uint32_t)(s * kSubW) + (sp == 1 ? (uint32_t)(2 * C::PLANE_BYTES >> 4) : 0u);
-                  const uint32_t b_d = b_lo32 + (sp == 2 ? (uint32_t)(2 * NPAD * 16 >> 4) : 0u);
-                  umma_bf16_split(d_base + (uint32_t)(s * NPAD), a_d, a_hi32, b_d, b_hi32, idesc, sp == 0 ? first : 1u);
-                }
+              for (int s = 0; s < S; s++)  // a_lo x w_hi
+                umma_bf16_split(d_base + (uint32_t)(s * C::SUB_COLS), a_tap + (uint32_t)(s * kSubW) + a_lo_off, a_hi32,
+                                b_lo32, b_hi32, idesc2, 1u);
+              if constexpr (!CONCAT) {
+#pragma unroll
+                for (int s = 0; s < S; s++)  // a_hi x w_lo
+                  umma_bf16_split(d_base + (uint32_t)(s * C::SUB_COLS), a_tap + (uint32_t)(s * kSubW), a_hi32,
+                                  b_lo32 + (uint32_t)(2 * NPAD * 16 >> 4), b_hi32, idesc2, 1u);
               }
               umma_commit(&b_empty[bstage]);
               if (tap == KS * KS - 1) {
@@ -339,18 +362,32 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
       for (int s = 0; s < S; s++) {
         const int gx = tx * C::TILE_W + s * kSubW + px;
         const bool inside = gx < g.W && gy < g.H;
-        const uint32_t t_addr = tmem_base + lane_base + (uint32_t)(acc * S * NPAD + s * NPAD);
+        const uint32_t t_addr = tmem_base + lane_base + (uint32_t)((acc * S + s) * C::SUB_COLS);
+        // 16 accumulator columns starting at output channel ch0 (+ the a_hi x w_lo half when CONCAT)
+        auto load16 = [&](int ch0, float* f) {
+          const int blk = NBLK > 1 ? ch0 / NPAD : 0;
+          const uint32_t col = (uint32_t)(blk * C::BLK_COLS + (NBLK > 1 ? ch0 % NPAD : ch0));
+          uint32_t v[16];
+          tmem_ld16(t_addr + col, v);
+#pragma unroll
+          for (int j = 0; j < 16; j++) f[j] = __uint_as_float(v[j]);
+          if constexpr (CONCAT) {
+            tmem_ld16(t_addr + col + NPAD, v);
+#pragma unroll
+            for (int j = 0; j < 16; j++) f[j] += __uint_as_float(v[j]);
+          }
+        };
         if constexpr (EPI == kEpiAct) {
 #pragma unroll 1
-          for (int c0 = 0; c0 < NPAD; c0 += 16) {
-            uint32_t v[16];
-            tmem_ld16(t_addr + c0, v);
+          for (int c0 = 0; c0 < NBLK * NPAD; c0 += 16) {
+            float f[16];
+            load16(c0, f);
             if (c0 < g.cout && inside) {
               uint32_t hi[8], lo[8];
 #pragma unroll
               for (int j = 0; j < 16; j += 2) {
-                float f0 = fmaxf(__uint_as_float(v[j]) + s_bias[c0 + j], 0.f);
-                float f1 = fmaxf(__uint_as_float(v[j + 1]) + s_bias[c0 + j + 1], 0.f);
+                float f0 = fmaxf(f[j] + s_bias[c0 + j], 0.f);
+                float f1 = fmaxf(f[j + 1] + s_bias[c0 + j + 1], 0.f);
                 __nv_bfloat16 h0 = __float2bfloat16_rn(f0), h1 = __float2bfloat16_rn(f1);
                 __nv_bfloat16 l0 = __float2bfloat16_rn(f0 - __bfloat162float(h0));
                 __nv_bfloat16 l1 = __float2bfloat16_rn(f1 - __bfloat162float(h1));
@@ -372,21 +409,18 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
             }
           }
         } else {
-          uint32_t v[16];
-          tmem_ld16(t_addr, v);
+          float f[16];
+          load16(0, f);
           if (inside) {
             const size_t hw = (size_t)g.H * g.W;
             const size_t o = (size_t)n * 3 * hw + (size_t)gy * g.W + gx;
             if constexpr (EPI == kEpiSigmoid) {
 #pragma unroll
-              for (int c = 0; c < 3; c++) {
-                float f = __uint_as_float(v[c]) + s_bias[c];
-                g.out_f32[o + c * hw] = 1.0f / (1.0f + expf(-f));
-              }
+              for (int c = 0; c < 3; c++) g.out_f32[o + c * hw] = 1.0f / (1.0f + expf(-(f[c] + s_bias[c])));
             } else {  // kEpiGate: columns 3r+c = refiner r, colour c  (net.py:104-108)
               float r[9];
 #pragma unroll
-              for (int j = 0; j < 9; j++) r[j] = fmaxf(__uint_as_float(v[j]) + s_bias[j], 0.f);
+              for (int j = 0; j < 9; j++) r[j] = fmaxf(f[j] + s_bias[j], 0.f);
               const float c0 = g.cm[o], c1 = g.cm[o + hw], c2 = g.cm[o + 2 * hw];
 #pragma unroll
               for (int c = 0; c < 3; c++)
@@ -431,20 +465,31 @@ __global__ void scatter_weights_kernel(const float* __restrict__ src, float* __r
 __global__ void scatter_bias_kernel(const float* __restrict__ src, float* __restrict__ dst, int co, int row_off) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < co; i += gridDim.x * blockDim.x) dst[row_off + i] = src[i];
 }
-// dense fp32 -> stages [(chunk*kk + tap)][split hi|lo][k8 0|1][npad][8] bf16
+// dense fp32 [nblk*npad][cinpad][kk] -> weight stages, one per (chunk, tap), holding the rows of the
+// diagonal block the chunk feeds:  concat ? [k8][hi rows | lo rows][8] : [hi|lo][k8][rows][8]   (bf16)
 __global__ void pack_stages_kernel(const float* __restrict__ dense, __nv_bfloat16* __restrict__ out, int npad,
-                                   int cinpad, int kk) {
-  const size_t total = (size_t)(cinpad / 16) * kk * 2 * 2 * npad * 8;
+                                   int cinpad, int kk, int concat, int nblk) {
+  const int nchunk = cinpad / 16, cpb = nchunk / nblk;
+  const size_t total = (size_t)nchunk * kk * 2 * 2 * npad * 8;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     int e = (int)(i % 8);
     size_t r = i / 8;
-    int nrow = (int)(r % npad); r /= npad;
-    int k8 = (int)(r % 2); r /= 2;
-    int split = (int)(r % 2); r /= 2;
+    int k8, split, nrow;
+    if (concat) {
+      int row2 = (int)(r % (2 * npad)); r /= 2 * npad;
+      k8 = (int)(r % 2); r /= 2;
+      split = row2 >= npad;
+      nrow = row2 - split * npad;
+    } else {
+      nrow = (int)(r % npad); r /= npad;
+      k8 = (int)(r % 2); r /= 2;
+      split = (int)(r % 2); r /= 2;
+    }
     int tap = (int)(r % kk);
     int chunk = (int)(r / kk);
     int cin = chunk * 16 + k8 * 8 + e;
-    float w = dense[((size_t)nrow * cinpad + cin) * kk + tap];
+    int row = (chunk / cpb) * npad + nrow;
+    float w = dense[((size_t)row * cinpad + cin) * kk + tap];
     __nv_bfloat16 hi = __float2bfloat16_rn(w);
     out[i] = split == 0 ? hi : __float2bfloat16_rn(w - __bfloat162float(hi));
   }
@@ -495,11 +540,12 @@ enum UmmaLayer {
   kNumUmmaLayers
 };
 struct UmmaLayerSpec {
-  int ks, cinpad, npad, cout, slot;
+  int ks, cinpad, npad, cout, slot, concat, nblk;  // npad = output columns per diagonal block
 };
 static const UmmaLayerSpec kSpecs[kNumUmmaLayers] = {
-    {7, 16, 224, 224, 0}, {5, 128, 128, 128, 1}, {3, 128, 128, 128, 2}, {1, 128, 64, 64, 3}, {7, 64, 64, 64, 4},
-    {5, 64, 64, 64, 5},   {3, 64, 64, 64, 6},    {3, 64, 16, 3, 7},     {5, 96, 96, 96, 9},  {3, 96, 16, 9, 10}};
+    {7, 16, 224, 224, 0, 0, 1}, {5, 128, 128, 128, 1, 0, 1}, {3, 128, 128, 128, 2, 0, 1}, {1, 128, 64, 64, 3, 1, 1},
+    {7, 64, 64, 64, 4, 1, 1},   {5, 64, 64, 64, 5, 1, 1},    {3, 64, 64, 64, 6, 1, 1},    {3, 64, 16, 3, 7, 1, 1},
+    {5, 96, 32, 96, 9, 1, 3},   {3, 96, 16, 9, 10, 1, 1}};
 
 struct UmmaWeights {
   uint8_t* stages[kNumUmmaLayers];
@@ -526,7 +572,7 @@ static int get_encoder() {
 }
 
 static size_t stage_bytes_total(const UmmaLayerSpec& s) {
-  return (size_t)(s.cinpad / 16) * s.ks * s.ks * s.npad * 64;
+  return (size_t)(s.cinpad / 16) * s.ks * s.ks * s.npad * 64;  // one block's rows per stage
 }
 
 int umma_pack_weights(wn_handle* h, const float* const* params, cudaStream_t stream) {
@@ -534,7 +580,7 @@ int umma_pack_weights(wn_handle* h, const float* const* params, cudaStream_t str
     h->umma = (UmmaWeights*)calloc(1, sizeof(UmmaWeights));
     for (int i = 0; i < kNumUmmaLayers; i++) {
       WN_CUDA(cudaMalloc(&h->umma->stages[i], stage_bytes_total(kSpecs[i])));
-      WN_CUDA(cudaMalloc(&h->umma->bias[i], kSpecs[i].npad * sizeof(float)));
+      WN_CUDA(cudaMalloc(&h->umma->bias[i], kSpecs[i].npad * kSpecs[i].nblk * sizeof(float)));
     }
     WN_CUDA(cudaMalloc(&h->umma->dense, (size_t)224 * 128 * 49 * sizeof(float)));
   }
@@ -544,8 +590,9 @@ int umma_pack_weights(wn_handle* h, const float* const* params, cudaStream_t str
   for (int li = 0; li < kNumUmmaLayers; li++) {
     const UmmaLayerSpec& s = kSpecs[li];
     const int kk = s.ks * s.ks;
-    WN_CUDA(cudaMemsetAsync(u->dense, 0, (size_t)s.npad * s.cinpad * kk * sizeof(float), stream));
-    WN_CUDA(cudaMemsetAsync(u->bias[li], 0, s.npad * sizeof(float), stream));
+    const int rows = s.npad * s.nblk;
+    WN_CUDA(cudaMemsetAsync(u->dense, 0, (size_t)rows * s.cinpad * kk * sizeof(float), stream));
+    WN_CUDA(cudaMemsetAsync(u->bias[li], 0, rows * sizeof(float), stream));
     auto scatter = [&](int conv, int co, int ci, int row_off, int split, int base0, int base1) -> int {
       scatter_weights_kernel<<<128, 256, 0, stream>>>(W(conv), u->dense, co, ci, kk, s.cinpad, row_off, split,
                                                       base0, base1);
@@ -569,7 +616,8 @@ int umma_pack_weights(wn_handle* h, const float* const* params, cudaStream_t str
       for (int r = 0; r < 3 && !rc; r++) rc = scatter(8 + 3 * r + 2, 3, 32, 3 * r, 32, 32 * r, 0);
     }
     if (rc) return rc;
-    pack_stages_kernel<<<256, 256, 0, stream>>>(u->dense, (__nv_bfloat16*)u->stages[li], s.npad, s.cinpad, kk);
+    pack_stages_kernel<<<256, 256, 0, stream>>>(u->dense, (__nv_bfloat16*)u->stages[li], s.npad, s.cinpad, kk,
+                                                s.concat, s.nblk);
     WN_LAUNCH_CHECK(h);
   }
   return WN_OK;
@@ -616,9 +664,14 @@ static int make_tmap(CUtensorMap* tm, void* base, int planes_total, int N, int H
   return WN_OK;
 }
 
-template <int KS, int CIN_PAD, int NPAD, int S, int AS, int EPI>
+template <int KS, int CIN_PAD, int NPAD, int S, int AS, int EPI, int CONCAT = 0, int NBLK = 1>
 static int launch_umma(wn_handle* h, int li, void* in_base, ConvArgs a, cudaStream_t stream) {
-  using C = UmmaCfg<KS, CIN_PAD, NPAD, S, AS>;
+  using C = UmmaCfg<KS, CIN_PAD, NPAD, S, AS, CONCAT, NBLK>;
+  const UmmaLayerSpec& spec = kSpecs[li];
+  if (spec.ks != KS || spec.cinpad != CIN_PAD || spec.npad != NPAD || spec.concat != CONCAT || spec.nblk != NBLK) {
+    set_error("internal: launch configuration of layer %d does not match its packed weights", li);
+    return WN_E_STATE;
+  }
   CUtensorMap tm;
   int rc = make_tmap(&tm, in_base, 2 * (CIN_PAD / 8), a.N, a.H, a.W, C::HALO_W, C::HALO_H);
   if (rc) return rc;
@@ -628,7 +681,7 @@ static int launch_umma(wn_handle* h, int li, void* in_base, ConvArgs a, cudaStre
   a.tiles_x = (a.W + C::TILE_W - 1) / C::TILE_W;
   a.tiles_y = (a.H + C::TILE_H - 1) / C::TILE_H;
   const long long tiles = (long long)a.tiles_x * a.tiles_y * a.N;
-  auto kern = conv_umma_kernel<KS, CIN_PAD, NPAD, S, AS, EPI>;
+  auto kern = conv_umma_kernel<KS, CIN_PAD, NPAD, S, AS, EPI, CONCAT, NBLK>;
   WN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
   int grid = (int)(tiles < h->sm_count ? tiles : h->sm_count);
   TimedScope ts(h, kSpecs[li].slot, stream);
@@ -702,26 +755,26 @@ static int umma_forward_chunk(wn_handle* h, const float* const in[4], const int6
   if ((rc = launch_umma<3, 128, 128, 4, 1, kEpiAct>(h, kC3, cmgB, a, stream))) return rc;
   if (dump(2, cmgA, 128)) return WN_OK;
   act(cmgB, 64, nullptr, 0);
-  if ((rc = launch_umma<1, 128, 64, 4, 2, kEpiAct>(h, kC4, cmgA, a, stream))) return rc;
+  if ((rc = launch_umma<1, 128, 64, 2, 2, kEpiAct, 1>(h, kC4, cmgA, a, stream))) return rc;
   if (dump(3, cmgB, 64)) return WN_OK;
   act(cmgA, 64, nullptr, 0);
-  if ((rc = launch_umma<7, 64, 64, 4, 2, kEpiAct>(h, kC5, cmgB, a, stream))) return rc;
+  if ((rc = launch_umma<7, 64, 64, 4, 1, kEpiAct, 1>(h, kC5, cmgB, a, stream))) return rc;
   if (dump(4, cmgA, 64)) return WN_OK;
   act(cmgB, 64, nullptr, 0);
-  if ((rc = launch_umma<5, 64, 64, 4, 2, kEpiAct>(h, kC6, cmgA, a, stream))) return rc;
+  if ((rc = launch_umma<5, 64, 64, 4, 1, kEpiAct, 1>(h, kC6, cmgA, a, stream))) return rc;
   if (dump(5, cmgB, 64)) return WN_OK;
   act(cmgA, 64, nullptr, 0);
-  if ((rc = launch_umma<3, 64, 64, 4, 2, kEpiAct>(h, kC7, cmgB, a, stream))) return rc;
+  if ((rc = launch_umma<3, 64, 64, 2, 2, kEpiAct, 1>(h, kC7, cmgB, a, stream))) return rc;
   if (dump(6, cmgA, 64)) return WN_OK;
   a.out_f32 = dbg_layer == 7 ? dbg_dst : cm;
-  if ((rc = launch_umma<3, 64, 16, 4, 2, kEpiSigmoid>(h, kC8, cmgA, a, stream))) return rc;
+  if ((rc = launch_umma<3, 64, 16, 4, 2, kEpiSigmoid, 1>(h, kC8, cmgA, a, stream))) return rc;
   if (dbg_layer == 7) return WN_OK;
   act(refB, 96, nullptr, 0);
-  if ((rc = launch_umma<5, 96, 96, 4, 1, kEpiAct>(h, kR2, refA, a, stream))) return rc;
+  if ((rc = launch_umma<5, 96, 32, 2, 1, kEpiAct, 1, 3>(h, kR2, refA, a, stream))) return rc;
   if (dump(9, refB, 96)) return WN_OK;
   a.out_f32 = out;
   a.cm = cm;
-  if ((rc = launch_umma<3, 96, 16, 4, 2, kEpiGate>(h, kR3, refB, a, stream))) return rc;
+  if ((rc = launch_umma<3, 96, 16, 4, 2, kEpiGate, 1>(h, kR3, refB, a, stream))) return rc;
   return WN_OK;
 }
 

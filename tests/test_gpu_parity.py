@@ -259,6 +259,7 @@ def test_training_step_gradients_match_torch_graph():
     assert torch.allclose(out.double(), out64, rtol=1e-4, atol=1e-6)
     # the backward pass re-evaluates the graph with torch's fp32 convolutions (TF32 on by default,
     # like the reference on a GPU: SURVEY appendix B.8), hence the looser gradient tolerance
-    g2 = m64.cmg.conv1.weight.grad
-    assert torch.allclose(g1.double(), g2, rtol=5e-2, atol=1e-3 * g2.abs().max().item())
-    assert torch.allclose(g1r.double(), m64.gc_refiner.conv3.bias.grad, rtol=5e-2, atol=1e-6)
+    def rel(a, b):
+        return ((a.double() - b).norm() / b.norm()).item()
+    assert rel(g1, m64.cmg.conv1.weight.grad) < 2e-2
+    assert rel(g1r, m64.gc_refiner.conv3.bias.grad) < 2e-2

@@ -26,6 +26,8 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace wn {
@@ -123,8 +125,8 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
         "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
         "=r"(v[15])
       : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ bool elect_one_sync() {
   uint32_t pred;
   asm volatile(
@@ -155,17 +157,23 @@ constexpr int kThreads = 256;
 //        N = NPAD.  Pays when NPAD <= 64, where an MMA is bound by the 4 KB A-operand read.
 // NBLK   number of diagonal blocks (the three refiners run as one block-diagonal layer): input
 //        chunk c only feeds block c / (NCHUNK / NBLK), so only that block's weights are staged.
-template <int KS, int CIN_PAD, int NPAD, int S, int AS, int CONCAT = 0, int NBLK = 1>
+// TPS    filter taps per weight stage: small-N layers batch a kernel row (or all taps) per stage so
+//        that the per-stage pipeline cost (barrier wait, commit, bulk-copy latency) is amortised.
+template <int KS, int CIN_PAD, int NPAD, int S, int AS, int CONCAT = 0, int NBLK = 1, int TPS = 1>
 struct UmmaCfg {
   static constexpr int TILE_W = kSubW * S, TILE_H = kSubH;
   static constexpr int HALO_W = TILE_W + KS - 1, HALO_H = TILE_H + KS - 1;
   static constexpr int NCHUNK = CIN_PAD / 16;
   static constexpr int PLANE_BYTES = HALO_W * HALO_H * 16;
   static constexpr int A_STAGE = (4 * PLANE_BYTES + 1023) / 1024 * 1024;  // hi k0, hi k1, lo k0, lo k1
-  static constexpr int B_STAGE = NPAD * 64;                                // [hi|lo][k8 0|1][NPAD][16 B]
-  static constexpr int NB = NPAD > 128 ? 4 : 6;
+  static constexpr int B_TAP = NPAD * 64;                                  // one tap: [hi|lo][k8 0|1][NPAD][16 B]
+  static constexpr int B_STAGE = TPS * B_TAP;
+  static constexpr int NSTAGE_PER_CHUNK = KS * KS / TPS;
+  static constexpr int NB_FIT = (64 * 1024) / B_STAGE;
+  static constexpr int NB = NB_FIT > 6 ? 6 : NB_FIT < 2 ? 2 : NB_FIT;
   static constexpr int BUDGET = 225 * 1024 - 2048;
   static constexpr int NA_FIT = (BUDGET - NB * B_STAGE) / A_STAGE;
+  static_assert((KS * KS) % TPS == 0, "taps per stage must divide the tap count");
   static constexpr int NA = NA_FIT > 3 ? 3 : NA_FIT;
   static constexpr int CPB = NCHUNK / NBLK;                // chunks per diagonal block
   static constexpr int N1 = CONCAT ? 2 * NPAD : NPAD;      // UMMA N of the a_hi pass
@@ -206,10 +214,10 @@ __device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b
   return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
 }
 
-template <int KS, int CIN_PAD, int NPAD, int S, int AS, int EPI, int CONCAT, int NBLK>
+template <int KS, int CIN_PAD, int NPAD, int S, int AS, int EPI, int CONCAT, int NBLK, int TPS>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) {
-  using C = UmmaCfg<KS, CIN_PAD, NPAD, S, AS, CONCAT, NBLK>;
+  using C = UmmaCfg<KS, CIN_PAD, NPAD, S, AS, CONCAT, NBLK, TPS>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* a_stages = smem;
@@ -273,7 +281,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        for (int it = 0; it < C::NCHUNK * KS * KS; it++) {
+        for (int it = 0; it < C::NCHUNK * C::NSTAGE_PER_CHUNK; it++) {
           mbar_wait(&b_empty[stage], phase ^ 1);
           mbar_expect_tx(&b_full[stage], C::B_STAGE);
           bulk_load(b_stages + stage * C::B_STAGE, g.wpk + (size_t)it * C::B_STAGE, C::B_STAGE, &b_full[stage]);
@@ -307,32 +315,37 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
           const uint32_t a_lo32 = (smem_u32(a_stages + astage * C::A_STAGE) >> 4) | ((uint32_t)(C::PLANE_BYTES >> 4) << 16);
           const int blk = NBLK > 1 ? c / C::CPB : 0;
           const uint32_t d_base = d_tile + (uint32_t)(blk * C::BLK_COLS);
-          for (int tap = 0; tap < KS * KS; tap++) {
+          for (int tg = 0; tg < C::NSTAGE_PER_CHUNK; tg++) {
             mbar_wait(&b_full[bstage], bphase);
             tc_fence_after();
-            const int ky = tap / KS, kx = tap - ky * KS;
-            const uint32_t b_lo32 = (smem_u32(b_stages + bstage * C::B_STAGE) >> 4) | ((b_lbo >> 4) << 16);
-            const uint32_t a_tap = a_lo32 + (uint32_t)(ky * C::HALO_W + kx);
-            const uint32_t first = ((NBLK > 1 ? c % C::CPB : c) | tap) == 0 ? 0u : 1u;
+            const uint32_t b_stage32 = (smem_u32(b_stages + bstage * C::B_STAGE) >> 4) | ((b_lbo >> 4) << 16);
             if (elect_one_sync()) {
-              // pass-major order: consecutive MMAs target different accumulators
               constexpr uint32_t a_lo_off = (uint32_t)(2 * C::PLANE_BYTES >> 4);
 #pragma unroll
-              for (int s = 0; s < S; s++)  // a_hi x w_hi (CONCAT: x [w_hi | w_lo])
-                umma_bf16_split(d_base + (uint32_t)(s * C::SUB_COLS), a_tap + (uint32_t)(s * kSubW), a_hi32, b_lo32,
-                                b_hi32, idesc1, first);
+              for (int t = 0; t < TPS; t++) {
+                const int tap = tg * TPS + t;
+                const int ky = tap / KS, kx = tap - ky * KS;
+                const uint32_t b_lo32 = b_stage32 + (uint32_t)(t * (C::B_TAP >> 4));
+                const uint32_t a_tap = a_lo32 + (uint32_t)(ky * C::HALO_W + kx);
+                const uint32_t first = ((NBLK > 1 ? c % C::CPB : c) | tap) == 0 ? 0u : 1u;
+                // pass-major order: consecutive MMAs target different accumulators
 #pragma unroll
-              for (int s = 0; s < S; s++)  // a_lo x w_hi
-                umma_bf16_split(d_base + (uint32_t)(s * C::SUB_COLS), a_tap + (uint32_t)(s * kSubW) + a_lo_off, a_hi32,
-                                b_lo32, b_hi32, idesc2, 1u);
-              if constexpr (!CONCAT) {
+                for (int s = 0; s < S; s++)  // a_hi x w_hi (CONCAT: x [w_hi | w_lo])
+                  umma_bf16_split(d_base + (uint32_t)(s * C::SUB_COLS), a_tap + (uint32_t)(s * kSubW), a_hi32, b_lo32,
+                                  b_hi32, idesc1, first);
 #pragma unroll
-                for (int s = 0; s < S; s++)  // a_hi x w_lo
-                  umma_bf16_split(d_base + (uint32_t)(s * C::SUB_COLS), a_tap + (uint32_t)(s * kSubW), a_hi32,
-                                  b_lo32 + (uint32_t)(2 * NPAD * 16 >> 4), b_hi32, idesc2, 1u);
+                for (int s = 0; s < S; s++)  // a_lo x w_hi
+                  umma_bf16_split(d_base + (uint32_t)(s * C::SUB_COLS), a_tap + (uint32_t)(s * kSubW) + a_lo_off,
+                                  a_hi32, b_lo32, b_hi32, idesc2, 1u);
+                if constexpr (!CONCAT) {
+#pragma unroll
+                  for (int s = 0; s < S; s++)  // a_hi x w_lo
+                    umma_bf16_split(d_base + (uint32_t)(s * C::SUB_COLS), a_tap + (uint32_t)(s * kSubW), a_hi32,
+                                    b_lo32 + (uint32_t)(2 * NPAD * 16 >> 4), b_hi32, idesc2, 1u);
+                }
               }
               umma_commit(&b_empty[bstage]);
-              if (tap == KS * KS - 1) {
+              if (tg == C::NSTAGE_PER_CHUNK - 1) {
                 umma_commit(&a_empty[astage]);
                 if (c == C::NCHUNK - 1) umma_commit(&t_full[acc]);
               }
@@ -363,54 +376,58 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
         const int gx = tx * C::TILE_W + s * kSubW + px;
         const bool inside = gx < g.W && gy < g.H;
         const uint32_t t_addr = tmem_base + lane_base + (uint32_t)((acc * S + s) * C::SUB_COLS);
-        // 16 accumulator columns starting at output channel ch0 (+ the a_hi x w_lo half when CONCAT)
-        auto load16 = [&](int ch0, float* f) {
+        // NC accumulator columns starting at output channel ch0 (+ the a_hi x w_lo half when CONCAT);
+        // all TMEM loads of a group are in flight before the single wait
+        auto load_cols = [&](int ch0, float* f, auto nc_tag) {
+          constexpr int NC = decltype(nc_tag)::value;
           const int blk = NBLK > 1 ? ch0 / NPAD : 0;
           const uint32_t col = (uint32_t)(blk * C::BLK_COLS + (NBLK > 1 ? ch0 % NPAD : ch0));
-          uint32_t v[16];
-          tmem_ld16(t_addr + col, v);
+          uint32_t v[NC], w[CONCAT ? NC : 1];
 #pragma unroll
-          for (int j = 0; j < 16; j++) f[j] = __uint_as_float(v[j]);
+          for (int q = 0; q < NC; q += 16) tmem_ld16(t_addr + col + q, v + q);
           if constexpr (CONCAT) {
-            tmem_ld16(t_addr + col + NPAD, v);
 #pragma unroll
-            for (int j = 0; j < 16; j++) f[j] += __uint_as_float(v[j]);
+            for (int q = 0; q < NC; q += 16) tmem_ld16(t_addr + col + NPAD + q, w + q);
           }
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < NC; j++) f[j] = __uint_as_float(v[j]) + (CONCAT ? __uint_as_float(w[CONCAT ? j : 0]) : 0.f);
         };
         if constexpr (EPI == kEpiAct) {
+          constexpr int GC = 32;  // channels per group
+          static_assert((NBLK * NPAD) % GC == 0 && (NBLK == 1 || NPAD % GC == 0), "channel groups of 32");
 #pragma unroll 1
-          for (int c0 = 0; c0 < NBLK * NPAD; c0 += 16) {
-            float f[16];
-            load16(c0, f);
+          for (int c0 = 0; c0 < NBLK * NPAD; c0 += GC) {
+            float f[GC];
+            load_cols(c0, f, std::integral_constant<int, GC>{});
             if (c0 < g.cout && inside) {
-              uint32_t hi[8], lo[8];
-#pragma unroll
-              for (int j = 0; j < 16; j += 2) {
-                float f0 = fmaxf(f[j] + s_bias[c0 + j], 0.f);
-                float f1 = fmaxf(f[j + 1] + s_bias[c0 + j + 1], 0.f);
-                __nv_bfloat16 h0 = __float2bfloat16_rn(f0), h1 = __float2bfloat16_rn(f1);
-                __nv_bfloat16 l0 = __float2bfloat16_rn(f0 - __bfloat162float(h0));
-                __nv_bfloat16 l1 = __float2bfloat16_rn(f1 - __bfloat162float(h1));
-                hi[j >> 1] = pack_bf16x2(h0, h1);
-                lo[j >> 1] = pack_bf16x2(l0, l1);
-              }
-              const bool second = c0 >= g.split_c;
-              const ActDst& d = second ? g.dst1 : g.dst0;
-              const int plane = ((second ? c0 - g.split_c : c0) >> 3);
-              const size_t img = (size_t)n * 2 * d.planes_half;
               const size_t pix = (size_t)gy * g.W + gx;
               const size_t hw = (size_t)g.H * g.W;
-              uint4* p_hi = d.base + (img + plane) * hw + pix;
-              uint4* p_lo = d.base + (img + d.planes_half + plane) * hw + pix;
-              p_hi[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-              p_hi[hw] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-              p_lo[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-              p_lo[hw] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+#pragma unroll
+              for (int q = 0; q < GC; q += 8) {  // one 8-channel plane at a time
+                const int ch = c0 + q;
+                uint32_t hi[4], lo[4];
+#pragma unroll
+                for (int j = 0; j < 8; j += 2) {
+                  float f0 = fmaxf(f[q + j] + s_bias[ch + j], 0.f);
+                  float f1 = fmaxf(f[q + j + 1] + s_bias[ch + j + 1], 0.f);
+                  __nv_bfloat16 h0 = __float2bfloat16_rn(f0), h1 = __float2bfloat16_rn(f1);
+                  hi[j >> 1] = pack_bf16x2(h0, h1);
+                  lo[j >> 1] = pack_bf16x2(__float2bfloat16_rn(f0 - __bfloat162float(h0)),
+                                           __float2bfloat16_rn(f1 - __bfloat162float(h1)));
+                }
+                const bool second = ch >= g.split_c;
+                const ActDst& d = second ? g.dst1 : g.dst0;
+                const int plane = (second ? ch - g.split_c : ch) >> 3;
+                uint4* p_hi = d.base + ((size_t)n * 2 * d.planes_half + plane) * hw + pix;
+                p_hi[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                p_hi[(size_t)d.planes_half * hw] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+              }
             }
           }
         } else {
           float f[16];
-          load16(0, f);
+          load_cols(0, f, std::integral_constant<int, 16>{});
           if (inside) {
             const size_t hw = (size_t)g.H * g.W;
             const size_t o = (size_t)n * 3 * hw + (size_t)gy * g.W + gx;
@@ -664,9 +681,9 @@ static int make_tmap(CUtensorMap* tm, void* base, int planes_total, int N, int H
   return WN_OK;
 }
 
-template <int KS, int CIN_PAD, int NPAD, int S, int AS, int EPI, int CONCAT = 0, int NBLK = 1>
+template <int KS, int CIN_PAD, int NPAD, int S, int AS, int EPI, int CONCAT = 0, int NBLK = 1, int TPS = 1>
 static int launch_umma(wn_handle* h, int li, void* in_base, ConvArgs a, cudaStream_t stream) {
-  using C = UmmaCfg<KS, CIN_PAD, NPAD, S, AS, CONCAT, NBLK>;
+  using C = UmmaCfg<KS, CIN_PAD, NPAD, S, AS, CONCAT, NBLK, TPS>;
   const UmmaLayerSpec& spec = kSpecs[li];
   if (spec.ks != KS || spec.cinpad != CIN_PAD || spec.npad != NPAD || spec.concat != CONCAT || spec.nblk != NBLK) {
     set_error("internal: launch configuration of layer %d does not match its packed weights", li);
@@ -681,7 +698,7 @@ static int launch_umma(wn_handle* h, int li, void* in_base, ConvArgs a, cudaStre
   a.tiles_x = (a.W + C::TILE_W - 1) / C::TILE_W;
   a.tiles_y = (a.H + C::TILE_H - 1) / C::TILE_H;
   const long long tiles = (long long)a.tiles_x * a.tiles_y * a.N;
-  auto kern = conv_umma_kernel<KS, CIN_PAD, NPAD, S, AS, EPI, CONCAT, NBLK>;
+  auto kern = conv_umma_kernel<KS, CIN_PAD, NPAD, S, AS, EPI, CONCAT, NBLK, TPS>;
   WN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
   int grid = (int)(tiles < h->sm_count ? tiles : h->sm_count);
   TimedScope ts(h, kSpecs[li].slot, stream);
@@ -749,32 +766,32 @@ static int umma_forward_chunk(wn_handle* h, const float* const in[4], const int6
   if ((rc = launch_umma<7, 16, 224, 2, 1, kEpiAct>(h, kL1, act0, a, stream))) return rc;
   if (dump(0, cmgA, 128) || dump(8, refA, 96)) return WN_OK;
   act(cmgB, 128, nullptr, 0);
-  if ((rc = launch_umma<5, 128, 128, 4, 1, kEpiAct>(h, kC2, cmgA, a, stream))) return rc;
+  if ((rc = launch_umma<5, 128, 128, 2, 2, kEpiAct>(h, kC2, cmgA, a, stream))) return rc;
   if (dump(1, cmgB, 128)) return WN_OK;
   act(cmgA, 128, nullptr, 0);
-  if ((rc = launch_umma<3, 128, 128, 4, 1, kEpiAct>(h, kC3, cmgB, a, stream))) return rc;
+  if ((rc = launch_umma<3, 128, 128, 2, 2, kEpiAct>(h, kC3, cmgB, a, stream))) return rc;
   if (dump(2, cmgA, 128)) return WN_OK;
   act(cmgB, 64, nullptr, 0);
   if ((rc = launch_umma<1, 128, 64, 2, 2, kEpiAct, 1>(h, kC4, cmgA, a, stream))) return rc;
   if (dump(3, cmgB, 64)) return WN_OK;
   act(cmgA, 64, nullptr, 0);
-  if ((rc = launch_umma<7, 64, 64, 4, 1, kEpiAct, 1>(h, kC5, cmgB, a, stream))) return rc;
+  if ((rc = launch_umma<7, 64, 64, 2, 2, kEpiAct, 1, 1, 7>(h, kC5, cmgB, a, stream))) return rc;
   if (dump(4, cmgA, 64)) return WN_OK;
   act(cmgB, 64, nullptr, 0);
-  if ((rc = launch_umma<5, 64, 64, 4, 1, kEpiAct, 1>(h, kC6, cmgA, a, stream))) return rc;
+  if ((rc = launch_umma<5, 64, 64, 2, 2, kEpiAct, 1, 1, 5>(h, kC6, cmgA, a, stream))) return rc;
   if (dump(5, cmgB, 64)) return WN_OK;
   act(cmgA, 64, nullptr, 0);
-  if ((rc = launch_umma<3, 64, 64, 2, 2, kEpiAct, 1>(h, kC7, cmgB, a, stream))) return rc;
+  if ((rc = launch_umma<3, 64, 64, 2, 2, kEpiAct, 1, 1, 3>(h, kC7, cmgB, a, stream))) return rc;
   if (dump(6, cmgA, 64)) return WN_OK;
   a.out_f32 = dbg_layer == 7 ? dbg_dst : cm;
-  if ((rc = launch_umma<3, 64, 16, 4, 2, kEpiSigmoid, 1>(h, kC8, cmgA, a, stream))) return rc;
+  if ((rc = launch_umma<3, 64, 16, 4, 2, kEpiSigmoid, 1, 1, 9>(h, kC8, cmgA, a, stream))) return rc;
   if (dbg_layer == 7) return WN_OK;
   act(refB, 96, nullptr, 0);
-  if ((rc = launch_umma<5, 96, 32, 2, 1, kEpiAct, 1, 3>(h, kR2, refA, a, stream))) return rc;
+  if ((rc = launch_umma<5, 96, 32, 2, 1, kEpiAct, 1, 3, 5>(h, kR2, refA, a, stream))) return rc;
   if (dump(9, refB, 96)) return WN_OK;
   a.out_f32 = out;
   a.cm = cm;
-  if ((rc = launch_umma<3, 96, 16, 4, 2, kEpiGate, 1>(h, kR3, refB, a, stream))) return rc;
+  if ((rc = launch_umma<3, 96, 16, 4, 2, kEpiGate, 1, 1, 9>(h, kR3, refB, a, stream))) return rc;
   return WN_OK;
 }
 

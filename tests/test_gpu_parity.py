@@ -51,8 +51,8 @@ def test_preprocess_bit_exact_vs_golden(eng, path):
         assert np.array_equal(res[key].cpu().numpy(), opre.arr2ten(arr)), key
 
 
-@pytest.mark.parametrize("shape", [(112, 112), (113, 117), (112, 117), (115, 112), (9, 11), (16, 9), (8, 8),
-                                   (64, 512), (270, 480), (1080, 1920)])
+@pytest.mark.parametrize("shape", [(112, 112), (113, 117), (112, 117), (115, 112), (9, 11), (16, 9), (8, 8), (7, 5),
+                                   (3, 4), (64, 512), (270, 480), (1080, 1920)])
 @pytest.mark.parametrize("kind", ["noise", "smooth"])
 def test_preprocess_bit_exact_vs_oracle(eng, shape, kind):
     rgb = ofw.synthetic_image(7 + shape[0], shape[0], shape[1], kind)
@@ -116,7 +116,8 @@ def test_forward_vs_golden(path, precision):
 
 
 @pytest.mark.parametrize("precision", MODES)
-@pytest.mark.parametrize("shape", [(1, 16, 16), (2, 33, 47), (1, 8, 200), (3, 64, 40), (1, 130, 70)])
+@pytest.mark.parametrize("shape", [(1, 16, 16), (2, 33, 47), (1, 8, 200), (3, 64, 40), (1, 130, 70), (1, 1, 1), (2, 3, 5),
+                                   (1, 1, 40), (1, 17, 2)])
 def test_forward_vs_oracle_ragged_shapes(precision, shape):
     n, h, w = shape
     torch.manual_seed(h * w)
@@ -141,6 +142,22 @@ def test_forward_accepts_channels_last_strides(precision):
         a = m(*strided)
         b = m(*[t.contiguous() for t in strided])
     assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("precision", MODES)
+def test_first_layer_fast_path_equals_general_path(precision):
+    """8-bit image levels take the 2-pass first layer; a perturbed copy takes the general 3-pass one."""
+    rgb = ofw.synthetic_image(8, 48, 64, "smooth")
+    sd = ofw.synthetic_state_dict(4, 3.0)
+    ins = _inputs_from_rgb([rgb])
+    m = _model(4, 3.0, precision)
+    with torch.no_grad():
+        exact = m(*[t.cuda() for t in ins]).cpu().numpy()
+        bumped = [t.clone() for t in ins]
+        bumped[0][0, 0, 0, 0] += 1e-3  # one non-level value disables the fast path for the whole batch
+        general = m(*[t.cuda() for t in bumped]).cpu().numpy()
+    _assert_close(exact, ofw.waternet_forward(sd, *ins, dtype=torch.float64).numpy())
+    _assert_close(general, ofw.waternet_forward(sd, *bumped, dtype=torch.float64).numpy())
 
 
 @pytest.mark.parametrize("precision", MODES)

@@ -208,6 +208,9 @@ struct ConvArgs {
   // kEpiSigmoid / kEpiGate
   float* out_f32;       // [n][3][H][W]
   const float* cm;      // [n][3][H][W] (gate)
+  // optional: *skip_lo != 0 means every input value is exactly representable in the hi plane
+  // (8-bit image levels), so the a_lo x w_hi pass contributes nothing and is not issued
+  const int* skip_lo;
 };
 
 __device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b) {
@@ -303,6 +306,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
       constexpr uint32_t b_lbo = (uint32_t)((CONCAT ? 2 * NPAD : NPAD) * 16);
       int astage = 0, bstage = 0, acc = 0;
       uint32_t aphase = 0, bphase = 0, tphase = 0;
+      const bool skip_lo = g.skip_lo != nullptr && *g.skip_lo != 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         mbar_wait(&t_empty[acc], tphase ^ 1);
         tc_fence_after();
@@ -333,10 +337,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
                 for (int s = 0; s < S; s++)  // a_hi x w_hi (CONCAT: x [w_hi | w_lo])
                   umma_bf16_split(d_base + (uint32_t)(s * C::SUB_COLS), a_tap + (uint32_t)(s * kSubW), a_hi32, b_lo32,
                                   b_hi32, idesc1, first);
+                if (!skip_lo) {
 #pragma unroll
-                for (int s = 0; s < S; s++)  // a_lo x w_hi
-                  umma_bf16_split(d_base + (uint32_t)(s * C::SUB_COLS), a_tap + (uint32_t)(s * kSubW) + a_lo_off,
-                                  a_hi32, b_lo32, b_hi32, idesc2, 1u);
+                  for (int s = 0; s < S; s++)  // a_lo x w_hi
+                    umma_bf16_split(d_base + (uint32_t)(s * C::SUB_COLS), a_tap + (uint32_t)(s * kSubW) + a_lo_off,
+                                    a_hi32, b_lo32, b_hi32, idesc2, 1u);
+                }
                 if constexpr (!CONCAT) {
 #pragma unroll
                   for (int s = 0; s < S; s++)  // a_hi x w_lo
@@ -469,14 +475,15 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
 // ------------------------------------------------------------------------------------------
 // scatter one OIHW fp32 tensor into a dense [npad][cinpad][ks*ks] fp32 block-matrix
 __global__ void scatter_weights_kernel(const float* __restrict__ src, float* __restrict__ dense, int co, int ci,
-                                       int kk, int cinpad, int row_off, int split, int base0, int base1) {
+                                       int kk, int cinpad, int row_off, int split, int base0, int base1,
+                                       float divisor) {
   const int total = co * ci * kk;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     int t = i % kk;
     int c = (i / kk) % ci;
     int o = i / (kk * ci);
     int cd = c < split ? base0 + c : base1 + (c - split);
-    dense[((size_t)(row_off + o) * cinpad + cd) * kk + t] = src[i];
+    dense[((size_t)(row_off + o) * cinpad + cd) * kk + t] = __fdiv_rn(src[i], divisor);
   }
 }
 __global__ void scatter_bias_kernel(const float* __restrict__ src, float* __restrict__ dst, int co, int row_off) {
@@ -512,36 +519,47 @@ __global__ void pack_stages_kernel(const float* __restrict__ dense, __nv_bfloat1
   }
 }
 
-// torch.cat([x, wb, ce, gc], 1) (net.py:46) -> act planes: 16 channels (12 + 4 zero), bf16 hi/lo
+// torch.cat([x, wb, ce, gc], 1) (net.py:46) -> act planes: 16 channels (12 + 4 zero), bf16 hi/lo of
+// v*255.  Inputs that came from 8-bit images (arr2ten: u/255) give integers 0..255, exact in the
+// 8-bit bf16 significand: then lo == 0 and the first layer can drop its a_lo pass (flag stays set).
 struct PackInArgs {
   const float* p[4];
   long long s[4][4];
 };
-__global__ void __launch_bounds__(256) pack_inputs_kernel(PackInArgs a, uint4* __restrict__ out, int H, int W) {
+__global__ void __launch_bounds__(256) pack_inputs_kernel(PackInArgs a, uint4* __restrict__ out, int H, int W,
+                                                          int* __restrict__ exact_flag) {
   const int n = blockIdx.y;
   const int pix = blockIdx.x * 256 + threadIdx.x;
   const int hw = H * W;
-  if (pix >= hw) return;
-  const int y = pix / W, x = pix - y * W;
-  float v[16];
+  bool exact = true;
+  if (pix < hw) {
+    const int y = pix / W, x = pix - y * W;
+    float v[16];
 #pragma unroll
-  for (int t = 0; t < 4; t++)
+    for (int t = 0; t < 4; t++)
 #pragma unroll
-    for (int c = 0; c < 3; c++) v[t * 3 + c] = a.p[t][n * a.s[t][0] + c * a.s[t][1] + y * a.s[t][2] + x * a.s[t][3]];
-  v[12] = v[13] = v[14] = v[15] = 0.f;
-  uint32_t hi[8], lo[8];
+      for (int c = 0; c < 3; c++) {
+        float f = __fmul_rn(a.p[t][n * a.s[t][0] + c * a.s[t][1] + y * a.s[t][2] + x * a.s[t][3]], 255.0f);
+        float r = rintf(f);
+        if (fabsf(f - r) <= 0.0009765625f && r >= 0.f && r <= 255.f) f = r; else exact = false;
+        v[t * 3 + c] = f;
+      }
+    v[12] = v[13] = v[14] = v[15] = 0.f;
+    uint32_t hi[8], lo[8];
 #pragma unroll
-  for (int j = 0; j < 16; j += 2) {
-    __nv_bfloat16 h0 = __float2bfloat16_rn(v[j]), h1 = __float2bfloat16_rn(v[j + 1]);
-    hi[j >> 1] = pack_bf16x2(h0, h1);
-    lo[j >> 1] = pack_bf16x2(__float2bfloat16_rn(v[j] - __bfloat162float(h0)),
-                             __float2bfloat16_rn(v[j + 1] - __bfloat162float(h1)));
+    for (int j = 0; j < 16; j += 2) {
+      __nv_bfloat16 h0 = __float2bfloat16_rn(v[j]), h1 = __float2bfloat16_rn(v[j + 1]);
+      hi[j >> 1] = pack_bf16x2(h0, h1);
+      lo[j >> 1] = pack_bf16x2(__float2bfloat16_rn(v[j] - __bfloat162float(h0)),
+                               __float2bfloat16_rn(v[j + 1] - __bfloat162float(h1)));
+    }
+    uint4* o = out + (size_t)n * 4 * hw + pix;  // planes: hi0, hi1, lo0, lo1
+    o[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    o[hw] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+    o[2 * (size_t)hw] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    o[3 * (size_t)hw] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
   }
-  uint4* o = out + (size_t)n * 4 * hw + pix;  // planes: hi0, hi1, lo0, lo1
-  o[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-  o[hw] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-  o[2 * (size_t)hw] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-  o[3 * (size_t)hw] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+  if (!__syncthreads_and(exact) && threadIdx.x == 0) atomicExch(exact_flag, 0);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -611,8 +629,9 @@ int umma_pack_weights(wn_handle* h, const float* const* params, cudaStream_t str
     WN_CUDA(cudaMemsetAsync(u->dense, 0, (size_t)rows * s.cinpad * kk * sizeof(float), stream));
     WN_CUDA(cudaMemsetAsync(u->bias[li], 0, rows * sizeof(float), stream));
     auto scatter = [&](int conv, int co, int ci, int row_off, int split, int base0, int base1) -> int {
+      // the first layer consumes image levels 0..255 (see pack_inputs_kernel): fold the /255 into its weights
       scatter_weights_kernel<<<128, 256, 0, stream>>>(W(conv), u->dense, co, ci, kk, s.cinpad, row_off, split,
-                                                      base0, base1);
+                                                      base0, base1, li == kL1 ? 255.0f : 1.0f);
       WN_LAUNCH_CHECK(h);
       scatter_bias_kernel<<<1, 256, 0, stream>>>(B(conv), u->bias[li], co, row_off);
       WN_LAUNCH_CHECK(h);
@@ -733,7 +752,8 @@ static int umma_forward_chunk(wn_handle* h, const float* const in[4], const int6
   uint4* cmgB = (uint4*)ws;   ws += px * 512;
   uint4* refA = (uint4*)ws;   ws += px * 384;
   uint4* refB = (uint4*)ws;   ws += px * 384;
-  float* cm = (float*)ws;
+  float* cm = (float*)ws;     ws += px * 12;
+  int* exact_flag = (int*)(((uintptr_t)ws + 255) / 256 * 256);
 
   PackInArgs pa;
   for (int t = 0; t < 4; t++) {
@@ -742,7 +762,8 @@ static int umma_forward_chunk(wn_handle* h, const float* const in[4], const int6
   }
   {
     TimedScope ts(h, kSlotPack, stream);
-    pack_inputs_kernel<<<dim3((H * W + 255) / 256, n), 256, 0, stream>>>(pa, act0, H, W);
+    WN_CUDA(cudaMemsetAsync(exact_flag, 1, sizeof(int), stream));  // nonzero = "all inputs are 8-bit levels"
+    pack_inputs_kernel<<<dim3((H * W + 255) / 256, n), 256, 0, stream>>>(pa, act0, H, W, exact_flag);
     WN_LAUNCH_CHECK(h);
   }
   ConvArgs a;
@@ -763,7 +784,9 @@ static int umma_forward_chunk(wn_handle* h, const float* const in[4], const int6
   };
   // L1: 16 -> 128 (cmg) + 96 (refiners)
   act(cmgA, 128, refA, 96);
+  a.skip_lo = exact_flag;
   if ((rc = launch_umma<7, 16, 224, 2, 1, kEpiAct>(h, kL1, act0, a, stream))) return rc;
+  a.skip_lo = nullptr;
   if (dump(0, cmgA, 128) || dump(8, refA, 96)) return WN_OK;
   act(cmgB, 128, nullptr, 0);
   if ((rc = launch_umma<5, 128, 128, 2, 2, kEpiAct>(h, kC2, cmgA, a, stream))) return rc;

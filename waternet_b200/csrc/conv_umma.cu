@@ -17,7 +17,8 @@
 // out-of-image pixels come back as zeros from the TMA (padding="same").
 //
 // One persistent CTA per SM, warp-specialised:
-//   warps 0-3  epilogue  (TMEM -> registers -> bias/act -> bf16 hi/lo planes or fp32)
+//   warps 0-3, 8-11  epilogue, two groups that split a tile's sub-tiles
+//              (TMEM -> registers -> bias/act -> bf16 hi/lo planes or fp32)
 //   warp 4     A producer (TMA halo tiles, one 16-channel chunk per stage)
 //   warp 5     B producer (bulk copies of pre-packed weight stages, one (chunk,tap) per stage)
 //   warp 6     MMA issuer (one thread; 3 MMAs per sub-tile per stage)
@@ -149,7 +150,7 @@ __device__ __forceinline__ void tc_fence_after() {
 enum Epilogue { kEpiAct = 0, kEpiSigmoid = 1, kEpiGate = 2 };
 
 constexpr int kSubW = 8, kSubH = 16;  // one M=128 sub-tile: 8 px wide, 16 px tall
-constexpr int kThreads = 256;
+constexpr int kThreads = 384;  // warps 0-3 and 8-11: epilogue; 4: A producer; 5: B producer; 6: MMA; 7: TMEM
 
 // NPAD   output channels per diagonal block (UMMA N of the lo*hi pass)
 // CONCAT weight stage rows are [hi rows | lo rows]: a_hi x [w_hi|w_lo] is ONE MMA of N = 2*NPAD (the
@@ -241,7 +242,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
   if (tid == 0) {
     for (int i = 0; i < C::NA; i++) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < C::NB; i++) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-    for (int i = 0; i < AS; i++) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4); }
+    for (int i = 0; i < AS; i++) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int i = tid; i < NBLK * NPAD; i += kThreads) s_bias[i] = g.bias[i];
@@ -364,12 +365,15 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
         if (++acc == AS) { acc = 0; tphase ^= 1; }
       }
     }
-  } else if (warp < 4) {
+  } else if (warp < 4 || warp >= 8) {
     // ===================== epilogue =====================
+    // a warp may only touch TMEM lanes 32*(warp%4)..+31; the two groups take alternate sub-tiles
     int acc = 0;
     uint32_t tphase = 0;
-    const int px = tid & 7, py = tid >> 3;  // this thread's pixel inside a sub-tile (TMEM lane == tid)
-    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    const int egroup = warp >> 3, quarter = warp & 3;
+    const int row = quarter * 32 + lane;      // TMEM lane == pixel row of the sub-tile
+    const int px = row & 7, py = row >> 3;
+    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int n = tile / (g.tiles_x * g.tiles_y);
       const int rem = tile - n * g.tiles_x * g.tiles_y;
@@ -378,7 +382,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
       tc_fence_after();
       const int gy = ty * C::TILE_H + py;
 #pragma unroll 1
-      for (int s = 0; s < S; s++) {
+      for (int s = egroup; s < S; s += 2) {
         const int gx = tx * C::TILE_W + s * kSubW + px;
         const bool inside = gx < g.W && gy < g.H;
         const uint32_t t_addr = tmem_base + lane_base + (uint32_t)((acc * S + s) * C::SUB_COLS);

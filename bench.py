@@ -277,13 +277,24 @@ def main():
         imgs_per_launch = args.steps * B / n_launch
         macs = macs_by_slot[top]
         fused = [names_by_slot[top]]
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+        if mode != _lib.MODE_FP32_SIMT and os.path.exists(tpath):
+            with open(tpath) as f:
+                tj = json.load(f)
+            ent = tj["kernels"].get(fused[0])
+            if ent and (tj["height"], tj["width"]) == (H, W):  # measured per 1080p image; scales with images per launch
+                traffic = ent["dram_bytes_per_image"] * imgs_per_launch
         flops = 2.0 * macs * H * W * imgs_per_launch
         achieved = flops / (avg_ms * 1e-3) / 1e12
         peak = peaks["tf_sustained"]
         conv_total = sum(conv_ms)
         roofline = {
             "bound": "tensor", "kernel": "+".join(fused), "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-            "frac": achieved / peak, "traffic": None,
+            "frac": achieved / peak, "traffic": traffic,
+            "traffic_note": "DRAM bytes per launch from the committed ncu --set full capture (profiles/r1_traffic.json)",
+            "algorithmic_bytes_per_launch": 4.0 * H * W * imgs_per_launch * {
+                "cmg.conv2": 256, "cmg.conv3": 256, "cmg.conv5": 128, "cmg.conv6": 128}.get(fused[0], 0) or None,
             "peak_source": peaks["source"] + ", bf16 dense sustained (kernel timed inside a long step)",
             "avg_launch_ms": avg_ms, "launches_timed": n_launch, "share_of_step": conv_ms[top] / (ms_per_step * args.steps),
             "forward_all_convs": {"achieved": 2.0 * TOTAL_MACS * H * W * B * args.steps / (conv_total * 1e-3) / 1e12,

@@ -170,12 +170,16 @@ struct UmmaCfg {
   static constexpr int B_TAP = NPAD * 64;                                  // one tap: [hi|lo][k8 0|1][NPAD][16 B]
   static constexpr int B_STAGE = TPS * B_TAP;
   static constexpr int NSTAGE_PER_CHUNK = KS * KS / TPS;
-  static constexpr int NB_FIT = (64 * 1024) / B_STAGE;
-  static constexpr int NB = NB_FIT > 6 ? 6 : NB_FIT < 2 ? 2 : NB_FIT;
   static constexpr int BUDGET = 225 * 1024 - 2048;
+  // halo ring: enough stages to prefetch the next chunk (or the next tile when there is one chunk)
+  static constexpr int NA_WANT = NCHUNK == 1 ? 2 : 3;
+  // weight ring: whatever is left after the halo ring, 2..8 stages; deep rings hide the L2 latency of
+  // the bulk copies when a stage carries only a few MMAs (first layer: 14 KB per 4-6 MMAs)
+  static constexpr int NB_FIT = (BUDGET - NA_WANT * A_STAGE) / B_STAGE;
+  static constexpr int NB = NB_FIT > 8 ? 8 : NB_FIT < 2 ? 2 : NB_FIT;
   static constexpr int NA_FIT = (BUDGET - NB * B_STAGE) / A_STAGE;
+  static constexpr int NA = NA_FIT > NA_WANT ? NA_WANT : NA_FIT;
   static_assert((KS * KS) % TPS == 0, "taps per stage must divide the tap count");
-  static constexpr int NA = NA_FIT > 3 ? 3 : NA_FIT;
   static constexpr int CPB = NCHUNK / NBLK;                // chunks per diagonal block
   static constexpr int N1 = CONCAT ? 2 * NPAD : NPAD;      // UMMA N of the a_hi pass
   static constexpr int BLK_COLS = N1;                      // accumulator columns per block

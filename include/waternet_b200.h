@@ -15,6 +15,8 @@
  *   wn_postprocess_u8     hubconf.py:24-34         ten2arr_noeinops (clip, *255, truncate, NCHW->NHWC)
  *   wn_enhance_u8         hubconf.py:85-94 + net.py:99-108: preprocess -> model -> postprocess
  *                         (the per-frame body of inference.py:261-323)
+ *   wn_forward_train /    train.py:108 `out = model(...)` and train.py:130-131 `loss.backward()`
+ *   wn_backward           (autograd through net.py:99-108)
  *
  * Conventions: every data pointer is a DEVICE pointer on the handle's device
  * unless its name ends in _host; the caller owns every buffer (the handle only
@@ -104,6 +106,21 @@ size_t wn_enhance_workspace_bytes(int n, int h, int w, int mode);
 int wn_enhance_u8(wn_handle* h, const uint8_t* rgb, uint8_t* out_nhwc, float* out_f32_or_null,
                   int n, int height, int width, int mode, void* workspace, size_t workspace_bytes,
                   void* stream);
+
+/*
+ * Training step (reference train.py:100-133: out = model(...); loss.backward()).
+ * wn_forward_train is wn_forward (tensor-core mode) that additionally keeps every activation in
+ * `train_workspace`; wn_backward consumes that workspace and d(loss)/d(out) (fp32 contiguous NCHW)
+ * and OVERWRITES the 34 gradient tensors `grads` (device pointers, same order, shapes and layout as
+ * `params` of wn_pack_weights).  Gradients with respect to the four input images are not produced.
+ * The workspace must stay untouched between the two calls; n*h*w <= 8 Mi pixels per call.
+ */
+size_t wn_train_workspace_bytes(int n, int h, int w);
+int wn_forward_train(wn_handle* h, const float* x, const float* wb, const float* he, const float* gc,
+                     const int64_t in_strides[4][4], float* out, int n, int height, int width,
+                     void* train_workspace, size_t workspace_bytes, void* stream);
+int wn_backward(wn_handle* h, const float* grad_out, float* const* grads, int n, int height, int width,
+                void* train_workspace, size_t workspace_bytes, void* stream);
 
 /*
  * Per-kernel device timing (measurement aid for bench.py, off by default).  When on, every

@@ -280,3 +280,79 @@ def test_training_step_gradients_match_torch_graph():
         return ((a.double() - b).norm() / b.norm()).item()
     assert rel(g1, m64.cmg.conv1.weight.grad) < 2e-2
     assert rel(g1r, m64.gc_refiner.conv3.bias.grad) < 2e-2
+
+
+def _fp64_grads(sd, ins, target):
+    """Ground truth: float64 autograd through the functional oracle graph."""
+    import torch.nn.functional as F
+    params = {k: v.double().clone().requires_grad_(True) for k, v in sd.items()}
+    x, wb, he, gc = [t.double() for t in ins]
+
+    def conv(prefix, t, k):
+        return F.conv2d(t, params[prefix + ".weight"], params[prefix + ".bias"], padding=k // 2)
+
+    out = torch.cat([x, wb, he, gc], 1)
+    for name, _, _, k in ofw.CMG_LAYERS[:-1]:
+        out = F.relu(conv(f"cmg.{name}", out, k))
+    cm = torch.sigmoid(conv("cmg.conv8", out, 3))
+    total = 0
+    for r, (ref, other) in enumerate(zip(ofw.REFINERS, (wb, he, gc))):
+        t = torch.cat([x, other], 1)
+        for name, _, _, k in ofw.REFINER_LAYERS:
+            t = F.relu(conv(f"{ref}.{name}", t, k))
+        total = total + t * cm[:, r:r + 1]
+    loss = F.mse_loss(total, target.double())
+    loss.backward()
+    return total.detach(), {k: v.grad for k, v in params.items()}
+
+
+@pytest.mark.parametrize("shape", [(2, 24, 24), (1, 37, 53), (3, 16, 40)])
+def test_native_backward_matches_fp64_autograd(shape):
+    """wn_forward_train + wn_backward: all 34 parameter gradients against float64 autograd."""
+    n, h, w = shape
+    torch.manual_seed(h)
+    sd = ofw.synthetic_state_dict(5, 3.0)
+    m = _model(5, 3.0, "default").train()
+    rgbs = [ofw.synthetic_image(30 + i, h, w, "smooth") for i in range(n)]
+    ins = _inputs_from_rgb(rgbs)
+    target = torch.rand(n, 3, h, w)
+    out = m(*[t.cuda() for t in ins])
+    assert out.grad_fn is not None
+    torch.nn.functional.mse_loss(out, target.cuda()).backward()
+    ref_out, ref = _fp64_grads(sd, ins, target)
+    _assert_close(out.detach().cpu().numpy(), ref_out.numpy())
+    worst = 0.0
+    for (name, p) in m.named_parameters():
+        g, r = p.grad.double().cpu(), ref[name]
+        rel = ((g - r).norm() / r.norm().clamp_min(1e-30)).item()
+        worst = max(worst, rel)
+        assert rel < 2e-3, f"{name}: relative gradient error {rel:.2e}"
+    print(f"worst relative gradient error {worst:.2e}")
+
+
+def test_native_training_steps_track_the_torch_graph():
+    """A few Adam steps with native gradients follow the same loss curve as pure torch autograd."""
+    import copy
+    torch.manual_seed(0)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    base = _model(6, 1.0, "default").train()
+    twin = copy.deepcopy(base)
+    ins = [t.cuda() for t in _inputs_from_rgb([ofw.synthetic_image(40 + i, 32, 32, "smooth") for i in range(4)])]
+    target = torch.rand(4, 3, 32, 32).cuda()
+    opt_a = torch.optim.Adam(base.parameters(), lr=1e-3)
+    opt_b = torch.optim.Adam(twin.parameters(), lr=1e-3)
+    la, lb = [], []
+    for _ in range(5):
+        opt_a.zero_grad()
+        loss = torch.nn.functional.mse_loss(base(*ins), target)
+        loss.backward()
+        opt_a.step()
+        la.append(loss.item())
+        opt_b.zero_grad()
+        loss = torch.nn.functional.mse_loss(twin._graph(*ins), target)
+        loss.backward()
+        opt_b.step()
+        lb.append(loss.item())
+    assert la[-1] < la[0]
+    assert np.allclose(la, lb, rtol=2e-3), (la, lb)

@@ -54,8 +54,9 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo, uint3
   d |= 1ull << 46;  // descriptor version for sm_100
   return d;          // base_offset 0, lbo_mode 0, layout SWIZZLE_NONE
 }
-__host__ __device__ inline uint32_t make_idesc(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+__host__ __device__ inline uint32_t make_idesc(int M, int N, int mn_major = 0) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24) |
+         (mn_major ? (1u << 15) | (1u << 16) : 0u);
 }
 __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc,
                                           uint32_t idesc, uint32_t accumulate) {
@@ -93,6 +94,7 @@ struct MmaArgs {
   int reps;                      // >1: timing mode, repeat the K loop
   int b_region_off;              // where the B image starts in smem (>= a_bytes, 128B aligned)
   int nacc;                      // timing mode: rotate over this many accumulators
+  int mn_major;                  // operands are MN-major (K = slow index inside a core matrix)
 };
 
 // One CTA, 128 threads.  smem images are copied verbatim from global.
@@ -123,7 +125,7 @@ __global__ void __launch_bounds__(128) mma_probe_kernel(const uint8_t* a_img, co
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_base_s;
-  const uint32_t idesc = make_idesc(128, g.N);
+  const uint32_t idesc = make_idesc(128, g.N, g.mn_major);
   const uint32_t a_base = smem_u32(smem) + g.a_off;
   const uint32_t b_base = smem_u32(smem + g.b_region_off) + g.b_off;
   long long t0 = 0, t1 = 0;
@@ -184,15 +186,25 @@ static void put(std::vector<uint8_t>& img, uint32_t off, uint32_t lbo, uint32_t 
   memcpy(&img[b], &v, 2);
 }
 
+// MN-major no-swizzle image: element (mn, k) at (mn/8)*sbo + (k/8)*lbo + (k%8)*16 + (mn%8)*2
+static void put_mn(std::vector<uint8_t>& img, uint32_t off, uint32_t lbo, uint32_t sbo, int mn, int k, uint16_t v) {
+  size_t b = (size_t)off + (size_t)(mn / 8) * sbo + (size_t)(k / 8) * lbo + (k % 8) * 16 + (mn % 8) * 2;
+  if (b + 2 > img.size()) {
+    printf("image overflow\n");
+    exit(3);
+  }
+  memcpy(&img[b], &v, 2);
+}
+
 static int run_mma(const char* name, int N, int K, uint32_t a_off, uint32_t a_lbo, uint32_t a_sbo,
-                   uint32_t b_lbo, uint32_t b_sbo, bool swap_fields, int reps, int nacc = 1) {
+                   uint32_t b_lbo, uint32_t b_sbo, bool swap_fields, int reps, int nacc = 1, int mn_major = 0) {
   const int M = 128;
   std::vector<float> A((size_t)M * K), B((size_t)N * K);
   srand(1234);
   for (auto& v : A) v = bf2f(f2bf((rand() % 2001 - 1000) / 1000.0f));
   for (auto& v : B) v = bf2f(f2bf((rand() % 2001 - 1000) / 1000.0f));
   uint32_t a_bytes = a_off + (M / 8) * a_sbo + (K / 8) * a_lbo + 256;
-  uint32_t b_bytes = (N / 8) * b_sbo + (K / 8) * b_lbo + 256;
+  uint32_t b_bytes = a_off + (N / 8) * b_sbo + (K / 8) * b_lbo + 256;
   a_bytes = (a_bytes + 1023) / 1024 * 1024;
   b_bytes = (b_bytes + 1023) / 1024 * 1024;
   std::vector<uint8_t> ai(a_bytes, 0), bi(b_bytes, 0);
@@ -200,9 +212,11 @@ static int run_mma(const char* name, int N, int K, uint32_t a_off, uint32_t a_lb
   for (size_t i = 0; i + 1 < ai.size(); i += 2) { uint16_t p = f2bf(77.0f); memcpy(&ai[i], &p, 2); }
   for (size_t i = 0; i + 1 < bi.size(); i += 2) { uint16_t p = f2bf(55.0f); memcpy(&bi[i], &p, 2); }
   for (int r = 0; r < M; r++)
-    for (int k = 0; k < K; k++) put(ai, a_off, a_lbo, a_sbo, r, k, f2bf(A[(size_t)r * K + k]));
+    for (int k = 0; k < K; k++)
+      (mn_major ? put_mn : put)(ai, a_off, a_lbo, a_sbo, r, k, f2bf(A[(size_t)r * K + k]));
   for (int r = 0; r < N; r++)
-    for (int k = 0; k < K; k++) put(bi, 0, b_lbo, b_sbo, r, k, f2bf(B[(size_t)r * K + k]));
+    for (int k = 0; k < K; k++)
+      (mn_major ? put_mn : put)(bi, mn_major ? a_off : 0, b_lbo, b_sbo, r, k, f2bf(B[(size_t)r * K + k]));
   uint8_t *da, *db;
   float* dd;
   int* ds;
@@ -222,10 +236,11 @@ static int run_mma(const char* name, int N, int K, uint32_t a_off, uint32_t a_lb
   g.a_bytes = a_bytes;
   g.b_bytes = b_bytes;
   g.a_off = a_off;
-  g.b_off = 0;
+  g.b_off = mn_major ? a_off : 0;
   g.b_region_off = a_bytes;
   g.reps = reps;
   g.nacc = nacc;
+  g.mn_major = mn_major;
   if (!swap_fields) {
     g.a_lbo = a_lbo; g.a_sbo = a_sbo; g.b_lbo = b_lbo; g.b_sbo = b_sbo;
   } else {
@@ -393,6 +408,11 @@ int main(int argc, char** argv) {
   if (!strcmp(t, "n16")) return run_mma(t, 16, 64, 0, 128 * 16, 128, 16 * 16, 128, false, 1);
   if (!strcmp(t, "n256")) return run_mma(t, 256, 32, 0, 128 * 16, 128, 256 * 16, 128, false, 1);
   if (!strcmp(t, "tma")) return run_tma();
+  // wgrad-like: K = 16 consecutive pixels (16 B apart), MN = channels (8 per 16 B, planes SBO apart);
+  // LBO = 128 B between the two 8-pixel K groups; start address offset by a pixel shift (tap)
+  if (!strcmp(t, "mnmajor")) return run_mma(t, 128, 16, 0, 128, 4096, 128, 4096, false, 1, 1, 1);
+  if (!strcmp(t, "mnmajor_k64")) return run_mma(t, 128, 64, 0, 128, 4096, 128, 4096, false, 1, 1, 1);
+  if (!strcmp(t, "mnmajor_shift")) return run_mma(t, 64, 64, 7 * 16, 128, 4096 + 320, 128, 4096 + 320, false, 1, 1, 1);
   if (!strcmp(t, "rate2") && argc >= 5) {
     int N = atoi(argv[2]), reps = atoi(argv[3]), nacc = atoi(argv[4]);
     return run_mma("rate2", N, 64, (3 * 20 + 2) * 16, 560 * 16, 20 * 16, N * 16, 128, false, reps, nacc);

@@ -104,6 +104,7 @@ void wn_destroy(wn_handle* h) {
   DeviceGuard guard(h->device);
   simt_free(h);
   umma_free(h);
+  bwd_free(h);
   if (h->d_tables) cudaFree(h->d_tables);
   if (h->timing) {
     for (int i = 0; i < h->timing->created; i++) {
@@ -129,6 +130,8 @@ int wn_pack_weights(wn_handle* h, const float* const* params, void* stream) {
   int rc = simt_pack_weights(h, params, (cudaStream_t)stream);
   if (rc) return rc;
   rc = umma_pack_weights(h, params, (cudaStream_t)stream);
+  if (rc) return rc;
+  rc = bwd_pack_weights(h, params, (cudaStream_t)stream);
   if (rc) return rc;
   h->packed = true;
   return WN_OK;
@@ -248,6 +251,48 @@ int wn_enhance_u8(wn_handle* h, const uint8_t* rgb, uint8_t* out_nhwc, float* ou
 }
 
 uint64_t wn_launch_count(const wn_handle* h) { return h ? h->launches : 0; }
+
+size_t wn_train_workspace_bytes(int n, int h, int w) {
+  if (n <= 0 || h <= 0 || w <= 0) return 0;
+  return train_workspace_bytes_padded(n, h, w);
+}
+
+int wn_forward_train(wn_handle* h, const float* x, const float* wb, const float* he, const float* gc,
+                     const int64_t in_strides[4][4], float* out, int n, int height, int width,
+                     void* train_workspace, size_t workspace_bytes, void* stream) {
+  if (!h || !x || !wb || !he || !gc || !in_strides || !out || !train_workspace || n <= 0 || height <= 0 ||
+      width <= 0) {
+    set_error("wn_forward_train: bad argument");
+    return WN_E_INVALID;
+  }
+  if (!h->packed) {
+    set_error("wn_forward_train: wn_pack_weights has not been called");
+    return WN_E_STATE;
+  }
+  DeviceGuard guard(h->device);
+  const float* in[4] = {x, wb, he, gc};
+  return forward_train(h, in, in_strides, out, n, height, width, train_workspace, workspace_bytes,
+                       (cudaStream_t)stream);
+}
+
+int wn_backward(wn_handle* h, const float* grad_out, float* const* grads, int n, int height, int width,
+                void* train_workspace, size_t workspace_bytes, void* stream) {
+  if (!h || !grad_out || !grads || !train_workspace || n <= 0 || height <= 0 || width <= 0) {
+    set_error("wn_backward: bad argument");
+    return WN_E_INVALID;
+  }
+  for (int i = 0; i < WN_NUM_PARAMS; i++)
+    if (!grads[i]) {
+      set_error("wn_backward: grads[%d] is NULL", i);
+      return WN_E_INVALID;
+    }
+  if (!h->packed) {
+    set_error("wn_backward: wn_pack_weights has not been called");
+    return WN_E_STATE;
+  }
+  DeviceGuard guard(h->device);
+  return backward(h, grad_out, grads, n, height, width, train_workspace, workspace_bytes, (cudaStream_t)stream);
+}
 
 int wn_debug_forward_layer(wn_handle* h, const float* x, const float* wb, const float* he,
                            const float* gc, const int64_t in_strides[4][4], int n, int height,

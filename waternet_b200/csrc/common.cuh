@@ -55,6 +55,7 @@ struct SimtLayer {
 };
 
 struct UmmaWeights;  // conv_umma.cu
+struct UmmaBwd;      // conv_bwd.cu
 
 // Optional per-kernel timing with CUDA events on the launching stream (bench.py's roofline leg).
 enum TimingSlot {
@@ -86,6 +87,7 @@ struct wn_handle {
   wn::UmmaWeights* umma;
   int sm_count;
   wn::Timing* timing;
+  wn::UmmaBwd* bwd;
 };
 
 namespace wn {
@@ -135,6 +137,17 @@ int simt_debug_layer(wn_handle* h, const float* const in[4], const int64_t in_st
                      size_t workspace_bytes, cudaStream_t stream);
 
 // conv_umma.cu
+struct FwdBuffers {
+  uint4* act0;    // packed input, 16 channels (bf16 hi/lo planes of v*255)
+  uint4* a[8];    // a[l] = output of cmg.conv<l>, l = 1..7 (planes)
+  uint4* r[3];    // r[1], r[2] = refiner conv1 / conv2 outputs, three refiners side by side (96 channels)
+  float* cm;      // sigmoid confidence maps, fp32 [n][3][H][W]
+  float* refined; // optional: refined images after ReLU, fp32 [n][9][H][W]
+  int* exact_flag;
+};
+int umma_forward_layers(wn_handle* h, const float* const in[4], const int64_t st[4][4], float* out, int n,
+                        int height, int width, const FwdBuffers& b, cudaStream_t stream, int dbg_layer = -1,
+                        float* dbg_dst = nullptr);
 int umma_debug_layer(wn_handle* h, const float* const in[4], const int64_t in_strides[4][4], int n,
                      int height, int width, int layer, float* dst, void* workspace,
                      size_t workspace_bytes, cudaStream_t stream);
@@ -144,5 +157,14 @@ size_t umma_forward_workspace_bytes(int n, int h, int w);
 int umma_forward(wn_handle* h, const float* const in[4], const int64_t in_strides[4][4], float* out,
                  int n, int height, int width, void* workspace, size_t workspace_bytes,
                  cudaStream_t stream);
+
+// conv_bwd.cu
+int bwd_pack_weights(wn_handle* h, const float* const* params, cudaStream_t stream);
+void bwd_free(wn_handle* h);
+size_t train_workspace_bytes_padded(int n, int h, int w);
+int forward_train(wn_handle* h, const float* const in[4], const int64_t in_strides[4][4], float* out, int n,
+                  int height, int width, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+int backward(wn_handle* h, const float* grad_out, float* const* grads, int n, int height, int width,
+             void* workspace, size_t workspace_bytes, cudaStream_t stream);
 
 }  // namespace wn

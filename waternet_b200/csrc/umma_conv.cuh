@@ -1,0 +1,593 @@
+// tcgen05 implicit-GEMM convolution kernel shared by the forward (conv_umma.cu) and the backward
+// data-gradient pass (conv_bwd.cu).  See conv_umma.cu for the design notes.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include <type_traits>
+
+#include "common.cuh"
+
+namespace wn {
+
+// ------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+// Bounded wait: a pipeline bug becomes a trap ("unspecified launch failure"), never a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  for (uint32_t it = 0; it < (1u << 26); it++) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (done) return;
+  }
+  __trap();
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* tmap, uint64_t* bar, int c0,
+                                            int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+// shared-memory matrix descriptor: no swizzle, K-major.  LBO = byte distance between the two
+// 8-element K halves of a K=16 step, SBO = byte distance between 8-row groups.
+__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr >> 4) & 0x3fff);
+  d |= (uint64_t)((lbo >> 4) & 0x3fff) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3fff) << 32;
+  d |= 1ull << 46;
+  return d;
+}
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+  // c=f32 (bit 4), a=b=bf16 (bits 7, 10), K-major both, N>>3 at 17, M>>4 at 24
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Same, descriptors given as (lo, hi) 32-bit halves so that the per-MMA work is one add.
+__device__ __forceinline__ void umma_bf16_split(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                                uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
+        "=r"(v[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+
+// ------------------------------------------------------------------------------------------
+// Kernel configuration
+// ------------------------------------------------------------------------------------------
+// kEpiAct: bias + ReLU -> bf16 hi/lo planes.  kEpiSigmoid: bias + sigmoid -> 3 fp32 maps.
+// kEpiGate: bias + ReLU, gated sum with the confidence maps -> fp32 NCHW output.
+// kEpiDgrad (backward): no bias; zero where the saved forward activation is zero (ReLU'), -> planes.
+enum Epilogue { kEpiAct = 0, kEpiSigmoid = 1, kEpiGate = 2, kEpiDgrad = 3 };
+
+constexpr int kSubW = 8, kSubH = 16;  // one M=128 sub-tile: 8 px wide, 16 px tall
+constexpr int kThreads = 384;  // warps 0-3 and 8-11: epilogue; 4: A producer; 5: B producer; 6: MMA; 7: TMEM
+
+// NPAD   output channels per diagonal block (UMMA N of the lo*hi pass)
+// CONCAT weight stage rows are [hi rows | lo rows]: a_hi x [w_hi|w_lo] is ONE MMA of N = 2*NPAD (the
+//        activation tile is read from shared memory once for two products), then a_lo x w_hi with
+//        N = NPAD.  Pays when NPAD <= 64, where an MMA is bound by the 4 KB A-operand read.
+// NBLK   number of diagonal blocks (the three refiners run as one block-diagonal layer): input
+//        chunk c only feeds block c / (NCHUNK / NBLK), so only that block's weights are staged.
+// TPS    filter taps per weight stage: small-N layers batch a kernel row (or all taps) per stage so
+//        that the per-stage pipeline cost (barrier wait, commit, bulk-copy latency) is amortised.
+template <int KS, int CIN_PAD, int NPAD, int S, int AS, int CONCAT = 0, int NBLK = 1, int TPS = 1>
+struct UmmaCfg {
+  static constexpr int TILE_W = kSubW * S, TILE_H = kSubH;
+  static constexpr int HALO_W = TILE_W + KS - 1, HALO_H = TILE_H + KS - 1;
+  static constexpr int NCHUNK = CIN_PAD / 16;
+  static constexpr int PLANE_BYTES = HALO_W * HALO_H * 16;
+  static constexpr int A_STAGE = (4 * PLANE_BYTES + 1023) / 1024 * 1024;  // hi k0, hi k1, lo k0, lo k1
+  static constexpr int B_TAP = NPAD * 64;                                  // one tap: [hi|lo][k8 0|1][NPAD][16 B]
+  static constexpr int B_STAGE = TPS * B_TAP;
+  static constexpr int NSTAGE_PER_CHUNK = KS * KS / TPS;
+  static constexpr int BUDGET = 225 * 1024 - 2048;
+  // halo ring: enough stages to prefetch the next chunk (or the next tile when there is one chunk)
+  static constexpr int NA_WANT = NCHUNK == 1 ? 2 : 3;
+  // weight ring: whatever is left after the halo ring, 2..8 stages; deep rings hide the L2 latency of
+  // the bulk copies when a stage carries only a few MMAs (first layer: 14 KB per 4-6 MMAs)
+  static constexpr int NB_FIT = (BUDGET - NA_WANT * A_STAGE) / B_STAGE;
+  static constexpr int NB = NB_FIT > 8 ? 8 : NB_FIT < 2 ? 2 : NB_FIT;
+  static constexpr int NA_FIT = (BUDGET - NB * B_STAGE) / A_STAGE;
+  static constexpr int NA = NA_FIT > NA_WANT ? NA_WANT : NA_FIT;
+  static_assert((KS * KS) % TPS == 0, "taps per stage must divide the tap count");
+  static constexpr int CPB = NCHUNK / NBLK;                // chunks per diagonal block
+  static constexpr int N1 = CONCAT ? 2 * NPAD : NPAD;      // UMMA N of the a_hi pass
+  static constexpr int BLK_COLS = N1;                      // accumulator columns per block
+  static constexpr int SUB_COLS = NBLK * BLK_COLS;         // accumulator columns per sub-tile
+  static constexpr int TMEM_COLS_USED = AS * S * SUB_COLS;
+  static_assert(NCHUNK % NBLK == 0, "chunks must split evenly over the diagonal blocks");
+  static_assert(N1 % 16 == 0 && N1 <= 256, "invalid UMMA N for the a_hi pass");
+  static constexpr int TMEM_COLS = TMEM_COLS_USED <= 32 ? 32 : TMEM_COLS_USED <= 64 ? 64
+                                   : TMEM_COLS_USED <= 128 ? 128 : TMEM_COLS_USED <= 256 ? 256 : 512;
+  static constexpr int SMEM_BYTES = NA * A_STAGE + NB * B_STAGE + 2048 + 1024;  // + barriers/bias + align slack
+  static_assert(NA >= 1, "halo tile does not fit in shared memory");
+  static_assert(TMEM_COLS_USED <= 512, "accumulators do not fit in TMEM");
+  static_assert(NPAD % 16 == 0 && NPAD >= 16 && NPAD <= 256, "invalid UMMA N");
+};
+
+struct ActDst {
+  uint4* base;   // [n][2*planes_half][H][W] of 16-byte (8 x bf16) units
+  int planes_half;
+};
+
+struct ConvArgs {
+  const uint8_t* wpk;   // packed weight stages
+  const float* bias;    // [NPAD]
+  int N, H, W;
+  int in_planes_half;   // C_in_pad / 8
+  int tiles_x, tiles_y;
+  // kEpiAct
+  ActDst dst0, dst1;
+  int split_c;          // channels [0, split_c) -> dst0, [split_c, cout) -> dst1
+  int cout;             // valid output channels
+  // kEpiSigmoid / kEpiGate
+  float* out_f32;       // [n][3][H][W]
+  const float* cm;      // [n][3][H][W] (gate)
+  // optional: *skip_lo != 0 means every input value is exactly representable in the hi plane
+  // (8-bit image levels), so the a_lo x w_hi pass contributes nothing and is not issued
+  const int* skip_lo;
+  // kEpiGate, training only: also store the three refined images (post-ReLU), fp32 [n][9][H][W]
+  float* refined_out;
+  // kEpiDgrad: saved forward activation (planes) whose zeros gate the gradient
+  const uint4* mask_base;
+  int mask_planes_half;
+};
+
+__device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b) {
+  return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+}
+
+template <int KS, int CIN_PAD, int NPAD, int S, int AS, int EPI, int CONCAT, int NBLK, int TPS>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) {
+  using C = UmmaCfg<KS, CIN_PAD, NPAD, S, AS, CONCAT, NBLK, TPS>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* a_stages = smem;
+  uint8_t* b_stages = smem + C::NA * C::A_STAGE;
+  uint8_t* tail = b_stages + C::NB * C::B_STAGE;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(tail);
+  uint64_t* a_empty = a_full + C::NA;
+  uint64_t* b_full = a_empty + C::NA;
+  uint64_t* b_empty = b_full + C::NB;
+  uint64_t* t_full = b_empty + C::NB;
+  uint64_t* t_empty = t_full + AS;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + AS);
+  float* s_bias = reinterpret_cast<float*>(tail + 512);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int num_tiles = g.tiles_x * g.tiles_y * g.N;
+
+  if (tid == 0) {
+    for (int i = 0; i < C::NA; i++) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < C::NB; i++) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < AS; i++) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = tid; i < NBLK * NPAD; i += kThreads) s_bias[i] = g.bias[i];
+  if (warp == 7) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)C::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (tmem_base != 0) __trap();  // see the MMA issuer: accumulators are addressed from column 0
+
+  if (warp == 4) {
+    // ===================== A producer: halo tiles by TMA =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int n = tile / (g.tiles_x * g.tiles_y);
+        const int rem = tile - n * g.tiles_x * g.tiles_y;
+        const int ty = rem / g.tiles_x, tx = rem - ty * g.tiles_x;
+        const int x0 = tx * C::TILE_W - KS / 2, y0 = ty * C::TILE_H - KS / 2;
+        for (int c = 0; c < C::NCHUNK; c++) {
+          mbar_wait(&a_empty[stage], phase ^ 1);
+          uint8_t* dst = a_stages + stage * C::A_STAGE;
+          mbar_expect_tx(&a_full[stage], 4 * C::PLANE_BYTES);
+          tma_load_5d(dst, &tmap_in, &a_full[stage], 0, x0, y0, 2 * c, n);
+          tma_load_5d(dst + 2 * C::PLANE_BYTES, &tmap_in, &a_full[stage], 0, x0, y0,
+                      g.in_planes_half + 2 * c, n);
+          if (++stage == C::NA) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ===================== B producer: packed weight stages =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int it = 0; it < C::NCHUNK * C::NSTAGE_PER_CHUNK; it++) {
+          mbar_wait(&b_empty[stage], phase ^ 1);
+          mbar_expect_tx(&b_full[stage], C::B_STAGE);
+          bulk_load(b_stages + stage * C::B_STAGE, g.wpk + (size_t)it * C::B_STAGE, C::B_STAGE, &b_full[stage]);
+          if (++stage == C::NB) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 6) {
+    // ===================== MMA issuer =====================
+    // The whole warp walks the pipeline (converged, so every operand stays in uniform registers);
+    // one elected lane issues the MMAs and commits.
+    {
+      constexpr uint32_t idesc1 = make_idesc(128, C::N1);  // a_hi pass
+      constexpr uint32_t idesc2 = make_idesc(128, NPAD);   // a_lo x w_hi (and a_hi x w_lo without CONCAT)
+      // descriptor halves: hi = SBO | version, lo = start address | LBO
+      constexpr uint32_t a_hi32 = ((uint32_t)(C::HALO_W * 16) >> 4) | (1u << 14);
+      constexpr uint32_t b_hi32 = (128u >> 4) | (1u << 14);
+      // weight stage: CONCAT [k8][hi rows | lo rows][16 B] (LBO = 2*NPAD*16), else [hi|lo][k8][rows][16 B]
+      constexpr uint32_t b_lbo = (uint32_t)((CONCAT ? 2 * NPAD : NPAD) * 16);
+      int astage = 0, bstage = 0, acc = 0;
+      uint32_t aphase = 0, bphase = 0, tphase = 0;
+      const bool skip_lo = g.skip_lo != nullptr && *g.skip_lo != 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&t_empty[acc], tphase ^ 1);
+        tc_fence_after();
+        // TMEM addresses are compile-time column offsets: this CTA is alone on its SM (shared memory
+        // footprint) and owns the allocation at column 0 (checked after the allocation).
+        const uint32_t d_tile = (uint32_t)(acc * S * C::SUB_COLS);
+        for (int c = 0; c < C::NCHUNK; c++) {
+          mbar_wait(&a_full[astage], aphase);
+          tc_fence_after();
+          const uint32_t a_lo32 = (smem_u32(a_stages + astage * C::A_STAGE) >> 4) | ((uint32_t)(C::PLANE_BYTES >> 4) << 16);
+          const int blk = NBLK > 1 ? c / C::CPB : 0;
+          const uint32_t d_base = d_tile + (uint32_t)(blk * C::BLK_COLS);
+          for (int tg = 0; tg < C::NSTAGE_PER_CHUNK; tg++) {
+            mbar_wait(&b_full[bstage], bphase);
+            tc_fence_after();
+            const uint32_t b_stage32 = (smem_u32(b_stages + bstage * C::B_STAGE) >> 4) | ((b_lbo >> 4) << 16);
+            if (elect_one_sync()) {
+              constexpr uint32_t a_lo_off = (uint32_t)(2 * C::PLANE_BYTES >> 4);
+#pragma unroll
+              for (int t = 0; t < TPS; t++) {
+                const int tap = tg * TPS + t;
+                const int ky = tap / KS, kx = tap - ky * KS;
+                const uint32_t b_lo32 = b_stage32 + (uint32_t)(t * (C::B_TAP >> 4));
+                const uint32_t a_tap = a_lo32 + (uint32_t)(ky * C::HALO_W + kx);
+                const uint32_t first = ((NBLK > 1 ? c % C::CPB : c) | tap) == 0 ? 0u : 1u;
+                // pass-major order: consecutive MMAs target different accumulators
+#pragma unroll
+                for (int s = 0; s < S; s++)  // a_hi x w_hi (CONCAT: x [w_hi | w_lo])
+                  umma_bf16_split(d_base + (uint32_t)(s * C::SUB_COLS), a_tap + (uint32_t)(s * kSubW), a_hi32, b_lo32,
+                                  b_hi32, idesc1, first);
+                if (!skip_lo) {
+#pragma unroll
+                  for (int s = 0; s < S; s++)  // a_lo x w_hi
+                    umma_bf16_split(d_base + (uint32_t)(s * C::SUB_COLS), a_tap + (uint32_t)(s * kSubW) + a_lo_off,
+                                    a_hi32, b_lo32, b_hi32, idesc2, 1u);
+                }
+                if constexpr (!CONCAT) {
+#pragma unroll
+                  for (int s = 0; s < S; s++)  // a_hi x w_lo
+                    umma_bf16_split(d_base + (uint32_t)(s * C::SUB_COLS), a_tap + (uint32_t)(s * kSubW), a_hi32,
+                                    b_lo32 + (uint32_t)(2 * NPAD * 16 >> 4), b_hi32, idesc2, 1u);
+                }
+              }
+              umma_commit(&b_empty[bstage]);
+              if (tg == C::NSTAGE_PER_CHUNK - 1) {
+                umma_commit(&a_empty[astage]);
+                if (c == C::NCHUNK - 1) umma_commit(&t_full[acc]);
+              }
+            }
+            __syncwarp();
+            if (++bstage == C::NB) { bstage = 0; bphase ^= 1; }
+          }
+          if (++astage == C::NA) { astage = 0; aphase ^= 1; }
+        }
+        if (++acc == AS) { acc = 0; tphase ^= 1; }
+      }
+    }
+  } else if (warp < 4 || warp >= 8) {
+    // ===================== epilogue =====================
+    // a warp may only touch TMEM lanes 32*(warp%4)..+31; the two groups take alternate sub-tiles
+    int acc = 0;
+    uint32_t tphase = 0;
+    const int egroup = warp >> 3, quarter = warp & 3;
+    const int row = quarter * 32 + lane;      // TMEM lane == pixel row of the sub-tile
+    const int px = row & 7, py = row >> 3;
+    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int n = tile / (g.tiles_x * g.tiles_y);
+      const int rem = tile - n * g.tiles_x * g.tiles_y;
+      const int ty = rem / g.tiles_x, tx = rem - ty * g.tiles_x;
+      mbar_wait(&t_full[acc], tphase);
+      tc_fence_after();
+      const int gy = ty * C::TILE_H + py;
+#pragma unroll 1
+      for (int s = egroup; s < S; s += 2) {
+        const int gx = tx * C::TILE_W + s * kSubW + px;
+        const bool inside = gx < g.W && gy < g.H;
+        const uint32_t t_addr = tmem_base + lane_base + (uint32_t)((acc * S + s) * C::SUB_COLS);
+        // NC accumulator columns starting at output channel ch0 (+ the a_hi x w_lo half when CONCAT);
+        // all TMEM loads of a group are in flight before the single wait
+        auto load_cols = [&](int ch0, float* f, auto nc_tag) {
+          constexpr int NC = decltype(nc_tag)::value;
+          const int blk = NBLK > 1 ? ch0 / NPAD : 0;
+          const uint32_t col = (uint32_t)(blk * C::BLK_COLS + (NBLK > 1 ? ch0 % NPAD : ch0));
+          uint32_t v[NC], w[CONCAT ? NC : 1];
+#pragma unroll
+          for (int q = 0; q < NC; q += 16) tmem_ld16(t_addr + col + q, v + q);
+          if constexpr (CONCAT) {
+#pragma unroll
+            for (int q = 0; q < NC; q += 16) tmem_ld16(t_addr + col + NPAD + q, w + q);
+          }
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < NC; j++) f[j] = __uint_as_float(v[j]) + (CONCAT ? __uint_as_float(w[CONCAT ? j : 0]) : 0.f);
+        };
+        if constexpr (EPI == kEpiAct || EPI == kEpiDgrad) {
+          constexpr int GC = 32;  // channels per group
+          static_assert((NBLK * NPAD) % GC == 0 && (NBLK == 1 || NPAD % GC == 0), "channel groups of 32");
+#pragma unroll 1
+          for (int c0 = 0; c0 < NBLK * NPAD; c0 += GC) {
+            float f[GC];
+            load_cols(c0, f, std::integral_constant<int, GC>{});
+            if (c0 < g.cout && inside) {
+              const size_t pix = (size_t)gy * g.W + gx;
+              const size_t hw = (size_t)g.H * g.W;
+#pragma unroll
+              for (int q = 0; q < GC; q += 8) {  // one 8-channel plane at a time
+                const int ch = c0 + q;
+                uint32_t hi[4], lo[4];
+                uint32_t mask[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+                if constexpr (EPI == kEpiDgrad) {
+                  const uint4 m = g.mask_base[((size_t)n * 2 * g.mask_planes_half + (ch >> 3)) * hw + pix];
+                  mask[0] = m.x; mask[1] = m.y; mask[2] = m.z; mask[3] = m.w;
+                }
+#pragma unroll
+                for (int j = 0; j < 8; j += 2) {
+                  float f0, f1;
+                  if constexpr (EPI == kEpiDgrad) {  // ReLU': pass the gradient where the activation was > 0
+                    f0 = (mask[j >> 1] & 0x0000ffffu) ? f[q + j] : 0.f;
+                    f1 = (mask[j >> 1] & 0xffff0000u) ? f[q + j + 1] : 0.f;
+                  } else {
+                    f0 = fmaxf(f[q + j] + s_bias[ch + j], 0.f);
+                    f1 = fmaxf(f[q + j + 1] + s_bias[ch + j + 1], 0.f);
+                  }
+                  __nv_bfloat16 h0 = __float2bfloat16_rn(f0), h1 = __float2bfloat16_rn(f1);
+                  hi[j >> 1] = pack_bf16x2(h0, h1);
+                  lo[j >> 1] = pack_bf16x2(__float2bfloat16_rn(f0 - __bfloat162float(h0)),
+                                           __float2bfloat16_rn(f1 - __bfloat162float(h1)));
+                }
+                const bool second = ch >= g.split_c;
+                const ActDst& d = second ? g.dst1 : g.dst0;
+                const int plane = (second ? ch - g.split_c : ch) >> 3;
+                uint4* p_hi = d.base + ((size_t)n * 2 * d.planes_half + plane) * hw + pix;
+                p_hi[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                p_hi[(size_t)d.planes_half * hw] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+              }
+            }
+          }
+        } else {
+          float f[16];
+          load_cols(0, f, std::integral_constant<int, 16>{});
+          if (inside) {
+            const size_t hw = (size_t)g.H * g.W;
+            const size_t o = (size_t)n * 3 * hw + (size_t)gy * g.W + gx;
+            if constexpr (EPI == kEpiSigmoid) {
+#pragma unroll
+              for (int c = 0; c < 3; c++) g.out_f32[o + c * hw] = 1.0f / (1.0f + expf(-(f[c] + s_bias[c])));
+            } else {  // kEpiGate: columns 3r+c = refiner r, colour c  (net.py:104-108)
+              float r[9];
+#pragma unroll
+              for (int j = 0; j < 9; j++) r[j] = fmaxf(f[j] + s_bias[j], 0.f);
+              if (g.refined_out) {
+#pragma unroll
+                for (int j = 0; j < 9; j++) g.refined_out[(size_t)n * 9 * hw + (size_t)gy * g.W + gx + j * hw] = r[j];
+              }
+              const float c0 = g.cm[o], c1 = g.cm[o + hw], c2 = g.cm[o + 2 * hw];
+#pragma unroll
+              for (int c = 0; c < 3; c++)
+                g.out_f32[o + c * hw] =
+                    __fadd_rn(__fadd_rn(__fmul_rn(r[c], c0), __fmul_rn(r[3 + c], c1)), __fmul_rn(r[6 + c], c2));
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&t_empty[acc]);
+      if (++acc == AS) { acc = 0; tphase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 7) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"((uint32_t)C::TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Operand packing kernels
+// ------------------------------------------------------------------------------------------
+// scatter one OIHW fp32 tensor into a dense [npad][cinpad][ks*ks] fp32 block-matrix
+static __global__ void scatter_weights_kernel(const float* __restrict__ src, float* __restrict__ dense, int co, int ci,
+                                       int kk, int cinpad, int row_off, int split, int base0, int base1,
+                                       float divisor) {
+  const int total = co * ci * kk;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    int t = i % kk;
+    int c = (i / kk) % ci;
+    int o = i / (kk * ci);
+    int cd = c < split ? base0 + c : base1 + (c - split);
+    dense[((size_t)(row_off + o) * cinpad + cd) * kk + t] = __fdiv_rn(src[i], divisor);
+  }
+}
+static __global__ void scatter_bias_kernel(const float* __restrict__ src, float* __restrict__ dst, int co, int row_off) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < co; i += gridDim.x * blockDim.x) dst[row_off + i] = src[i];
+}
+// dense fp32 [nblk*npad][cinpad][kk] -> weight stages, one per (chunk, tap), holding the rows of the
+// diagonal block the chunk feeds:  concat ? [k8][hi rows | lo rows][8] : [hi|lo][k8][rows][8]   (bf16)
+static __global__ void pack_stages_kernel(const float* __restrict__ dense, __nv_bfloat16* __restrict__ out, int npad,
+                                   int cinpad, int kk, int concat, int nblk) {
+  const int nchunk = cinpad / 16, cpb = nchunk / nblk;
+  const size_t total = (size_t)nchunk * kk * 2 * 2 * npad * 8;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    int e = (int)(i % 8);
+    size_t r = i / 8;
+    int k8, split, nrow;
+    if (concat) {
+      int row2 = (int)(r % (2 * npad)); r /= 2 * npad;
+      k8 = (int)(r % 2); r /= 2;
+      split = row2 >= npad;
+      nrow = row2 - split * npad;
+    } else {
+      nrow = (int)(r % npad); r /= npad;
+      k8 = (int)(r % 2); r /= 2;
+      split = (int)(r % 2); r /= 2;
+    }
+    int tap = (int)(r % kk);
+    int chunk = (int)(r / kk);
+    int cin = chunk * 16 + k8 * 8 + e;
+    int row = (chunk / cpb) * npad + nrow;
+    float w = dense[((size_t)row * cinpad + cin) * kk + tap];
+    __nv_bfloat16 hi = __float2bfloat16_rn(w);
+    out[i] = split == 0 ? hi : __float2bfloat16_rn(w - __bfloat162float(hi));
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Host helpers
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+
+static int get_encoder() {
+  if (g_encode) return WN_OK;
+  cudaDriverEntryPointQueryResult q;
+  void* fn = nullptr;
+  WN_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+  if (!fn || q != cudaDriverEntryPointSuccess) {
+    set_error("cuTensorMapEncodeTiled is not available from this driver");
+    return WN_E_UNSUPPORTED;
+  }
+  g_encode = (EncodeTiledFn)fn;
+  return WN_OK;
+}
+
+static int make_tmap(CUtensorMap* tm, void* base, int planes_total, int N, int H, int W, int halo_w, int halo_h) {
+  cuuint64_t dims[5] = {8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)planes_total, (cuuint64_t)N};
+  cuuint64_t strides[4] = {16, (cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)planes_total * H * W * 16};
+  cuuint32_t box[5] = {8, (cuuint32_t)halo_w, (cuuint32_t)halo_h, 2, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with %d (planes=%d N=%d H=%d W=%d box=%dx%d)", (int)r, planes_total, N, H,
+              W, halo_w, halo_h);
+    return WN_E_CUDA;
+  }
+  return WN_OK;
+}
+
+// Launch one convolution.  `slot` is the timing slot (common.cuh).
+template <int KS, int CIN_PAD, int NPAD, int S, int AS, int EPI, int CONCAT = 0, int NBLK = 1, int TPS = 1>
+static int launch_conv(wn_handle* h, int slot, const uint8_t* wpk, const float* bias, void* in_base, ConvArgs a,
+                       cudaStream_t stream) {
+  using C = UmmaCfg<KS, CIN_PAD, NPAD, S, AS, CONCAT, NBLK, TPS>;
+  int rc = get_encoder();
+  if (rc) return rc;
+  CUtensorMap tm;
+  rc = make_tmap(&tm, in_base, 2 * (CIN_PAD / 8), a.N, a.H, a.W, C::HALO_W, C::HALO_H);
+  if (rc) return rc;
+  a.wpk = wpk;
+  a.bias = bias;
+  a.in_planes_half = CIN_PAD / 8;
+  a.tiles_x = (a.W + C::TILE_W - 1) / C::TILE_W;
+  a.tiles_y = (a.H + C::TILE_H - 1) / C::TILE_H;
+  const long long tiles = (long long)a.tiles_x * a.tiles_y * a.N;
+  auto kern = conv_umma_kernel<KS, CIN_PAD, NPAD, S, AS, EPI, CONCAT, NBLK, TPS>;
+  WN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+  int grid = (int)(tiles < h->sm_count ? tiles : h->sm_count);
+  TimedScope ts(h, slot, stream);
+  kern<<<grid, kThreads, C::SMEM_BYTES, stream>>>(tm, a);
+  WN_LAUNCH_CHECK(h);
+  return WN_OK;
+}
+
+}  // namespace wn

@@ -145,6 +145,33 @@ class Engine:
         _lib.check(rc, "wn_debug_forward_layer")
         return dst
 
+    # ---- training step (wn_forward_train / wn_backward) ---------------------------------------
+    def forward_train(self, x, wb, he, gc):
+        """Tensor-core forward that keeps every activation.  Returns (out, saved-workspace tensor)."""
+        ins = [t.detach() if t.dtype == torch.float32 else t.detach().float() for t in (x, wb, he, gc)]
+        n, _, h, w = ins[0].shape
+        out = torch.empty((n, 3, h, w), dtype=torch.float32, device=self.device)
+        strides = (ctypes.c_int64 * 16)(*[s for t in ins for s in t.stride()])
+        ws = torch.empty(self.lib.wn_train_workspace_bytes(n, h, w), dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = self.lib.wn_forward_train(self.handle, ins[0].data_ptr(), ins[1].data_ptr(), ins[2].data_ptr(),
+                                           ins[3].data_ptr(), strides, out.data_ptr(), n, h, w, ws.data_ptr(),
+                                           ws.numel(), _stream_ptr(self.device))
+        _lib.check(rc, "wn_forward_train")
+        return out, ws
+
+    def backward(self, grad_out: torch.Tensor, saved_ws: torch.Tensor, shapes):
+        """d(loss)/d(out) + the workspace of forward_train -> the 34 parameter gradients (state-dict order)."""
+        g = grad_out.detach().to(self.device, torch.float32).contiguous()
+        n, _, h, w = g.shape
+        grads = [torch.empty(tuple(s), dtype=torch.float32, device=self.device) for s in shapes]
+        arr = (ctypes.c_void_p * _lib.NUM_PARAMS)(*[t.data_ptr() for t in grads])
+        with torch.cuda.device(self.device):
+            rc = self.lib.wn_backward(self.handle, g.data_ptr(), arr, n, h, w, saved_ws.data_ptr(), saved_ws.numel(),
+                                      _stream_ptr(self.device))
+        _lib.check(rc, "wn_backward")
+        return grads
+
     # ---- preprocess / postprocess ----------------------------------------------
     def preprocess(self, rgb_u8: torch.Tensor, tensors: bool = True, images: bool = False):
         """rgb_u8: uint8 (N,H,W,3) CUDA tensor.  Returns dict with the requested outputs.

@@ -8,10 +8,11 @@ reference's checkpoints load with strict ``load_state_dict`` and callers
 * ``WaterNet.forward(x, wb, ce, gc)`` (reference ``net.py:99-108``) dispatches to
   ``libwaternet_b200.so`` (``wn_forward``).  There is no CPU path: CPU tensors
   raise.
-* When autograd needs a graph (training, ``train.py:100-133``), the forward values
-  still come from the CUDA kernels; the backward pass re-evaluates the network
-  with torch ops to obtain gradients (dgrad/wgrad kernels are SURVEY.md section
-  8f "next", not part of the inference hot path).
+* When autograd needs a graph (training, ``train.py:100-133``), forward values and
+  the 34 parameter gradients both come from the CUDA library (``wn_forward_train`` /
+  ``wn_backward``: tensor-core data-gradient and weight-gradient kernels).  Only when
+  an *input image* requires grad, or in the fp32 CUDA-core mode, the backward pass
+  re-evaluates the network with torch ops.
 """
 from __future__ import annotations
 
@@ -78,19 +79,38 @@ class Refiner(_ConvStack):
 
 
 class _KernelForward(torch.autograd.Function):
-    """Values from the CUDA library; gradients by re-evaluating the torch graph."""
+    """Forward values AND parameter gradients from the CUDA library (wn_forward_train / wn_backward).
+
+    Gradients with respect to the four input images are not produced by the kernels; when an input
+    requires grad the backward pass re-evaluates the torch graph instead.
+    """
 
     @staticmethod
     def forward(ctx, model, mode, x, wb, ce, gc, *params):
         ctx.model = model
+        ctx.native = not any(t.requires_grad for t in (x, wb, ce, gc)) and mode != _lib.MODE_FP32_SIMT
+        if ctx.native:
+            eng = model._engine_with_weights(x)
+            out, ws = eng.forward_train(x, wb, ce, gc)
+            ctx.engine, ctx.saved_ws = eng, ws
+            ctx.weights_key = eng._weights_key
+            return out
         ctx.save_for_backward(x, wb, ce, gc)
         return model._kernel_forward(x, wb, ce, gc, mode)
 
     @staticmethod
     def backward(ctx, grad_out):
         model = ctx.model
-        x, wb, ce, gc = ctx.saved_tensors
         params = list(model.parameters())
+        if ctx.native:
+            eng = ctx.engine
+            if eng._weights_key != ctx.weights_key:  # parameters changed between forward and backward
+                raise RuntimeError("model parameters were modified between forward and backward")
+            grads = eng.backward(grad_out, ctx.saved_ws, [p.shape for p in params])
+            ctx.saved_ws = None
+            gpar = [g if p.requires_grad else None for g, p in zip(grads, params)]
+            return (None, None, None, None, None, None, *gpar)
+        x, wb, ce, gc = ctx.saved_tensors
         with torch.enable_grad():
             ins = [t.detach().requires_grad_(t.requires_grad) for t in (x, wb, ce, gc)]
             out = model._graph(*ins)
@@ -136,7 +156,7 @@ class WaterNet(nn.Module):
                 out += [conv.weight, conv.bias]
         return out
 
-    def _kernel_forward(self, x, wb, ce, gc, mode):
+    def _engine_with_weights(self, x):
         if not x.is_cuda:
             raise _lib.WaterNetLibraryError(
                 "WaterNet.forward got CPU tensors: waternet_b200 has no CPU path; move the model and inputs to a "
@@ -147,7 +167,10 @@ class WaterNet(nn.Module):
             raise RuntimeError(f"model parameters on {params[0].device}, inputs on {x.device}")
         key = tuple((p.data_ptr(), p._version) for p in params)
         eng.pack_weights(params, key=key)
-        return eng.forward(x, wb, ce, gc, mode)
+        return eng
+
+    def _kernel_forward(self, x, wb, ce, gc, mode):
+        return self._engine_with_weights(x).forward(x, wb, ce, gc, mode)
 
     def _graph(self, x, wb, ce, gc):
         """Differentiable torch-op evaluation, used only to obtain gradients."""

@@ -261,13 +261,13 @@ def main():
         macs_by_slot = list(CONV_MACS)
         names_by_slot = list(CONV_NAMES)
         if mode != _lib.MODE_FP32_SIMT:
-            # tensor-core path: eleven launches.  slot 8 = the three refiner conv1 (one 16->96 GEMM),
+            # tensor-core path: ten launches.  slot 0 = cmg.conv1 + the three refiner conv1 (one 16->224 GEMM),
             # slot 9 = the three refiner conv2 (block-diagonal 96->96), slot 10 = the three conv3 + gated sum
             macs_by_slot = CONV_MACS[:8] + [0] * 9
-            macs_by_slot[8] = 3 * 9408
+            macs_by_slot[0] += 3 * 9408
             macs_by_slot[9] = 3 * 25600
             macs_by_slot[10] = 3 * 864
-            names_by_slot[8] = "refiner.conv1x3"
+            names_by_slot[0] = "cmg.conv1+refiner.conv1x3"
             names_by_slot[9] = "refiner.conv2x3"
             names_by_slot[10] = "refiner.conv3x3+gate"
         top = int(np.argmax(conv_ms))

@@ -74,25 +74,22 @@ __global__ void __launch_bounds__(256) pack_inputs_kernel(PackInArgs a, uint4* _
 // ------------------------------------------------------------------------------------------
 // Host side
 // ------------------------------------------------------------------------------------------
-// The eleven tensor-core launches of one forward (fused layer list).
+// The ten tensor-core launches of one forward (fused layer list).
 enum UmmaLayer {
-  kL1 = 0,    // cmg.conv1: cat[x,wb,he,gc] (12 -> pad 16) -> 128, 7x7
+  kL1 = 0,    // cmg.conv1 (12->128) + the three refiner conv1 (6->32 each): 16 -> 224, 7x7
   kC2, kC3, kC4, kC5, kC6, kC7,
   kC8,        // 64 -> 3 (pad 16), sigmoid
   kR2,        // three refiner conv2 as one block-diagonal 96 -> 96, 5x5
   kR3,        // three refiner conv3 as block-diagonal 96 -> 9 (pad 16), ReLU, gated sum
-  kR1,        // the three refiner conv1 (6 -> 32 each) as one 16 -> 96 GEMM over the same packed input.
-              // (A single 16 -> 224 GEMM with cmg.conv1 was measured slower: TMEM then only holds two
-              //  sub-tiles, so every 14 KB weight stage feeds 4-6 MMAs and the L2 stream starves them.)
   kNumUmmaLayers
 };
 struct UmmaLayerSpec {
   int ks, cinpad, npad, cout, slot, concat, nblk;  // npad = output columns per diagonal block
 };
 static const UmmaLayerSpec kSpecs[kNumUmmaLayers] = {
-    {7, 16, 128, 128, 0, 0, 1}, {5, 128, 128, 128, 1, 0, 1}, {3, 128, 128, 128, 2, 0, 1}, {1, 128, 64, 64, 3, 1, 1},
+    {7, 16, 224, 224, 0, 0, 1}, {5, 128, 128, 128, 1, 0, 1}, {3, 128, 128, 128, 2, 0, 1}, {1, 128, 64, 64, 3, 1, 1},
     {7, 64, 64, 64, 4, 1, 1},   {5, 64, 64, 64, 5, 1, 1},    {3, 64, 64, 64, 6, 1, 1},    {3, 64, 16, 3, 7, 1, 1},
-    {5, 96, 32, 96, 9, 1, 3},   {3, 96, 16, 9, 10, 1, 1},    {7, 16, 96, 96, 8, 0, 1}};
+    {5, 96, 32, 96, 9, 1, 3},   {3, 96, 16, 9, 10, 1, 1}};
 
 struct UmmaWeights {
   uint8_t* stages[kNumUmmaLayers];
@@ -125,7 +122,7 @@ int umma_pack_weights(wn_handle* h, const float* const* params, cudaStream_t str
     auto scatter = [&](int conv, int co, int ci, int row_off, int split, int base0, int base1) -> int {
       // the first layer consumes image levels 0..255 (see pack_inputs_kernel): fold the /255 into its weights
       scatter_weights_kernel<<<128, 256, 0, stream>>>(W(conv), u->dense, co, ci, kk, s.cinpad, row_off, split,
-                                                      base0, base1, (li == kL1 || li == kR1) ? 255.0f : 1.0f);
+                                                      base0, base1, li == kL1 ? 255.0f : 1.0f);
       WN_LAUNCH_CHECK(h);
       scatter_bias_kernel<<<1, 256, 0, stream>>>(B(conv), u->bias[li], co, row_off);
       WN_LAUNCH_CHECK(h);
@@ -134,9 +131,8 @@ int umma_pack_weights(wn_handle* h, const float* const* params, cudaStream_t str
     int rc = WN_OK;
     if (li == kL1) {
       rc = scatter(0, 128, 12, 0, 12, 0, 0);
-    } else if (li == kR1) {
       for (int r = 0; r < 3 && !rc; r++)  // refiner r sees cat[x, input r+1]: channels 0..2 and 3(r+1)..3(r+1)+2
-        rc = scatter(8 + 3 * r, 32, 6, 32 * r, 3, 0, 3 * (r + 1));
+        rc = scatter(8 + 3 * r, 32, 6, 128 + 32 * r, 3, 0, 3 * (r + 1));
     } else if (li >= kC2 && li <= kC8) {
       const int conv = li;  // cmg.conv2..conv8 are convs 1..7
       const LayerDesc& d = kCmg[conv];
@@ -237,15 +233,12 @@ int umma_forward_layers(wn_handle* h, const float* const in[4], const int64_t st
     a.dst1.base = d1; a.dst1.planes_half = c1 / 8;
     a.split_c = c0; a.cout = c0 + c1;
   };
-  // first layers of both stacks read the same packed input: 16 -> 128 (cmg.conv1), 16 -> 96 (refiner conv1 x3)
+  // L1: 16 -> 128 (cmg) + 96 (refiners)
+  act(b.a[1], 128, b.r[1], 96);
   a.skip_lo = b.exact_flag;
-  act(b.a[1], 128, nullptr, 0);
-  if ((rc = launch_umma<7, 16, 128, 4, 1, kEpiAct>(h, kL1, b.act0, a, stream))) return rc;
-  if (dump(0, b.a[1], 128)) return WN_OK;
-  act(b.r[1], 96, nullptr, 0);
-  if ((rc = launch_umma<7, 16, 96, 4, 1, kEpiAct>(h, kR1, b.act0, a, stream))) return rc;
+  if ((rc = launch_umma<7, 16, 224, 2, 1, kEpiAct>(h, kL1, b.act0, a, stream))) return rc;
   a.skip_lo = nullptr;
-  if (dump(8, b.r[1], 96)) return WN_OK;
+  if (dump(0, b.a[1], 128) || dump(8, b.r[1], 96)) return WN_OK;
   act(b.a[2], 128, nullptr, 0);
   if ((rc = launch_umma<5, 128, 128, 2, 2, kEpiAct>(h, kC2, b.a[1], a, stream))) return rc;
   if (dump(1, b.a[2], 128)) return WN_OK;

@@ -253,10 +253,7 @@ gate_bwd_kernel(const float* __restrict__ g_out, const float* __restrict__ cm, c
     uint32_t hi[8], lo[8];
 #pragma unroll
     for (int j = 0; j < 16; j += 2) {
-      __nv_bfloat16 h0 = __float2bfloat16_rn(v[j]), h1 = __float2bfloat16_rn(v[j + 1]);
-      hi[j >> 1] = pack_bf16x2(h0, h1);
-      lo[j >> 1] = pack_bf16x2(__float2bfloat16_rn(v[j] - __bfloat162float(h0)),
-                               __float2bfloat16_rn(v[j + 1] - __bfloat162float(h1)));
+      split_bf16x2(v[j], v[j + 1], hi[j >> 1], lo[j >> 1]);
     }
     uint4* o = base + (size_t)n * 4 * hw + pix;  // planes: hi0, hi1, lo0, lo1
     o[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);

@@ -207,6 +207,15 @@ struct ConvArgs {
 __device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b) {
   return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
 }
+// v = hi + lo with hi = bf16(v), lo = bf16(v - hi), for two values at once: two packed conversions
+// (F2FP.BF16.PACK_AB) instead of four scalar F2F, and the back-conversion is a shift.
+__device__ __forceinline__ void split_bf16x2(float f0, float f1, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(f0, f1);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  const float h0 = __uint_as_float(hi << 16), h1 = __uint_as_float(hi & 0xffff0000u);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(f0 - h0, f1 - h1);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
 
 template <int KS, int CIN_PAD, int NPAD, int S, int AS, int EPI, int CONCAT, int NBLK, int TPS>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -376,30 +385,34 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
         const int gx = tx * C::TILE_W + s * kSubW + px;
         const bool inside = gx < g.W && gy < g.H;
         const uint32_t t_addr = tmem_base + lane_base + (uint32_t)((acc * S + s) * C::SUB_COLS);
-        // NC accumulator columns starting at output channel ch0 (+ the a_hi x w_lo half when CONCAT);
-        // all TMEM loads of a group are in flight before the single wait
-        auto load_cols = [&](int ch0, float* f, auto nc_tag) {
+        // Issue the TMEM loads of NC accumulator columns starting at output channel ch0 (+ the
+        // a_hi x w_lo half when CONCAT); the caller waits once, later, so loads overlap ALU work.
+        auto issue_cols = [&](int ch0, uint32_t* v, uint32_t* w, auto nc_tag) {
           constexpr int NC = decltype(nc_tag)::value;
           const int blk = NBLK > 1 ? ch0 / NPAD : 0;
           const uint32_t col = (uint32_t)(blk * C::BLK_COLS + (NBLK > 1 ? ch0 % NPAD : ch0));
-          uint32_t v[NC], w[CONCAT ? NC : 1];
 #pragma unroll
           for (int q = 0; q < NC; q += 16) tmem_ld16(t_addr + col + q, v + q);
           if constexpr (CONCAT) {
 #pragma unroll
             for (int q = 0; q < NC; q += 16) tmem_ld16(t_addr + col + NPAD + q, w + q);
           }
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < NC; j++) f[j] = __uint_as_float(v[j]) + (CONCAT ? __uint_as_float(w[CONCAT ? j : 0]) : 0.f);
         };
         if constexpr (EPI == kEpiAct || EPI == kEpiDgrad) {
           constexpr int GC = 32;  // channels per group
+          constexpr int NG = NBLK * NPAD / GC;
           static_assert((NBLK * NPAD) % GC == 0 && (NBLK == 1 || NPAD % GC == 0), "channel groups of 32");
-#pragma unroll 1
-          for (int c0 = 0; c0 < NBLK * NPAD; c0 += GC) {
+          uint32_t vb[2][GC], wb[2][CONCAT ? GC : 1];
+          issue_cols(0, vb[0], wb[0], std::integral_constant<int, GC>{});
+#pragma unroll
+          for (int gi = 0; gi < NG; gi++) {
+            const int c0 = gi * GC;
+            tmem_ld_wait();
+            if (gi + 1 < NG) issue_cols(c0 + GC, vb[(gi + 1) & 1], wb[(gi + 1) & 1], std::integral_constant<int, GC>{});
             float f[GC];
-            load_cols(c0, f, std::integral_constant<int, GC>{});
+#pragma unroll
+            for (int j = 0; j < GC; j++)
+              f[j] = __uint_as_float(vb[gi & 1][j]) + (CONCAT ? __uint_as_float(wb[gi & 1][CONCAT ? j : 0]) : 0.f);
             if (c0 < g.cout && inside) {
               const size_t pix = (size_t)gy * g.W + gx;
               const size_t hw = (size_t)g.H * g.W;
@@ -422,10 +435,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
                     f0 = fmaxf(f[q + j] + s_bias[ch + j], 0.f);
                     f1 = fmaxf(f[q + j + 1] + s_bias[ch + j + 1], 0.f);
                   }
-                  __nv_bfloat16 h0 = __float2bfloat16_rn(f0), h1 = __float2bfloat16_rn(f1);
-                  hi[j >> 1] = pack_bf16x2(h0, h1);
-                  lo[j >> 1] = pack_bf16x2(__float2bfloat16_rn(f0 - __bfloat162float(h0)),
-                                           __float2bfloat16_rn(f1 - __bfloat162float(h1)));
+                  split_bf16x2(f0, f1, hi[j >> 1], lo[j >> 1]);
                 }
                 const bool second = ch >= g.split_c;
                 const ActDst& d = second ? g.dst1 : g.dst0;
@@ -437,8 +447,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
             }
           }
         } else {
+          uint32_t v16[16], w16[CONCAT ? 16 : 1];
+          issue_cols(0, v16, w16, std::integral_constant<int, 16>{});
+          tmem_ld_wait();
           float f[16];
-          load_cols(0, f, std::integral_constant<int, 16>{});
+#pragma unroll
+          for (int j = 0; j < 16; j++) f[j] = __uint_as_float(v16[j]) + (CONCAT ? __uint_as_float(w16[CONCAT ? j : 0]) : 0.f);
           if (inside) {
             const size_t hw = (size_t)g.H * g.W;
             const size_t o = (size_t)n * 3 * hw + (size_t)gy * g.W + gx;

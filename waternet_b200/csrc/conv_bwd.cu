@@ -297,12 +297,11 @@ struct UmmaBwd {
 static size_t dgrad_stage_bytes(const DgradSpec& s) { return (size_t)(s.kpad / 16) * s.ks * s.ks * s.npad * 64; }
 
 int bwd_pack_weights(wn_handle* h, const float* const* params, cudaStream_t stream) {
-  if (!h->bwd) {
-    h->bwd = (UmmaBwd*)calloc(1, sizeof(UmmaBwd));
-    for (int i = 0; i < kNumDgrad; i++) WN_CUDA(cudaMalloc(&h->bwd->stages[i], dgrad_stage_bytes(kDSpecs[i])));
-    WN_CUDA(cudaMalloc(&h->bwd->zero_bias, 256 * sizeof(float)));
-    WN_CUDA(cudaMalloc(&h->bwd->dense, (size_t)128 * 128 * 49 * sizeof(float)));
-  }
+  if (!h->bwd) h->bwd = (UmmaBwd*)calloc(1, sizeof(UmmaBwd));
+  for (int i = 0; i < kNumDgrad; i++)
+    if (!h->bwd->stages[i]) WN_CUDA(cudaMalloc(&h->bwd->stages[i], dgrad_stage_bytes(kDSpecs[i])));
+  if (!h->bwd->zero_bias) WN_CUDA(cudaMalloc(&h->bwd->zero_bias, 256 * sizeof(float)));
+  if (!h->bwd->dense) WN_CUDA(cudaMalloc(&h->bwd->dense, (size_t)128 * 128 * 49 * sizeof(float)));
   UmmaBwd* u = h->bwd;
   WN_CUDA(cudaMemsetAsync(u->zero_bias, 0, 256 * sizeof(float), stream));
   for (int li = 0; li < kNumDgrad; li++) {

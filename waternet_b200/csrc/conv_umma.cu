@@ -99,14 +99,12 @@ static size_t stage_bytes_total(const UmmaLayerSpec& s) {
 }
 
 int umma_pack_weights(wn_handle* h, const float* const* params, cudaStream_t stream) {
-  if (!h->umma) {
-    h->umma = (UmmaWeights*)calloc(1, sizeof(UmmaWeights));
-    for (int i = 0; i < kNumUmmaLayers; i++) {
-      WN_CUDA(cudaMalloc(&h->umma->stages[i], stage_bytes_total(kSpecs[i])));
-      WN_CUDA(cudaMalloc(&h->umma->bias[i], kSpecs[i].npad * kSpecs[i].nblk * sizeof(float)));
-    }
-    WN_CUDA(cudaMalloc(&h->umma->dense, (size_t)224 * 128 * 49 * sizeof(float)));
+  if (!h->umma) h->umma = (UmmaWeights*)calloc(1, sizeof(UmmaWeights));
+  for (int i = 0; i < kNumUmmaLayers; i++) {  // (re)allocate whatever an earlier, failed call left unallocated
+    if (!h->umma->stages[i]) WN_CUDA(cudaMalloc(&h->umma->stages[i], stage_bytes_total(kSpecs[i])));
+    if (!h->umma->bias[i]) WN_CUDA(cudaMalloc(&h->umma->bias[i], kSpecs[i].npad * kSpecs[i].nblk * sizeof(float)));
   }
+  if (!h->umma->dense) WN_CUDA(cudaMalloc(&h->umma->dense, (size_t)224 * 128 * 49 * sizeof(float)));
   UmmaWeights* u = h->umma;
   auto W = [&](int conv) { return params[2 * conv]; };
   auto B = [&](int conv) { return params[2 * conv + 1]; };

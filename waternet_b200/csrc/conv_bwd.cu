@@ -22,16 +22,24 @@ namespace wn {
 // ------------------------------------------------------------------------------------------
 template <int KS, int NCI, int TPG>
 struct WgradCfg {
-  static constexpr int TY = 8, TX = 16;
-  static constexpr int HALO_W = TX + KS - 1, HALO_H = TY + KS - 1;
+  static constexpr int TX = 16;  // one K=16 step = 16 consecutive pixels of a row
+  static constexpr int HALO_W = TX + KS - 1;
+  static constexpr int A_PLANES = NCI / 8;
+  static constexpr int stage_bytes(int ty) {
+    return (2 * 16 * ty * TX * 16 + 2 * A_PLANES * (ty + KS - 1) * HALO_W * 16 + 1023) / 1024 * 1024;
+  }
+  // two pipeline stages (the TMA of the next tile overlaps the MMAs of this one): 8 rows per tile
+  // when that fits in shared memory, else 4
+  static constexpr int TY = 2 * stage_bytes(8) + 2048 <= 227 * 1024 ? 8 : 4;
+  static constexpr int HALO_H = TY + KS - 1;
   static constexpr int G_PLANE = TY * TX * 16;            // one 8-channel plane of the gradient tile
   static constexpr int G_HALF = 16 * G_PLANE;             // M = 128 output channels = 16 planes
   static constexpr int G_BYTES = 2 * G_HALF;              // hi | lo
-  static constexpr int A_PLANES = NCI / 8;
   static constexpr int A_PLANE = HALO_W * HALO_H * 16;
   static constexpr int A_HALF = A_PLANES * A_PLANE;
-  static constexpr int A_BYTES = (2 * A_HALF + 1023) / 1024 * 1024;
-  static constexpr int SMEM_BYTES = G_BYTES + A_BYTES + 1024 + 1024;
+  static constexpr int STAGE = stage_bytes(TY);
+  static constexpr int NSTAGE = 2;
+  static constexpr int SMEM_BYTES = NSTAGE * STAGE + 1024 + 1024;
   static constexpr int NGROUPS = (KS * KS + TPG - 1) / TPG;
   static constexpr int COLS = TPG * NCI;
   static constexpr int TMEM_COLS = COLS <= 32 ? 32 : COLS <= 64 ? 64 : COLS <= 128 ? 128 : COLS <= 256 ? 256 : 512;
@@ -58,13 +66,12 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
   using C = WgradCfg<KS, NCI, TPG>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* g_tile = smem;
-  uint8_t* a_tile = smem + C::G_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(a_tile + C::A_BYTES);
-  uint64_t* full = bars;
-  uint64_t* empty = bars + 1;
-  uint64_t* done = bars + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+  // stage s: [gradient tile hi | lo][activation halo hi | lo]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::NSTAGE * C::STAGE);
+  uint64_t* full = bars;                 // [NSTAGE]
+  uint64_t* empty = bars + C::NSTAGE;    // [NSTAGE]
+  uint64_t* done = bars + 2 * C::NSTAGE;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::NSTAGE + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int group = blockIdx.x;
@@ -75,10 +82,11 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
   const int ntaps = min(TPG, KS * KS - tap0);
 
   // planes the TMA never writes (output channels beyond co_planes*8) must read as zero
-  for (int i = tid; i < C::G_BYTES / 16; i += kWgradThreads) reinterpret_cast<uint4*>(g_tile)[i] = make_uint4(0, 0, 0, 0);
+  for (int st = 0; st < C::NSTAGE; st++)
+    for (int i = tid; i < C::G_BYTES / 16; i += kWgradThreads)
+      reinterpret_cast<uint4*>(smem + st * C::STAGE)[i] = make_uint4(0, 0, 0, 0);
   if (tid == 0) {
-    mbar_init(full, 1);
-    mbar_init(empty, 1);
+    for (int st = 0; st < C::NSTAGE; st++) { mbar_init(&full[st], 1); mbar_init(&empty[st], 1); }
     mbar_init(done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -97,6 +105,7 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
 
   if (warp == 4) {
     if (lane == 0) {
+      int st = 0;
       uint32_t phase = 0;
       for (int i = 0; i < my_tiles; i++) {
         const int tile = blockIdx.y + i * gridDim.y;
@@ -104,13 +113,15 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
         const int rem = tile - n * g.tiles_x * g.tiles_y;
         const int ty = rem / g.tiles_x, tx = rem - ty * g.tiles_x;
         const int x0 = tx * C::TX, y0 = ty * C::TY;
-        mbar_wait(empty, phase ^ 1);
-        mbar_expect_tx(full, (uint32_t)(2 * g.co_planes * C::G_PLANE + 2 * C::A_HALF));
-        tma_load_5d(g_tile, &tmap_g, full, 0, x0, y0, 0, n);
-        tma_load_5d(g_tile + C::G_HALF, &tmap_g, full, 0, x0, y0, g.planes_half, n);
-        tma_load_5d(a_tile, &tmap_a, full, 0, x0 - KS / 2, y0 - KS / 2, 0, n);
-        tma_load_5d(a_tile + C::A_HALF, &tmap_a, full, 0, x0 - KS / 2, y0 - KS / 2, C::A_PLANES, n);
-        phase ^= 1;
+        uint8_t* g_tile = smem + st * C::STAGE;
+        uint8_t* a_tile = g_tile + C::G_BYTES;
+        mbar_wait(&empty[st], phase ^ 1);
+        mbar_expect_tx(&full[st], (uint32_t)(2 * g.co_planes * C::G_PLANE + 2 * C::A_HALF));
+        tma_load_5d(g_tile, &tmap_g, &full[st], 0, x0, y0, 0, n);
+        tma_load_5d(g_tile + C::G_HALF, &tmap_g, &full[st], 0, x0, y0, g.planes_half, n);
+        tma_load_5d(a_tile, &tmap_a, &full[st], 0, x0 - KS / 2, y0 - KS / 2, 0, n);
+        tma_load_5d(a_tile + C::A_HALF, &tmap_a, &full[st], 0, x0 - KS / 2, y0 - KS / 2, C::A_PLANES, n);
+        if (++st == C::NSTAGE) { st = 0; phase ^= 1; }
       }
     }
   } else if (warp == 5) {
@@ -119,12 +130,13 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
     constexpr uint32_t g_hi32 = ((uint32_t)C::G_PLANE >> 4) | (1u << 14);
     constexpr uint32_t a_hi32 = ((uint32_t)C::A_PLANE >> 4) | (1u << 14);
     constexpr uint32_t lbo = (128u >> 4) << 16;
-    const uint32_t g_lo32 = (smem_u32(g_tile) >> 4) | lbo;
-    const uint32_t a_lo32 = (smem_u32(a_tile) >> 4) | lbo;
+    int st = 0;
     uint32_t phase = 0;
     for (int i = 0; i < my_tiles; i++) {
-      mbar_wait(full, phase);
+      mbar_wait(&full[st], phase);
       tc_fence_after();
+      const uint32_t g_lo32 = (smem_u32(smem + st * C::STAGE) >> 4) | lbo;
+      const uint32_t a_lo32 = (smem_u32(smem + st * C::STAGE + C::G_BYTES) >> 4) | lbo;
       if (elect_one_sync()) {
         for (int tl = 0; tl < ntaps; tl++) {
           const int tap = tap0 + tl;
@@ -140,11 +152,11 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
             umma_bf16_split(d, g_row, g_hi32, a_row + (uint32_t)(C::A_HALF >> 4), a_hi32, idesc, 1u);         // g_hi x a_lo
           }
         }
-        umma_commit(empty);
+        umma_commit(&empty[st]);
         if (i == my_tiles - 1) umma_commit(done);
       }
       __syncwarp();
-      phase ^= 1;
+      if (++st == C::NSTAGE) { st = 0; phase ^= 1; }
     }
   } else if (warp < 4) {
     mbar_wait(done, 0);
@@ -441,7 +453,7 @@ static int launch_wgrad(wn_handle* h, uint4* gplanes, int co_valid, uint4* aplan
   a.tiles_x = (W + C::TX - 1) / C::TX;
   a.tiles_y = (H + C::TY - 1) / C::TY;
   const long long tiles = (long long)a.tiles_x * a.tiles_y * n;
-  long long splits = (2ll * h->sm_count + C::NGROUPS - 1) / C::NGROUPS;
+  long long splits = h->sm_count / C::NGROUPS;  // one wave: every CTA owns an SM (shared memory footprint)
   if (splits > tiles) splits = tiles;
   if (splits < 1) splits = 1;
   WN_CUDA(cudaMemsetAsync(dense, 0, (size_t)KS * KS * 128 * NCI * sizeof(float), stream));

@@ -356,3 +356,29 @@ def test_native_training_steps_track_the_torch_graph():
         lb.append(loss.item())
     assert la[-1] < la[0]
     assert np.allclose(la, lb, rtol=2e-3), (la, lb)
+
+
+def test_gpu_batch_loader_matches_per_item_path():
+    """GpuBatchLoader (one batched preprocess on the device) == the reference-style per-item dictionary."""
+    from waternet_b200.training_utils import GpuBatchLoader, SyntheticUIEB
+    ds = SyntheticUIEB(length=10, im_height=48, im_width=64, seed=3)
+    subset = torch.utils.data.Subset(ds, [7, 2, 5, 0, 9])
+    loader = GpuBatchLoader(subset, batch_size=2, device="cuda:0", augment=False)
+    assert len(loader) == 3
+    seen = 0
+    for b, batch in enumerate(loader):
+        for j in range(batch["raw"].shape[0]):
+            raw, ref = ds.pair(subset.indices[b * 2 + j])
+            wb, gc, he = opre.transform(raw)
+            for key, arr in (("raw", raw), ("wb", wb), ("gc", gc), ("he", he), ("ref", ref)):
+                assert np.array_equal(batch[key][j].cpu().numpy(), opre.arr2ten(arr)[0]), key
+            seen += 1
+    assert seen == 5
+    # augmentation: raw and ref receive the same flips / rotations, values only permuted
+    aug = GpuBatchLoader(ds, batch_size=4, device="cuda:0", augment=True, seed=0)
+    batch = next(iter(aug))
+    assert batch["raw"].shape == (4, 3, 48, 64) and batch["ref"].shape == (4, 3, 48, 64)
+    for j in range(4):
+        raw, ref = ds.pair(j)
+        assert np.array_equal(np.sort((batch["raw"][j].cpu().numpy() * 255).round().astype(np.uint8).ravel()), np.sort(raw.ravel()))
+        assert np.array_equal(np.sort((batch["ref"][j].cpu().numpy() * 255).round().astype(np.uint8).ravel()), np.sort(ref.ravel()))

@@ -13,7 +13,7 @@ from timeit import default_timer as timer
 import torch
 
 from waternet.net import WaterNet
-from waternet.training_utils import FlipRotate, SyntheticUIEB, UIEBDataset
+from waternet.training_utils import FlipRotate, GpuBatchLoader, SyntheticUIEB, UIEBDataset
 from waternet_b200 import training as T
 
 
@@ -30,6 +30,9 @@ def main():
     ap.add_argument("--seed", type=int, default=None, help="(Optional) Seed for torch, defaults to None")
     ap.add_argument("--synthetic", action="store_true", help="Use UIEB-shaped synthetic pairs (no dataset offline)")
     ap.add_argument("--precision", default="default", choices=["default", "fp32", "bf16x3"])
+    ap.add_argument("--loader", default="gpu", choices=["gpu", "torch"],
+                    help="gpu: batches augmented + preprocessed on the device in one call; torch: the reference's "
+                         "per-item DataLoader path")
     args = ap.parse_args()
     if args.seed is not None:
         torch.manual_seed(args.seed)
@@ -39,18 +42,23 @@ def main():
     print(f"Using device: {device}")
     savedir = T.next_run_dir(root / "training")
 
-    aug = FlipRotate(seed=args.seed)
+    aug = FlipRotate(seed=args.seed) if args.loader == "torch" else None
     raw_dir, ref_dir = root / "data/raw-890", root / "data/reference-890"
     if args.synthetic or not raw_dir.exists():
         if not args.synthetic:
             print(f"{raw_dir} not found: falling back to --synthetic data")
         dataset = SyntheticUIEB(890, args.height, args.width, seed=args.seed or 0, transform=aug)
     else:
-        dataset = UIEBDataset(raw_dir, ref_dir, im_height=args.height, im_width=args.width, transform=aug)
+        dataset = UIEBDataset(raw_dir, ref_dir, im_height=args.height, im_width=args.width,
+                              transform=aug if aug is not None else (lambda image, mask: {"image": image, "mask": mask}))
     n_val = 90 if len(dataset) >= 180 else max(1, len(dataset) // 10)
     train_set, val_set = torch.utils.data.random_split(dataset, [len(dataset) - n_val, n_val])
-    train_loader = torch.utils.data.DataLoader(train_set, batch_size=args.batch_size)
-    val_loader = torch.utils.data.DataLoader(val_set, batch_size=args.batch_size)
+    if args.loader == "gpu":
+        train_loader = GpuBatchLoader(train_set, args.batch_size, device, augment=True, seed=args.seed)
+        val_loader = GpuBatchLoader(val_set, args.batch_size, device, augment=True, seed=args.seed)
+    else:
+        train_loader = torch.utils.data.DataLoader(train_set, batch_size=args.batch_size)
+        val_loader = torch.utils.data.DataLoader(val_set, batch_size=args.batch_size)
 
     model = WaterNet(precision=args.precision)
     if args.weights is not None:

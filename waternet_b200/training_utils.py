@@ -83,7 +83,8 @@ class UIEBDataset(torch.utils.data.Dataset):
     def __len__(self):
         return len(self.im_fns)
 
-    def __getitem__(self, idx):
+    def pair(self, idx):
+        """Decoded, resized RGB uint8 (raw, ref) arrays of item ``idx`` -- no augmentation, no preprocess."""
         import cv2  # file decode / resize only
         raw_im = cv2.imread(os.fspath(self.raw_dir / self.im_fns[idx]))
         ref_im = cv2.imread(os.fspath(self.ref_dir / self.im_fns[idx]))
@@ -93,6 +94,10 @@ class UIEBDataset(torch.utils.data.Dataset):
             size = (int(raw_im.shape[0] / 32) * 32, int(raw_im.shape[1] / 32) * 32)
         raw_im = cv2.cvtColor(cv2.resize(raw_im, size), cv2.COLOR_BGR2RGB)
         ref_im = cv2.cvtColor(cv2.resize(ref_im, size), cv2.COLOR_BGR2RGB)
+        return raw_im, ref_im
+
+    def __getitem__(self, idx):
+        raw_im, ref_im = self.pair(idx)
         if self.transform is not None:
             t = self.transform(image=raw_im, mask=ref_im)
             raw_im, ref_im = t["image"], t["mask"]
@@ -119,9 +124,77 @@ class SyntheticUIEB(torch.utils.data.Dataset):
         raw = np.maximum(raw, 1)
         return raw, ref
 
+    def pair(self, idx):
+        return self._scene(idx)
+
     def __getitem__(self, idx):
         raw_im, ref_im = self._scene(idx)
         if self.transform is not None:
             t = self.transform(image=raw_im, mask=ref_im)
             raw_im, ref_im = t["image"], t["mask"]
         return _item(raw_im, ref_im)
+
+
+class GpuBatchLoader:
+    """Training batches assembled on the GPU.
+
+    The reference's loop is data-loading bound: every item runs ``transform`` and four ``arr2ten`` on
+    the CPU in the main process (``training_utils.py:89-132``, ``train.py:234``).  Here a batch of
+    uint8 (raw, ref) pairs goes to the device once; the flip / rot90 augmentation (same p=0.5 choices
+    as ``training_utils.py:72-78``, applied identically to raw and ref) and ONE batched
+    ``wn_preprocess_u8`` produce the five fp32 tensors of the reference's item dictionary, already
+    on the device.  ``dataset`` needs ``__len__`` and ``pair(idx) -> (raw_u8, ref_u8)`` (both
+    datasets of this module have it); ``torch.utils.data.Subset`` views are accepted.
+    """
+
+    def __init__(self, dataset, batch_size: int, device=None, augment: bool = True, seed: Optional[int] = None,
+                 drop_last: bool = False):
+        from .engine import get_engine
+        self.engine = get_engine(device)
+        self.indices = list(range(len(dataset)))
+        while isinstance(dataset, torch.utils.data.Subset):  # unwrap random_split views
+            self.indices = [dataset.indices[i] for i in self.indices]
+            dataset = dataset.dataset
+        self.dataset = dataset
+        self.batch_size = batch_size
+        self.augment = augment
+        self.drop_last = drop_last
+        self.rng = np.random.default_rng(seed)
+
+    def __len__(self):
+        n = len(self.indices)
+        return n // self.batch_size if self.drop_last else (n + self.batch_size - 1) // self.batch_size
+
+    def _augment(self, raw: torch.Tensor, ref: torch.Tensor):
+        """Per-sample HorizontalFlip / VerticalFlip / RandomRotate90 (p=0.5 each) on NHWC uint8 batches."""
+        square = raw.shape[1] == raw.shape[2]
+        outs_raw, outs_ref = [], []
+        for i in range(raw.shape[0]):
+            a, b = raw[i], ref[i]
+            if self.rng.random() < 0.5:
+                a, b = a.flip(1), b.flip(1)
+            if self.rng.random() < 0.5:
+                a, b = a.flip(0), b.flip(0)
+            if self.rng.random() < 0.5:
+                k = int(self.rng.integers(0, 4))
+                if not square:
+                    k = (k // 2) * 2  # a quarter turn would change the shape inside a batch
+                a, b = torch.rot90(a, k, (0, 1)), torch.rot90(b, k, (0, 1))
+            outs_raw.append(a)
+            outs_ref.append(b)
+        return torch.stack(outs_raw).contiguous(), torch.stack(outs_ref).contiguous()
+
+    def __iter__(self):
+        dev = self.engine.device
+        for start in range(0, len(self.indices), self.batch_size):
+            idx = self.indices[start:start + self.batch_size]
+            if self.drop_last and len(idx) < self.batch_size:
+                break
+            pairs = [self.dataset.pair(i) for i in idx]
+            raw = torch.from_numpy(np.stack([p[0] for p in pairs])).to(dev, non_blocking=True)
+            ref = torch.from_numpy(np.stack([p[1] for p in pairs])).to(dev, non_blocking=True)
+            if self.augment:
+                raw, ref = self._augment(raw, ref)
+            pre = self.engine.preprocess(raw, tensors=True, images=False)
+            yield {"raw": pre["x"], "wb": pre["wb"], "gc": pre["gc"], "he": pre["he"],
+                   "ref": (ref.float() / 255).permute(0, 3, 1, 2).contiguous()}

@@ -26,7 +26,9 @@ def arr2ten_noeinops(arr, device=None) -> torch.Tensor:
     t = torch.from_numpy(np.ascontiguousarray(a)).to(eng.device)
     if t.dtype == torch.uint8 and t.shape[3] == 3:
         return eng.preprocess(t, tensors=True, images=False)["x"]
-    return (t / 255).permute(0, 3, 1, 2)
+    # other dtypes / channel counts: true division (a 0-dim tensor divisor; "tensor / python scalar" on CUDA
+    # multiplies by a reciprocal and would differ from the reference by an ulp)
+    return (t / torch.tensor(255.0, device=t.device)).permute(0, 3, 1, 2)
 
 
 def ten2arr_noeinops(ten: torch.Tensor) -> np.ndarray:

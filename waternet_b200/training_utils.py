@@ -196,5 +196,7 @@ class GpuBatchLoader:
             if self.augment:
                 raw, ref = self._augment(raw, ref)
             pre = self.engine.preprocess(raw, tensors=True, images=False)
-            yield {"raw": pre["x"], "wb": pre["wb"], "gc": pre["gc"], "he": pre["he"],
-                   "ref": (ref.float() / 255).permute(0, 3, 1, 2).contiguous()}
+            # u/255 must be the true fp32 quotient (arr2ten): torch's CUDA "tensor / scalar" multiplies by a
+            # reciprocal, so the reference image goes through the library's exact table as well
+            ref_t = self.engine.preprocess(ref, tensors=True, images=False)["x"]
+            yield {"raw": pre["x"], "wb": pre["wb"], "gc": pre["gc"], "he": pre["he"], "ref": ref_t}

@@ -1,0 +1,22 @@
+"""Tiny end-to-end pass (preprocess, both forward modes, training forward + backward) for compute-sanitizer."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from waternet_b200 import _lib
+from waternet_b200.engine import get_engine
+from waternet_b200.net import WaterNet
+
+torch.manual_seed(0)
+eng = get_engine("cuda:0")
+m = WaterNet().cuda()
+eng.pack_weights(m._ordered_params())
+rgb = torch.randint(0, 256, (2, 37, 53, 3), dtype=torch.uint8, device="cuda")
+for mode in (_lib.MODE_BF16X3, _lib.MODE_FP32_SIMT):
+    out = eng.enhance(rgb, mode=mode)
+pre = eng.preprocess(rgb)
+ins = [pre[k] for k in ("x", "wb", "he", "gc")]
+m.train()
+loss = m(*ins).square().mean()
+loss.backward()
+torch.cuda.synchronize()
+print("ok", float(loss), float(m.cmg.conv2.weight.grad.abs().sum()))

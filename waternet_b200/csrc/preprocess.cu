@@ -299,6 +299,7 @@ struct ApplyOut {
   uint8_t* u8[3];   // wb, he, gc     -- NHWC, may be null
 };
 
+template <bool VEC4>
 __global__ void __launch_bounds__(256)
 apply_kernel(const uint8_t* __restrict__ rgb, int H, int W, int th, int tw,
              const Tables* __restrict__ tables, const uint8_t* __restrict__ clahe_lut,
@@ -331,47 +332,92 @@ apply_kernel(const uint8_t* __restrict__ rgb, int H, int W, int th, int tw,
   __syncthreads();
   const int plane = H * W;
   const float inv_tw = __fdiv_rn(1.0f, (float)tw), inv_th = __fdiv_rn(1.0f, (float)th);
-  for (int it = 0; it < kApplyIters; it++) {
-  const int pix = (blockIdx.x * kApplyIters + it) * 256 + tid;
-  if (pix >= plane) break;
-  const int y = pix / W, x = pix - y * W;
-  const uint8_t* p = rgb + ((size_t)n * plane + pix) * 3;
-  const int r = p[0], g = p[1], b = p[2];
 
-  // hist-eq: RGB -> Lab, CLAHE bilinear blend of the four neighbouring tile LUTs, Lab -> RGB
-  int L, A, Bv;
-  rgb2lab(s_gtab, s_ctab, r, g, b, L, A, Bv);
-  float txf = __fsub_rn(__fmul_rn((float)x, inv_tw), 0.5f);
-  float tyf = __fsub_rn(__fmul_rn((float)y, inv_th), 0.5f);
-  int tx1 = (int)floorf(txf), ty1 = (int)floorf(tyf);
-  float xa = __fsub_rn(txf, (float)tx1), ya = __fsub_rn(tyf, (float)ty1);
-  float xa1 = __fsub_rn(1.0f, xa), ya1 = __fsub_rn(1.0f, ya);
-  int tx2 = min(tx1 + 1, 7), ty2 = min(ty1 + 1, 7);
-  tx1 = max(tx1, 0);
-  ty1 = max(ty1, 0);
-  float l11 = (float)s_clahe[(ty1 * 8 + tx1) * 256 + L];
-  float l12 = (float)s_clahe[(ty1 * 8 + tx2) * 256 + L];
-  float l21 = (float)s_clahe[(ty2 * 8 + tx1) * 256 + L];
-  float l22 = (float)s_clahe[(ty2 * 8 + tx2) * 256 + L];
-  float top = __fadd_rn(__fmul_rn(l11, xa1), __fmul_rn(l12, xa));
-  float bot = __fadd_rn(__fmul_rn(l21, xa1), __fmul_rn(l22, xa));
-  float res = __fadd_rn(__fmul_rn(top, ya1), __fmul_rn(bot, ya));
-  int Leq = (int)fminf(fmaxf(rintf(res), 0.f), 255.f);
-  int hr, hg, hb;
-  lab2rgb(s_ytab, s_fytab, s_igtab, Leq, A, Bv, hr, hg, hb);
+  // one pixel: levels of the raw, white-balanced, hist-equalised and gamma-corrected images
+  auto one_pixel = [&](int pix, int r, int g, int b, int* lv /* [4][3] */) {
+    const int y = pix / W, x = pix - y * W;
+    // hist-eq: RGB -> Lab, CLAHE bilinear blend of the four neighbouring tile LUTs, Lab -> RGB
+    int L, A, Bv;
+    rgb2lab(s_gtab, s_ctab, r, g, b, L, A, Bv);
+    float txf = __fsub_rn(__fmul_rn((float)x, inv_tw), 0.5f);
+    float tyf = __fsub_rn(__fmul_rn((float)y, inv_th), 0.5f);
+    int tx1 = (int)floorf(txf), ty1 = (int)floorf(tyf);
+    float xa = __fsub_rn(txf, (float)tx1), ya = __fsub_rn(tyf, (float)ty1);
+    float xa1 = __fsub_rn(1.0f, xa), ya1 = __fsub_rn(1.0f, ya);
+    int tx2 = min(tx1 + 1, 7), ty2 = min(ty1 + 1, 7);
+    tx1 = max(tx1, 0);
+    ty1 = max(ty1, 0);
+    float l11 = (float)s_clahe[(ty1 * 8 + tx1) * 256 + L];
+    float l12 = (float)s_clahe[(ty1 * 8 + tx2) * 256 + L];
+    float l21 = (float)s_clahe[(ty2 * 8 + tx1) * 256 + L];
+    float l22 = (float)s_clahe[(ty2 * 8 + tx2) * 256 + L];
+    float top = __fadd_rn(__fmul_rn(l11, xa1), __fmul_rn(l12, xa));
+    float bot = __fadd_rn(__fmul_rn(l21, xa1), __fmul_rn(l22, xa));
+    float res = __fadd_rn(__fmul_rn(top, ya1), __fmul_rn(bot, ya));
+    int Leq = (int)fminf(fmaxf(rintf(res), 0.f), 255.f);
+    lv[0] = r; lv[1] = g; lv[2] = b;
+    lv[3] = s_wb[r]; lv[4] = s_wb[256 + g]; lv[5] = s_wb[512 + b];
+    lab2rgb(s_ytab, s_fytab, s_igtab, Leq, A, Bv, lv[6], lv[7], lv[8]);
+    lv[9] = s_gamma[r]; lv[10] = s_gamma[g]; lv[11] = s_gamma[b];
+  };
 
-  const int wr = s_wb[r], wg = s_wb[256 + g], wbb = s_wb[512 + b];
-  const int gr = s_gamma[r], gg = s_gamma[g], gb = s_gamma[b];
-
-  const size_t o = (size_t)n * 3 * plane + pix;
-  if (out.f32[0]) { float* q = out.f32[0] + o; q[0] = s_div[r]; q[plane] = s_div[g]; q[2 * plane] = s_div[b]; }
-  if (out.f32[1]) { float* q = out.f32[1] + o; q[0] = s_div[wr]; q[plane] = s_div[wg]; q[2 * plane] = s_div[wbb]; }
-  if (out.f32[2]) { float* q = out.f32[2] + o; q[0] = s_div[hr]; q[plane] = s_div[hg]; q[2 * plane] = s_div[hb]; }
-  if (out.f32[3]) { float* q = out.f32[3] + o; q[0] = s_div[gr]; q[plane] = s_div[gg]; q[2 * plane] = s_div[gb]; }
-  const size_t o8 = ((size_t)n * plane + pix) * 3;
-  if (out.u8[0]) { uint8_t* q = out.u8[0] + o8; q[0] = wr; q[1] = wg; q[2] = wbb; }
-  if (out.u8[1]) { uint8_t* q = out.u8[1] + o8; q[0] = hr; q[1] = hg; q[2] = hb; }
-  if (out.u8[2]) { uint8_t* q = out.u8[2] + o8; q[0] = gr; q[1] = gg; q[2] = gb; }
+  if constexpr (VEC4) {
+    // four consecutive pixels per thread: 12 input bytes as three 32-bit loads, one float4 store per plane
+    for (int it = 0; it < kApplyIters; it++) {
+      const int pix = ((blockIdx.x * kApplyIters + it) * 256 + tid) * 4;
+      if (pix >= plane) break;
+      const uint32_t* p32 = reinterpret_cast<const uint32_t*>(rgb + ((size_t)n * plane + pix) * 3);
+      const uint32_t w0 = p32[0], w1 = p32[1], w2 = p32[2];
+      const int px[4][3] = {{(int)(w0 & 255), (int)((w0 >> 8) & 255), (int)((w0 >> 16) & 255)},
+                            {(int)(w0 >> 24), (int)(w1 & 255), (int)((w1 >> 8) & 255)},
+                            {(int)((w1 >> 16) & 255), (int)(w1 >> 24), (int)(w2 & 255)},
+                            {(int)((w2 >> 8) & 255), (int)((w2 >> 16) & 255), (int)(w2 >> 24)}};
+      int lv[4][12];
+#pragma unroll
+      for (int k = 0; k < 4; k++) one_pixel(pix + k, px[k][0], px[k][1], px[k][2], lv[k]);
+      const size_t o = (size_t)n * 3 * plane + pix;
+#pragma unroll
+      for (int t = 0; t < 4; t++) {
+        if (!out.f32[t]) continue;
+#pragma unroll
+        for (int c = 0; c < 3; c++)
+          *reinterpret_cast<float4*>(out.f32[t] + o + (size_t)c * plane) =
+              make_float4(s_div[lv[0][t * 3 + c]], s_div[lv[1][t * 3 + c]], s_div[lv[2][t * 3 + c]], s_div[lv[3][t * 3 + c]]);
+      }
+      const size_t o8 = ((size_t)n * plane + pix) * 3;
+#pragma unroll
+      for (int t = 0; t < 3; t++) {
+        if (!out.u8[t]) continue;
+        uint32_t* q = reinterpret_cast<uint32_t*>(out.u8[t] + o8);
+        const int* a0 = lv[0] + (t + 1) * 3; const int* a1 = lv[1] + (t + 1) * 3;
+        const int* a2 = lv[2] + (t + 1) * 3; const int* a3 = lv[3] + (t + 1) * 3;
+        q[0] = (uint32_t)a0[0] | ((uint32_t)a0[1] << 8) | ((uint32_t)a0[2] << 16) | ((uint32_t)a1[0] << 24);
+        q[1] = (uint32_t)a1[1] | ((uint32_t)a1[2] << 8) | ((uint32_t)a2[0] << 16) | ((uint32_t)a2[1] << 24);
+        q[2] = (uint32_t)a2[2] | ((uint32_t)a3[0] << 8) | ((uint32_t)a3[1] << 16) | ((uint32_t)a3[2] << 24);
+      }
+    }
+  } else {
+    for (int it = 0; it < kApplyIters; it++) {
+      const int pix = (blockIdx.x * kApplyIters + it) * 256 + tid;
+      if (pix >= plane) break;
+      const uint8_t* p = rgb + ((size_t)n * plane + pix) * 3;
+      int lv[12];
+      one_pixel(pix, p[0], p[1], p[2], lv);
+      const size_t o = (size_t)n * 3 * plane + pix;
+#pragma unroll
+      for (int t = 0; t < 4; t++) {
+        if (!out.f32[t]) continue;
+        float* q = out.f32[t] + o;
+        q[0] = s_div[lv[t * 3]]; q[plane] = s_div[lv[t * 3 + 1]]; q[2 * (size_t)plane] = s_div[lv[t * 3 + 2]];
+      }
+      const size_t o8 = ((size_t)n * plane + pix) * 3;
+#pragma unroll
+      for (int t = 0; t < 3; t++) {
+        if (!out.u8[t]) continue;
+        uint8_t* q = out.u8[t] + o8;
+        q[0] = lv[(t + 1) * 3]; q[1] = lv[(t + 1) * 3 + 1]; q[2] = lv[(t + 1) * 3 + 2];
+      }
+    }
   }
 }
 
@@ -477,8 +523,19 @@ int preprocess_u8(wn_handle* h, const uint8_t* rgb, int n, int H, int W, float* 
   ao.f32[0] = x; ao.f32[1] = wb; ao.f32[2] = he; ao.f32[3] = gc;
   ao.u8[0] = wb_u8; ao.u8[1] = he_u8; ao.u8[2] = gc_u8;
   TimedScope ts(h, kSlotApply, stream);
-  apply_kernel<<<dim3((H * W + 256 * kApplyIters - 1) / (256 * kApplyIters), n), 256, 0, stream>>>(rgb, H, W, g.th, g.tw,
-                                                                 h->d_tables, clahe_lut, wb_lut, ao);
+  // vector path: 4 pixels per thread needs 4-pixel groups that do not straddle images (and aligned bases)
+  const bool vec4 = (H * W) % 4 == 0 && ((uintptr_t)rgb % 4) == 0 && ((uintptr_t)x % 16) == 0 &&
+                    ((uintptr_t)wb % 16) == 0 && ((uintptr_t)he % 16) == 0 && ((uintptr_t)gc % 16) == 0 &&
+                    ((uintptr_t)wb_u8 % 4) == 0 && ((uintptr_t)he_u8 % 4) == 0 && ((uintptr_t)gc_u8 % 4) == 0;
+  if (vec4) {
+    const int per_cta = 256 * kApplyIters * 4;
+    apply_kernel<true><<<dim3((H * W + per_cta - 1) / per_cta, n), 256, 0, stream>>>(rgb, H, W, g.th, g.tw, h->d_tables,
+                                                                                   clahe_lut, wb_lut, ao);
+  } else {
+    const int per_cta = 256 * kApplyIters;
+    apply_kernel<false><<<dim3((H * W + per_cta - 1) / per_cta, n), 256, 0, stream>>>(rgb, H, W, g.th, g.tw, h->d_tables,
+                                                                                    clahe_lut, wb_lut, ao);
+  }
   WN_LAUNCH_CHECK(h);
   return WN_OK;
 }

@@ -37,4 +37,21 @@ for (n, h, w) in [(1, 112, 112), (16, 112, 112), (1, 480, 720), (1, 1080, 1920)]
         e2e_ms, e2e_wall = timed(lambda: eng.enhance(rgb, mode=mode, out_u8=out), 50 if h < 500 else 10)
         res.append({"batch": n, "h": h, "w": w, "mode": name, "forward_ms": round(dev_ms, 4), "forward_wall_ms": round(wall_ms, 4),
                     "enhance_ms": round(e2e_ms, 4), "images_per_s_enhance": round(n / (e2e_ms * 1e-3), 1)})
+# host-buffer call with and without CUDA-graph replay (small frames are launch-bound)
+import numpy as np
+from waternet_b200.api import Enhancer
+for (n, h, w) in [(1, 112, 112), (1, 240, 320), (1, 480, 720)]:
+    frame = np.random.default_rng(0).integers(0, 256, (n, h, w, 3), dtype=np.uint8)
+    row = {"batch": n, "h": h, "w": w, "mode": "bf16x3 host-buffer call"}
+    for flag in (False, True):
+        enh = Enhancer(m, cuda_graph=flag)
+        pin_in = torch.from_numpy(frame).pin_memory()
+        pin_out = torch.empty_like(pin_in).pin_memory()
+        for _ in range(5):
+            enh.enhance_pinned(pin_in, pin_out)
+        t0 = time.perf_counter()
+        for _ in range(100):
+            enh.enhance_pinned(pin_in, pin_out)
+        row["graph_ms" if flag else "launch_ms"] = round((time.perf_counter() - t0) * 10, 4)
+    res.append(row)
 print(json.dumps(res))

@@ -16,9 +16,16 @@ from .engine import Engine, get_engine
 
 
 class Enhancer:
-    """Holds a model's packed weights and pinned staging buffers for repeated calls."""
+    """Holds a model's packed weights and pinned staging buffers for repeated calls.
 
-    def __init__(self, model, device=None, precision: Optional[str] = None):
+    For small frames the ~15 kernel launches of one enhance call cost more host time than the GPU
+    needs to run them; with ``cuda_graph=True`` (default for batches up to ``GRAPH_MAX_PIXELS``) the
+    launch sequence is captured once per input shape into a CUDA graph and replayed.
+    """
+
+    GRAPH_MAX_PIXELS = 1 << 20
+
+    def __init__(self, model, device=None, precision: Optional[str] = None, cuda_graph: bool = True):
         self.engine: Engine = get_engine(device if device is not None else next(model.parameters()).device)
         self.model = model.to(self.engine.device)
         self.mode = model._mode() if precision is None else {
@@ -27,9 +34,13 @@ class Enhancer:
         self._pin_out = None
         self._dev_in = None
         self._dev_out = None
+        self.cuda_graph = cuda_graph
+        self._graph = None
+        self._graph_key = None
 
     def _buffers(self, shape):
         if self._dev_in is None or tuple(self._dev_in.shape) != tuple(shape):
+            self._graph = None
             self._dev_in = torch.empty(shape, dtype=torch.uint8, device=self.engine.device)
             self._dev_out = torch.empty(shape, dtype=torch.uint8, device=self.engine.device)
 
@@ -52,6 +63,28 @@ class Enhancer:
         out = self._pin_out.numpy().copy()
         return out[0] if single else out
 
+    def _run_kernels(self) -> None:
+        """preprocess -> forward -> postprocess from ``_dev_in`` into ``_dev_out`` (graph replay when small)."""
+        eng = self.engine
+        shape = tuple(self._dev_in.shape)
+        if not self.cuda_graph or shape[0] * shape[1] * shape[2] > self.GRAPH_MAX_PIXELS:
+            eng.enhance(self._dev_in, mode=self.mode, out_u8=self._dev_out)
+            return
+        def key():  # everything a captured launch sequence has baked in
+            ws = eng._ws.get("enhance")
+            return (shape, self.mode, self._dev_in.data_ptr(), self._dev_out.data_ptr(), eng._weights_key,
+                    None if ws is None else (ws.data_ptr(), ws.numel()))
+
+        if self._graph is None or self._graph_key != key():
+            eng.enhance(self._dev_in, mode=self.mode, out_u8=self._dev_out)  # warm-up: workspace, func attributes
+            torch.cuda.current_stream(eng.device).synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                eng.enhance(self._dev_in, mode=self.mode, out_u8=self._dev_out)
+            self._graph, self._graph_key = graph, key()
+            return  # the warm-up call already produced this frame's result
+        self._graph.replay()
+
     def enhance_pinned(self, pin_in: torch.Tensor, pin_out: torch.Tensor, after_device=None) -> None:
         """Pinned uint8 NHWC host tensor -> pinned uint8 NHWC host tensor (H2D, kernels, D2H, sync).
 
@@ -59,7 +92,7 @@ class Enhancer:
         """
         self._buffers(tuple(pin_in.shape))
         self._dev_in.copy_(pin_in, non_blocking=True)
-        self.engine.enhance(self._dev_in, mode=self.mode, out_u8=self._dev_out)
+        self._run_kernels()
         if after_device is not None:
             after_device(self._dev_out)
         pin_out.copy_(self._dev_out, non_blocking=True)

@@ -145,6 +145,13 @@ int wn_debug_forward_layer(wn_handle* h, const float* x, const float* wb, const 
                            int width, int mode, int layer, float* dst, void* workspace,
                            size_t workspace_bytes, void* stream);
 
+/*
+ * Bring-up aid: switch pieces of the tensor-core conv pipeline off to attribute time (bit 0: epilogue
+ * stores, bit 1: weight-stage refetch, bit 2: the lo passes).  RESULTS ARE WRONG with any bit set;
+ * 0 restores normal operation.  Used by tools/pipeline_attribution.py only.
+ */
+int wn_debug_set_flags(wn_handle* h, int flags);
+
 /* Number of kernels the library has launched on this handle since creation. */
 uint64_t wn_launch_count(const wn_handle* h);
 

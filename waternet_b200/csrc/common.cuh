@@ -88,6 +88,7 @@ struct wn_handle {
   int sm_count;
   wn::Timing* timing;
   wn::UmmaBwd* bwd;
+  int dbg_flags;  // bring-up switches for the conv kernel (wn_debug_set_flags); 0 in normal use
 };
 
 namespace wn {

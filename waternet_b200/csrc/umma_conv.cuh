@@ -202,6 +202,10 @@ struct ConvArgs {
   // kEpiDgrad: saved forward activation (planes) whose zeros gate the gradient
   const uint4* mask_base;
   int mask_planes_half;
+  // bring-up only (wn_debug_set_flags): bit 0 = epilogue skips its global stores, bit 1 = weight stages
+  // are not re-fetched after the first ring fill, bit 2 = the a_lo / a_hi x w_lo passes are not issued.
+  // Results are wrong with any bit set; used to attribute time to pipeline pieces.
+  int dbg;
 };
 
 __device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b) {
@@ -286,8 +290,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         for (int it = 0; it < C::NCHUNK * C::NSTAGE_PER_CHUNK; it++) {
           mbar_wait(&b_empty[stage], phase ^ 1);
-          mbar_expect_tx(&b_full[stage], C::B_STAGE);
-          bulk_load(b_stages + stage * C::B_STAGE, g.wpk + (size_t)it * C::B_STAGE, C::B_STAGE, &b_full[stage]);
+          if ((g.dbg & 2) && (phase || tile != (int)blockIdx.x)) {
+            mbar_arrive(&b_full[stage]);  // bring-up: reuse whatever the stage holds
+          } else {
+            mbar_expect_tx(&b_full[stage], C::B_STAGE);
+            bulk_load(b_stages + stage * C::B_STAGE, g.wpk + (size_t)it * C::B_STAGE, C::B_STAGE, &b_full[stage]);
+          }
           if (++stage == C::NB) { stage = 0; phase ^= 1; }
         }
       }
@@ -306,7 +314,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
       constexpr uint32_t b_lbo = (uint32_t)((CONCAT ? 2 * NPAD : NPAD) * 16);
       int astage = 0, bstage = 0, acc = 0;
       uint32_t aphase = 0, bphase = 0, tphase = 0;
-      const bool skip_lo = g.skip_lo != nullptr && *g.skip_lo != 0;
+      const bool skip_lo = (g.skip_lo != nullptr && *g.skip_lo != 0) || (g.dbg & 4);
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         mbar_wait(&t_empty[acc], tphase ^ 1);
         tc_fence_after();
@@ -343,7 +351,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
                     umma_bf16_split(d_base + (uint32_t)(s * C::SUB_COLS), a_tap + (uint32_t)(s * kSubW) + a_lo_off,
                                     a_hi32, b_lo32, b_hi32, idesc2, 1u);
                 }
-                if constexpr (!CONCAT) {
+                if (!CONCAT && !(g.dbg & 4)) {
 #pragma unroll
                   for (int s = 0; s < S; s++)  // a_hi x w_lo
                     umma_bf16_split(d_base + (uint32_t)(s * C::SUB_COLS), a_tap + (uint32_t)(s * kSubW), a_hi32,
@@ -413,7 +421,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
 #pragma unroll
             for (int j = 0; j < GC; j++)
               f[j] = __uint_as_float(vb[gi & 1][j]) + (CONCAT ? __uint_as_float(wb[gi & 1][CONCAT ? j : 0]) : 0.f);
-            if (c0 < g.cout && inside) {
+            if (c0 < g.cout && inside && !(g.dbg & 1)) {
               const size_t pix = (size_t)gy * g.W + gx;
               const size_t hw = (size_t)g.H * g.W;
 #pragma unroll
@@ -591,6 +599,7 @@ static int launch_conv(wn_handle* h, int slot, const uint8_t* wpk, const float* 
   if (rc) return rc;
   a.wpk = wpk;
   a.bias = bias;
+  a.dbg = h->dbg_flags;
   a.in_planes_half = CIN_PAD / 8;
   a.tiles_x = (a.W + C::TILE_W - 1) / C::TILE_W;
   a.tiles_y = (a.H + C::TILE_H - 1) / C::TILE_H;

@@ -548,12 +548,12 @@ int backward(wn_handle* h, const float* grad_out, float* const* grads, int n, in
   if ((rc = launch_wgrad<3, 128, 4>(h, t.ga, 128, t.f.a[2], t.dense, n, H, W, stream))) return rc;
   if ((rc = extract(h, t.dense, gw(2), 128, 128, 3, 128, 0, 128, 0, 0, 1.f, stream))) return rc;
   if ((rc = bias_grad(h, t.ga, 16, 128, gb(2), n, hw, stream))) return rc;
-  if ((rc = launch_dgrad<3, 128, 128, 2, 2>(h, kD3, t.ga, t.gb, 128, t.f.a[2], n, H, W, stream))) return rc;
+  if ((rc = launch_dgrad<3, 128, 128, 2, 2, 0, 1, 3>(h, kD3, t.ga, t.gb, 128, t.f.a[2], n, H, W, stream))) return rc;
   // conv2 (5x5): g = gb
   if ((rc = launch_wgrad<5, 128, 4>(h, t.gb, 128, t.f.a[1], t.dense, n, H, W, stream))) return rc;
   if ((rc = extract(h, t.dense, gw(1), 128, 128, 5, 128, 0, 128, 0, 0, 1.f, stream))) return rc;
   if ((rc = bias_grad(h, t.gb, 16, 128, gb(1), n, hw, stream))) return rc;
-  if ((rc = launch_dgrad<5, 128, 128, 2, 2>(h, kD2, t.gb, t.ga, 128, t.f.a[1], n, H, W, stream))) return rc;
+  if ((rc = launch_dgrad<5, 128, 128, 2, 2, 0, 1, 5>(h, kD2, t.gb, t.ga, 128, t.f.a[1], n, H, W, stream))) return rc;
   // conv1 (12 -> 128, 7x7): g = ga, a = act0 (holds v*255 -> scale the gradient back)
   if ((rc = launch_wgrad<7, 16, 32>(h, t.ga, 128, t.f.act0, t.dense, n, H, W, stream))) return rc;
   if ((rc = extract(h, t.dense, gw(0), 128, 12, 7, 16, 0, 12, 0, 0, 1.f / 255.f, stream))) return rc;

@@ -235,10 +235,10 @@ int umma_forward_layers(wn_handle* h, const float* const in[4], const int64_t st
   a.skip_lo = nullptr;
   if (dump(0, b.a[1], 128) || dump(8, b.r[1], 96)) return WN_OK;
   act(b.a[2], 128, nullptr, 0);
-  if ((rc = launch_umma<5, 128, 128, 2, 2, kEpiAct>(h, kC2, b.a[1], a, stream))) return rc;
+  if ((rc = launch_umma<5, 128, 128, 2, 2, kEpiAct, 0, 1, 5>(h, kC2, b.a[1], a, stream))) return rc;
   if (dump(1, b.a[2], 128)) return WN_OK;
   act(b.a[3], 128, nullptr, 0);
-  if ((rc = launch_umma<3, 128, 128, 2, 2, kEpiAct>(h, kC3, b.a[2], a, stream))) return rc;
+  if ((rc = launch_umma<3, 128, 128, 2, 2, kEpiAct, 0, 1, 3>(h, kC3, b.a[2], a, stream))) return rc;
   if (dump(2, b.a[3], 128)) return WN_OK;
   act(b.a[4], 64, nullptr, 0);
   if ((rc = launch_umma<1, 128, 64, 2, 2, kEpiAct, 1>(h, kC4, b.a[3], a, stream))) return rc;

@@ -17,12 +17,12 @@
 // out-of-image pixels come back as zeros from the TMA (padding="same").
 //
 // One persistent CTA per SM, warp-specialised:
-//   warps 0-3, 8-11  epilogue, two groups that split a tile's sub-tiles
+//   warps 0-7  epilogue, two groups that split a tile's sub-tiles
 //              (TMEM -> registers -> bias/act -> bf16 hi/lo planes or fp32)
-//   warp 4     A producer (TMA halo tiles, one 16-channel chunk per stage)
-//   warp 5     B producer (bulk copies of pre-packed weight stages, one (chunk,tap) per stage)
-//   warp 6     MMA issuer (one thread; 3 MMAs per sub-tile per stage)
-//   warp 7     TMEM allocator
+//   warp 8     A producer (TMA halo tiles, one 16-channel chunk per stage)
+//   warp 9     B producer (bulk copies of pre-packed weight stages, 1-9 taps of a chunk per stage)
+//   warp 10    TMEM allocator
+//   warp 11    MMA issuer (converged warp, one elected lane issues; highest warp id = scheduling priority)
 // A CTA tile is S sub-tiles of 8x16 pixels (M = 128 each) sharing every weight stage.
 #include "umma_conv.cuh"
 

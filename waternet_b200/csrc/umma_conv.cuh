@@ -35,6 +35,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
   __trap();
 }
+// One non-blocking probe of a barrier phase; lets a waiter look at the NEXT stage's barrier while
+// it still has work to issue for the current one (the probe's ~100-cycle latency is then hidden).
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return done != 0;
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -131,7 +144,10 @@ __device__ __forceinline__ void tc_fence_after() {
 enum Epilogue { kEpiAct = 0, kEpiSigmoid = 1, kEpiGate = 2, kEpiDgrad = 3 };
 
 constexpr int kSubW = 8, kSubH = 16;  // one M=128 sub-tile: 8 px wide, 16 px tall
-constexpr int kThreads = 384;  // warps 0-3 and 8-11: epilogue; 4: A producer; 5: B producer; 6: MMA; 7: TMEM
+// warps 0-7: epilogue (two groups); 8: A producer; 9: B producer; 10: TMEM allocator; 11: MMA issuer.
+// The issuer has the highest warp id: the sub-partition arbiter serves higher warp ids first, and the
+// issuer's few instructions per stage must not queue behind the epilogue warps' ALU streams.
+constexpr int kThreads = 384;
 
 // NPAD   output channels per diagonal block (UMMA N of the lo*hi pass)
 // CONCAT weight stage rows are [hi rows | lo rows]: a_hi x [w_hi|w_lo] is ONE MMA of N = 2*NPAD (the
@@ -202,8 +218,9 @@ struct ConvArgs {
   // kEpiDgrad: saved forward activation (planes) whose zeros gate the gradient
   const uint4* mask_base;
   int mask_planes_half;
-  // bring-up only (wn_debug_set_flags): bit 0 = epilogue skips its global stores, bit 1 = weight stages
-  // are not re-fetched after the first ring fill, bit 2 = the a_lo / a_hi x w_lo passes are not issued.
+  // bring-up only (wn_debug_set_flags): bit 0 = epilogue skips its global stores (bit 6: also its arithmetic; bit 7: shared-memory stores instead), bit 1 = weight stages
+  // are not re-fetched after the first ring fill, bit 2 = the a_lo / a_hi x w_lo passes are not issued,
+  // bit 3 = no early probe of the next weight barrier.
   // Results are wrong with any bit set; used to attribute time to pipeline pieces.
   int dbg;
 };
@@ -249,7 +266,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int i = tid; i < NBLK * NPAD; i += kThreads) s_bias[i] = g.bias[i];
-  if (warp == 7) {
+  if (warp == 10) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "r"((uint32_t)C::TMEM_COLS)
                  : "memory");
@@ -261,7 +278,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
   const uint32_t tmem_base = *tmem_slot;
   if (tmem_base != 0) __trap();  // see the MMA issuer: accumulators are addressed from column 0
 
-  if (warp == 4) {
+  if (warp == 8) {
     // ===================== A producer: halo tiles by TMA =====================
     if (lane == 0) {
       int stage = 0;
@@ -282,7 +299,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     // ===================== B producer: packed weight stages =====================
     if (lane == 0) {
       int stage = 0;
@@ -300,7 +317,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
         }
       }
     }
-  } else if (warp == 6) {
+  } else if (warp == 11) {
     // ===================== MMA issuer =====================
     // The whole warp walks the pipeline (converged, so every operand stays in uniform registers);
     // one elected lane issues the MMAs and commits.
@@ -315,6 +332,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
       int astage = 0, bstage = 0, acc = 0;
       uint32_t aphase = 0, bphase = 0, tphase = 0;
       const bool skip_lo = (g.skip_lo != nullptr && *g.skip_lo != 0) || (g.dbg & 4);
+      bool b_ready = false;  // result of the early probe of the upcoming weight stage
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         mbar_wait(&t_empty[acc], tphase ^ 1);
         tc_fence_after();
@@ -328,8 +346,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
           const int blk = NBLK > 1 ? c / C::CPB : 0;
           const uint32_t d_base = d_tile + (uint32_t)(blk * C::BLK_COLS);
           for (int tg = 0; tg < C::NSTAGE_PER_CHUNK; tg++) {
-            mbar_wait(&b_full[bstage], bphase);
+            if (!b_ready) mbar_wait(&b_full[bstage], bphase);
             tc_fence_after();
+            {  // probe the next stage's barrier now; its latency overlaps the MMA issue below
+              const int nstage = bstage + 1 == C::NB ? 0 : bstage + 1;
+              b_ready = (g.dbg & 8) ? false : mbar_try(&b_full[nstage], nstage == 0 ? bphase ^ 1 : bphase);
+            }
             const uint32_t b_stage32 = (smem_u32(b_stages + bstage * C::B_STAGE) >> 4) | ((b_lbo >> 4) << 16);
             if (elect_one_sync()) {
               constexpr uint32_t a_lo_off = (uint32_t)(2 * C::PLANE_BYTES >> 4);
@@ -372,12 +394,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
         if (++acc == AS) { acc = 0; tphase ^= 1; }
       }
     }
-  } else if (warp < 4 || warp >= 8) {
+  } else if (warp < 8) {
     // ===================== epilogue =====================
     // a warp may only touch TMEM lanes 32*(warp%4)..+31; the two groups take alternate sub-tiles
     int acc = 0;
     uint32_t tphase = 0;
-    const int egroup = warp >> 3, quarter = warp & 3;
+    const int egroup = warp >> 2, quarter = warp & 3;
     const int row = quarter * 32 + lane;      // TMEM lane == pixel row of the sub-tile
     const int px = row & 7, py = row >> 3;
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
@@ -421,7 +443,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
 #pragma unroll
             for (int j = 0; j < GC; j++)
               f[j] = __uint_as_float(vb[gi & 1][j]) + (CONCAT ? __uint_as_float(wb[gi & 1][CONCAT ? j : 0]) : 0.f);
-            if (c0 < g.cout && inside && !(g.dbg & 1)) {
+            if (c0 < g.cout && inside && !(g.dbg & 64)) {
               const size_t pix = (size_t)gy * g.W + gx;
               const size_t hw = (size_t)g.H * g.W;
 #pragma unroll
@@ -449,8 +471,15 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
                 const ActDst& d = second ? g.dst1 : g.dst0;
                 const int plane = (second ? ch - g.split_c : ch) >> 3;
                 uint4* p_hi = d.base + ((size_t)n * 2 * d.planes_half + plane) * hw + pix;
-                p_hi[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                p_hi[(size_t)d.planes_half * hw] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                // bring-up bit 0: do all the arithmetic but (practically) never store
+                if (g.dbg & 128) {  // bring-up: shared-memory stores of the same size instead (corrupts a halo stage)
+                  uint4* sp = reinterpret_cast<uint4*>(a_stages) + ((tid & 255) + ((q >> 3) & 1) * 512);
+                  sp[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                  sp[256] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                } else if (!(g.dbg & 1) || (hi[0] == 0x7fc07fc0u && lo[3] == 0x7fc17fc1u)) {
+                  p_hi[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                  p_hi[(size_t)d.planes_half * hw] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                }
               }
             }
           }
@@ -493,7 +522,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 7) {
+  if (warp == 10) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
                  "r"((uint32_t)C::TMEM_COLS)

@@ -66,12 +66,13 @@ def load() -> ctypes.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("WATERNET_B200_LIB", LIB_PATH)  # experiment variants (see build.py); default in-tree
+    if not os.path.exists(path):
         raise WaterNetLibraryError(
-            f"{LIB_PATH} is missing: the CUDA library has not been built. "
+            f"{path} is missing: the CUDA library has not been built. "
             "Run `python -m waternet_b200.build` (needs nvcc 12.9); there is no CPU fallback."
         )
-    lib = ctypes.CDLL(LIB_PATH)
+    lib = ctypes.CDLL(path)
     for name, (res, args) in _SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype = res

@@ -39,19 +39,25 @@ def _stale(target: str, deps) -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile every .cu under csrc/ for sm_100a and link the shared library."""
+def build(force: bool = False, verbose: bool = False, defines=(), lib_name: str = LIB_NAME) -> str:
+    """Compile every .cu under csrc/ for sm_100a and link the shared library.
+
+    ``defines`` / ``lib_name`` build an experiment variant next to the product library (A/B runs on one
+    GPU box: ``WATERNET_B200_LIB=<path>`` makes ``_lib.load()`` pick it up).
+    """
     nvcc = _nvcc()
-    os.makedirs(OBJ_DIR, exist_ok=True)
+    obj_dir = OBJ_DIR if not defines else OBJ_DIR + "_" + "_".join(d.replace("=", "-") for d in defines)
+    lib_path = os.path.join(PKG_DIR, lib_name)
+    os.makedirs(obj_dir, exist_ok=True)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers.append(os.path.join(os.path.dirname(PKG_DIR), "include", "waternet_b200.h"))
     objs = []
     for src in _sources():
         src_path = os.path.join(CSRC, src)
-        obj = os.path.join(OBJ_DIR, src[:-3] + ".o")
+        obj = os.path.join(obj_dir, src[:-3] + ".o")
         objs.append(obj)
         if force or _stale(obj, [src_path] + headers):
-            cmd = [nvcc] + ARCH_FLAGS + NVCC_FLAGS + ["-c", src_path, "-o", obj]
+            cmd = [nvcc] + ARCH_FLAGS + NVCC_FLAGS + [f"-D{d}" for d in defines] + ["-c", src_path, "-o", obj]
             res = subprocess.run(cmd, capture_output=True, text=True)
             log = res.stdout + res.stderr
             with open(obj + ".log", "w") as f:
@@ -60,13 +66,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
                 sys.stderr.write(log)
             if res.returncode != 0:
                 raise RuntimeError(f"nvcc failed for {src} (see {obj}.log)")
-    if force or _stale(LIB_PATH, objs):
-        cmd = [nvcc] + ARCH_FLAGS + ["-shared", "-o", LIB_PATH] + objs
+    if force or _stale(lib_path, objs):
+        cmd = [nvcc] + ARCH_FLAGS + ["-shared", "-o", lib_path] + objs
         res = subprocess.run(cmd, capture_output=True, text=True)
         if res.returncode != 0:
             sys.stderr.write(res.stdout + res.stderr)
             raise RuntimeError("link failed")
-    return LIB_PATH
+    return lib_path
 
 
 if __name__ == "__main__":

@@ -50,7 +50,8 @@ __global__ void __launch_bounds__(256) pack_inputs_kernel(PackInArgs a, uint4* _
       for (int c = 0; c < 3; c++) {
         float f = __fmul_rn(a.p[t][n * a.s[t][0] + c * a.s[t][1] + y * a.s[t][2] + x * a.s[t][3]], 255.0f);
         float r = rintf(f);
-        if (fabsf(f - r) <= 0.0009765625f && r >= 0.f && r <= 255.f) f = r; else exact = false;
+        // (u/255)*255 lands within ~2e-5 of u; anything within 2^-14 of a level is treated as that level
+        if (fabsf(f - r) <= 6.103515625e-5f && r >= 0.f && r <= 255.f) f = r; else exact = false;
         v[t * 3 + c] = f;
       }
     v[12] = v[13] = v[14] = v[15] = 0.f;

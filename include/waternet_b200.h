@@ -112,15 +112,16 @@ int wn_enhance_u8(wn_handle* h, const uint8_t* rgb, uint8_t* out_nhwc, float* ou
  * wn_forward_train is wn_forward (tensor-core mode) that additionally keeps every activation in
  * `train_workspace`; wn_backward consumes that workspace and d(loss)/d(out) (fp32 contiguous NCHW)
  * and OVERWRITES the 34 gradient tensors `grads` (device pointers, same order, shapes and layout as
- * `params` of wn_pack_weights).  Gradients with respect to the four input images are not produced.
+ * `params` of wn_pack_weights).  input_grads is NULL or four device pointers to fp32 contiguous
+ * (N,3,H,W) tensors that receive d(loss)/d(x), d/d(wb), d/d(he), d/d(gc).
  * The workspace must stay untouched between the two calls; n*h*w <= 8 Mi pixels per call.
  */
 size_t wn_train_workspace_bytes(int n, int h, int w);
 int wn_forward_train(wn_handle* h, const float* x, const float* wb, const float* he, const float* gc,
                      const int64_t in_strides[4][4], float* out, int n, int height, int width,
                      void* train_workspace, size_t workspace_bytes, void* stream);
-int wn_backward(wn_handle* h, const float* grad_out, float* const* grads, int n, int height, int width,
-                void* train_workspace, size_t workspace_bytes, void* stream);
+int wn_backward(wn_handle* h, const float* grad_out, float* const* grads, float* const* input_grads, int n,
+                int height, int width, void* train_workspace, size_t workspace_bytes, void* stream);
 
 /*
  * Per-kernel device timing (measurement aid for bench.py, off by default).  When on, every

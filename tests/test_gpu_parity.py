@@ -286,7 +286,7 @@ def _fp64_grads(sd, ins, target):
     """Ground truth: float64 autograd through the functional oracle graph."""
     import torch.nn.functional as F
     params = {k: v.double().clone().requires_grad_(True) for k, v in sd.items()}
-    x, wb, he, gc = [t.double() for t in ins]
+    x, wb, he, gc = leaves = [t.double().clone().requires_grad_(True) for t in ins]
 
     def conv(prefix, t, k):
         return F.conv2d(t, params[prefix + ".weight"], params[prefix + ".bias"], padding=k // 2)
@@ -303,7 +303,9 @@ def _fp64_grads(sd, ins, target):
         total = total + t * cm[:, r:r + 1]
     loss = F.mse_loss(total, target.double())
     loss.backward()
-    return total.detach(), {k: v.grad for k, v in params.items()}
+    grads = {k: v.grad for k, v in params.items()}
+    grads["__inputs__"] = [t.grad for t in leaves]
+    return total.detach(), grads
 
 
 @pytest.mark.parametrize("shape", [(2, 24, 24), (1, 37, 53), (3, 16, 40)])
@@ -328,6 +330,31 @@ def test_native_backward_matches_fp64_autograd(shape):
         worst = max(worst, rel)
         assert rel < 2e-3, f"{name}: relative gradient error {rel:.2e}"
     print(f"worst relative gradient error {worst:.2e}")
+
+
+@pytest.mark.parametrize("needs", [(True, True, True, True), (False, True, False, False)])
+def test_native_input_image_gradients_match_fp64_autograd(needs):
+    """wn_backward's optional input_grads: d(loss)/d(x, wb, he, gc) against float64 autograd; parameter
+    gradients are unchanged by asking for them."""
+    n, h, w = 2, 29, 43
+    sd = ofw.synthetic_state_dict(7, 3.0)
+    m = _model(7, 3.0, "default").train()
+    ins = _inputs_from_rgb([ofw.synthetic_image(60 + i, h, w, "smooth") for i in range(n)])
+    target = torch.rand(n, 3, h, w, generator=torch.Generator().manual_seed(3))
+    cu = [t.cuda().requires_grad_(need) for t, need in zip(ins, needs)]
+    out = m(*cu)
+    torch.nn.functional.mse_loss(out, target.cuda()).backward()
+    ref_out, ref = _fp64_grads(sd, ins, target)
+    _assert_close(out.detach().cpu().numpy(), ref_out.numpy())
+    for t, need, r in zip(cu, needs, ref["__inputs__"]):
+        if not need:
+            assert t.grad is None
+            continue
+        rel = ((t.grad.double().cpu() - r).norm() / r.norm()).item()
+        assert rel < 2e-3, f"input gradient relative error {rel:.2e}"
+    for name, p in m.named_parameters():
+        rel = ((p.grad.double().cpu() - ref[name]).norm() / ref[name].norm().clamp_min(1e-30)).item()
+        assert rel < 2e-3, f"{name}: {rel:.2e}"
 
 
 def test_native_training_steps_track_the_torch_graph():
@@ -397,3 +424,28 @@ def test_enhancer_cuda_graph_replay_equals_direct_launches():
     batch = np.stack(frames[:2])
     assert np.array_equal(graphed(batch), direct(batch))  # new shape -> new capture
     assert np.array_equal(graphed(batch[::-1].copy()), direct(batch[::-1].copy()))
+
+
+def test_empty_batch_is_a_no_op(eng):
+    m = _model(0, 1.0, "default")
+    empty = [torch.empty(0, 3, 32, 48).cuda() for _ in range(4)]
+    with torch.no_grad():
+        assert m(*empty).shape == (0, 3, 32, 48)
+    assert eng.enhance(torch.empty(0, 32, 48, 3, dtype=torch.uint8).cuda()).shape == (0, 32, 48, 3)
+    res = eng.preprocess(torch.empty(0, 32, 48, 3, dtype=torch.uint8).cuda(), tensors=True, images=True)
+    assert res["x"].shape == (0, 3, 32, 48) and res["he_u8"].shape == (0, 32, 48, 3)
+    assert eng.postprocess(torch.empty(0, 3, 8, 8).cuda()).shape == (0, 8, 8, 3)
+
+
+def test_single_4k_frame_tensor_cores_vs_fp32_path():
+    """Largest single-image case exercised: 3840x2160 (one image per pass, ~16 GB of workspace)."""
+    from waternet_b200.engine import get_engine
+    eng = get_engine("cuda:0")
+    rgb = ofw.synthetic_image(77, 2160, 3840, "smooth")
+    r = eng.preprocess(torch.from_numpy(rgb[None]).cuda())
+    ins = [r[k] for k in ("x", "wb", "he", "gc")]
+    with torch.no_grad():
+        a = _model(0, 3.0, "fp32")(*ins)
+        b = _model(0, 3.0, "bf16x3")(*ins)
+    _assert_close(b.cpu().numpy(), a.cpu().numpy())
+    eng.release_workspaces()

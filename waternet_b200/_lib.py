@@ -44,8 +44,8 @@ _SIGNATURES = {
     "wn_train_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "wn_forward_train": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, POINTER(c_int64), c_void_p,
                                  c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
-    "wn_backward": (c_int, [c_void_p, c_void_p, POINTER(c_void_p), c_int, c_int, c_int, c_void_p, c_size_t,
-                            c_void_p]),
+    "wn_backward": (c_int, [c_void_p, c_void_p, POINTER(c_void_p), POINTER(c_void_p), c_int, c_int, c_int, c_void_p,
+                            c_size_t, c_void_p]),
     "wn_debug_forward_layer": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, POINTER(c_int64), c_int,
                                        c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "wn_enable_timing": (c_int, [c_void_p, c_int]),

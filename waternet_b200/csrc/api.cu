@@ -284,8 +284,8 @@ int wn_forward_train(wn_handle* h, const float* x, const float* wb, const float*
                        (cudaStream_t)stream);
 }
 
-int wn_backward(wn_handle* h, const float* grad_out, float* const* grads, int n, int height, int width,
-                void* train_workspace, size_t workspace_bytes, void* stream) {
+int wn_backward(wn_handle* h, const float* grad_out, float* const* grads, float* const* input_grads, int n,
+                int height, int width, void* train_workspace, size_t workspace_bytes, void* stream) {
   if (!h || !grad_out || !grads || !train_workspace || n <= 0 || height <= 0 || width <= 0) {
     set_error("wn_backward: bad argument");
     return WN_E_INVALID;
@@ -299,8 +299,15 @@ int wn_backward(wn_handle* h, const float* grad_out, float* const* grads, int n,
     set_error("wn_backward: wn_pack_weights has not been called");
     return WN_E_STATE;
   }
+  if (input_grads)
+    for (int i = 0; i < 4; i++)
+      if (!input_grads[i]) {
+        set_error("wn_backward: input_grads[%d] is NULL", i);
+        return WN_E_INVALID;
+      }
   DeviceGuard guard(h->device);
-  return backward(h, grad_out, grads, n, height, width, train_workspace, workspace_bytes, (cudaStream_t)stream);
+  return backward(h, grad_out, grads, input_grads, n, height, width, train_workspace, workspace_bytes,
+                  (cudaStream_t)stream);
 }
 
 int wn_debug_forward_layer(wn_handle* h, const float* x, const float* wb, const float* he,

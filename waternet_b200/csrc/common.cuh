@@ -165,7 +165,7 @@ void bwd_free(wn_handle* h);
 size_t train_workspace_bytes_padded(int n, int h, int w);
 int forward_train(wn_handle* h, const float* const in[4], const int64_t in_strides[4][4], float* out, int n,
                   int height, int width, void* workspace, size_t workspace_bytes, cudaStream_t stream);
-int backward(wn_handle* h, const float* grad_out, float* const* grads, int n, int height, int width,
-             void* workspace, size_t workspace_bytes, cudaStream_t stream);
+int backward(wn_handle* h, const float* grad_out, float* const* grads, float* const* input_grads, int n,
+             int height, int width, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 
 }  // namespace wn

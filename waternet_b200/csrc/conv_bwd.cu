@@ -278,27 +278,66 @@ gate_bwd_kernel(const float* __restrict__ g_out, const float* __restrict__ cm, c
 }
 
 // data-gradient weights: dense_d[row_off + c][col(o)][kk-1-t] = W[o][c][t]   (transpose + spatial flip)
+// input channel c lands in row  row_off + c  (c < split)  or  row_off + c + shift  (c >= split)
 __global__ void scatter_weights_T_kernel(const float* __restrict__ src, float* __restrict__ dense, int co, int ci,
-                                         int kk, int kpad, int row_off, int col_off) {
+                                         int kk, int kpad, int row_off, int col_off, int split, int shift) {
   const int total = co * ci * kk;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     int t = i % kk;
     int c = (i / kk) % ci;
     int o = i / (kk * ci);
-    dense[((size_t)(row_off + c) * kpad + col_off + o) * kk + (kk - 1 - t)] = src[i];
+    int row = row_off + c + (c >= split ? shift : 0);
+    dense[((size_t)row * kpad + col_off + o) * kk + (kk - 1 - t)] = src[i];
   }
+}
+
+// d(loss)/d(input images) from the two 32-channel gradient buffers of the first layers (12 real channels:
+// x, wb, he, gc): sum them (hi + lo each) and write the four fp32 (N,3,H,W) tensors.
+struct InputGrads {
+  float* p[4];
+};
+__global__ void __launch_bounds__(256)
+input_grads_kernel(const uint4* __restrict__ ga, const uint4* __restrict__ gb, InputGrads out, int hw) {
+  const int n = blockIdx.y;
+  const int pix = blockIdx.x * 256 + threadIdx.x;
+  if (pix >= hw) return;
+  float v[16];
+#pragma unroll
+  for (int j = 0; j < 16; j++) v[j] = 0.f;
+  const uint4* bufs[2] = {ga, gb};
+#pragma unroll
+  for (int b = 0; b < 2; b++) {
+#pragma unroll
+    for (int plane = 0; plane < 2; plane++) {
+#pragma unroll
+      for (int half = 0; half < 2; half++) {  // 32-channel buffers: 4 planes per half
+        const uint4 q = bufs[b][((size_t)n * 8 + half * 4 + plane) * hw + pix];
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+          v[plane * 8 + j] += __uint_as_float(((w[j >> 1] >> ((j & 1) * 16)) & 0xffffu) << 16);
+      }
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < 4; t++)
+#pragma unroll
+    for (int c = 0; c < 3; c++) out.p[t][((size_t)n * 3 + c) * hw + pix] = v[t * 3 + c];
 }
 
 // ------------------------------------------------------------------------------------------
 // Host side
 // ------------------------------------------------------------------------------------------
-enum DgradLayer { kD8 = 0, kD7, kD6, kD5, kD4, kD3, kD2, kDR3, kDR2, kNumDgrad };
+enum DgradLayer { kD8 = 0, kD7, kD6, kD5, kD4, kD3, kD2, kDR3, kDR2, kD1, kDR1, kNumDgrad };
 struct DgradSpec {
   int ks, kpad, npad, nblk, concat, conv;  // K = forward Cout (padded), N per block = forward Cin
 };
 static const DgradSpec kDSpecs[kNumDgrad] = {
     {3, 16, 64, 1, 1, 7},   {3, 64, 64, 1, 1, 6},   {5, 64, 64, 1, 1, 5},  {7, 64, 64, 1, 1, 4}, {1, 64, 128, 1, 0, 3},
-    {3, 128, 128, 1, 0, 2}, {5, 128, 128, 1, 0, 1}, {3, 16, 96, 1, 0, -1}, {5, 96, 32, 3, 1, -1}};
+    {3, 128, 128, 1, 0, 2}, {5, 128, 128, 1, 0, 1}, {3, 16, 96, 1, 0, -1}, {5, 96, 32, 3, 1, -1},
+    // gradients with respect to the packed 16-channel input (only when an input image requires grad):
+    // from cmg.conv1 (K = 128) and from the three refiner conv1 (K = 96); 32 rows, 12 real
+    {7, 128, 32, 1, 1, 0},  {7, 96, 32, 1, 1, -2}};
 
 struct UmmaBwd {
   uint8_t* stages[kNumDgrad];
@@ -322,14 +361,21 @@ int bwd_pack_weights(wn_handle* h, const float* const* params, cudaStream_t stre
     WN_CUDA(cudaMemsetAsync(u->dense, 0, (size_t)rows * s.kpad * kk * sizeof(float), stream));
     if (s.conv >= 0) {
       const LayerDesc& d = kCmg[s.conv];
-      scatter_weights_T_kernel<<<128, 256, 0, stream>>>(params[2 * s.conv], u->dense, d.cout, d.cin, kk, s.kpad, 0, 0);
+      scatter_weights_T_kernel<<<128, 256, 0, stream>>>(params[2 * s.conv], u->dense, d.cout, d.cin, kk, s.kpad, 0, 0,
+                                                        d.cin, 0);
       WN_LAUNCH_CHECK(h);
+    } else if (s.conv == -2) {
+      for (int r = 0; r < 3; r++) {  // refiner r reads cat[x, input r+1]: rows 0..2 and 3(r+1)..3(r+1)+2
+        scatter_weights_T_kernel<<<128, 256, 0, stream>>>(params[2 * (8 + 3 * r)], u->dense, 32, 6, kk, s.kpad, 0, 32 * r,
+                                                          3, 3 * (r + 1) - 3);
+        WN_LAUNCH_CHECK(h);
+      }
     } else {
       for (int r = 0; r < 3; r++) {
         const int conv = 8 + 3 * r + (li == kDR3 ? 2 : 1);
         const int co = li == kDR3 ? 3 : 32;
         scatter_weights_T_kernel<<<128, 256, 0, stream>>>(params[2 * conv], u->dense, co, 32, kk, s.kpad, 32 * r,
-                                                          (li == kDR3 ? 3 : 32) * r);
+                                                          (li == kDR3 ? 3 : 32) * r, 32, 0);
         WN_LAUNCH_CHECK(h);
       }
     }
@@ -353,13 +399,14 @@ void bwd_free(wn_handle* h) {
 // ---- training workspace ------------------------------------------------------------------
 struct TrainBuffers {
   FwdBuffers f;
-  uint4 *ga, *gb, *gra, *grb, *g8, *gr3;
+  uint4 *ga, *gb, *gra, *grb, *g8, *gr3, *gin_a, *gin_b;
   float* dense;
 };
 static constexpr size_t kDenseBytes = (size_t)49 * 128 * 128 * sizeof(float);
 // bytes per pixel: act0 64 | a1..a3 512 each | a4..a7 256 each | r1, r2 384 each | cm 12 | refined 36 |
 //                  gradient ping-pong 512 + 512 + 384 + 384 | 16-channel gradients 64 + 64
-static constexpr size_t kTrainBytesPerPixel = 64 + 3 * 512 + 4 * 256 + 2 * 384 + 12 + 36 + 2 * 512 + 2 * 384 + 2 * 64;
+static constexpr size_t kTrainBytesPerPixel =
+    64 + 3 * 512 + 4 * 256 + 2 * 384 + 12 + 36 + 2 * 512 + 2 * 384 + 2 * 64 + 2 * 128;  // + two 32-ch input-gradient buffers
 static constexpr long long kTrainMaxPixels = 8ll << 20;
 
 size_t train_workspace_bytes(int n, int h, int w) {
@@ -388,6 +435,8 @@ static void carve(TrainBuffers* t, void* workspace, size_t px) {
   t->grb = (uint4*)take(px * 384);
   t->g8 = (uint4*)take(px * 64);
   t->gr3 = (uint4*)take(px * 64);
+  t->gin_a = (uint4*)take(px * 128);
+  t->gin_b = (uint4*)take(px * 128);
   t->dense = (float*)take(kDenseBytes);
 }
 
@@ -397,14 +446,14 @@ static int check_train_args(int n, int H, int W, size_t bytes) {
     return WN_E_UNSUPPORTED;
   }
   // carve() aligns every region to 1 KiB: allow for it
-  if (bytes < train_workspace_bytes(n, H, W) + 20 * 1024) {
-    set_error("training workspace too small: %zu < %zu", bytes, train_workspace_bytes(n, H, W) + 20 * 1024);
+  if (bytes < train_workspace_bytes(n, H, W) + 24 * 1024) {
+    set_error("training workspace too small: %zu < %zu", bytes, train_workspace_bytes(n, H, W) + 24 * 1024);
     return WN_E_WORKSPACE;
   }
   return WN_OK;
 }
 
-size_t train_workspace_bytes_padded(int n, int h, int w) { return train_workspace_bytes(n, h, w) + 20 * 1024; }
+size_t train_workspace_bytes_padded(int n, int h, int w) { return train_workspace_bytes(n, h, w) + 24 * 1024; }
 
 int forward_train(wn_handle* h, const float* const in[4], const int64_t st[4][4], float* out, int n, int H, int W,
                   void* workspace, size_t workspace_bytes, cudaStream_t stream) {
@@ -494,14 +543,14 @@ static int launch_dgrad(wn_handle* h, int li, uint4* g_in, uint4* g_out, int out
   a.dst0.planes_half = out_channels / 8;
   a.split_c = out_channels;
   a.cout = out_channels;
-  a.mask_base = saved;
+  a.mask_base = saved;  // nullptr: no ReLU in front (network input)
   a.mask_planes_half = out_channels / 8;
   return launch_conv<KS, KPAD, NPAD, S, AS, kEpiDgrad, CONCAT, NBLK, TPS>(h, kSlotGate, h->bwd->stages[li],
                                                                          h->bwd->zero_bias, g_in, a, stream);
 }
 
-int backward(wn_handle* h, const float* grad_out, float* const* grads, int n, int H, int W, void* workspace,
-             size_t workspace_bytes, cudaStream_t stream) {
+int backward(wn_handle* h, const float* grad_out, float* const* grads, float* const* input_grads, int n, int H,
+             int W, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   if (!h->bwd) {
     set_error("backward weights have not been packed");
     return WN_E_STATE;
@@ -558,6 +607,9 @@ int backward(wn_handle* h, const float* grad_out, float* const* grads, int n, in
   if ((rc = launch_wgrad<7, 16, 32>(h, t.ga, 128, t.f.act0, t.dense, n, H, W, stream))) return rc;
   if ((rc = extract(h, t.dense, gw(0), 128, 12, 7, 16, 0, 12, 0, 0, 1.f / 255.f, stream))) return rc;
   if ((rc = bias_grad(h, t.ga, 16, 128, gb(0), n, hw, stream))) return rc;
+  if (input_grads) {  // d/d(packed input) from cmg.conv1: ga (128) -> g8 region reused as a 32-channel buffer
+    if ((rc = launch_dgrad<7, 128, 32, 2, 2, 1, 1, 7>(h, kD1, t.ga, t.gin_a, 32, nullptr, n, H, W, stream))) return rc;
+  }
 
   // ---- refiners: conv3, conv2, conv1 (three side by side) ---------------------------------
   if ((rc = launch_wgrad<3, 96, 5>(h, t.gr3, 9, t.f.r[2], t.dense, n, H, W, stream))) return rc;
@@ -591,6 +643,13 @@ int backward(wn_handle* h, const float* grad_out, float* const* grads, int n, in
       if ((rc = extract(h, t.dense, gw(8 + 3 * r), 32, 6, 7, 16, 32 * r, 3, 0, 3 * (r + 1), 1.f / 255.f, stream))) return rc;
       WN_CUDA(cudaMemcpyAsync(gb(8 + 3 * r), tmp + 32 * r, 32 * sizeof(float), cudaMemcpyDeviceToDevice, stream));
     }
+  }
+  if (input_grads) {
+    if ((rc = launch_dgrad<7, 96, 32, 2, 2, 1, 1, 7>(h, kDR1, t.grb, t.gin_b, 32, nullptr, n, H, W, stream))) return rc;
+    InputGrads ig;
+    for (int i = 0; i < 4; i++) ig.p[i] = input_grads[i];
+    input_grads_kernel<<<dim3((hw + 255) / 256, n), 256, 0, stream>>>(t.gin_a, t.gin_b, ig, hw);
+    WN_LAUNCH_CHECK(h);
   }
   return WN_OK;
 }

@@ -454,8 +454,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
                 uint32_t hi[4], lo[4];
                 uint32_t mask[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
                 if constexpr (EPI == kEpiDgrad) {
-                  const uint4 m = g.mask_base[((size_t)n * 2 * g.mask_planes_half + (ch >> 3)) * hw + pix];
-                  mask[0] = m.x; mask[1] = m.y; mask[2] = m.z; mask[3] = m.w;
+                  if (g.mask_base) {  // no mask: gradient with respect to the network input (no ReLU in front)
+                    const uint4 m = g.mask_base[((size_t)n * 2 * g.mask_planes_half + (ch >> 3)) * hw + pix];
+                    mask[0] = m.x; mask[1] = m.y; mask[2] = m.z; mask[3] = m.w;
+                  }
                 }
 #pragma unroll
                 for (int j = 0; j < 8; j += 2) {

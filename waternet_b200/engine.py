@@ -119,6 +119,8 @@ class Engine:
                 raise ValueError("the four inputs must have the same shape")
         if out is None:
             out = torch.empty((n, 3, h, w), dtype=torch.float32, device=self.device)
+        if n == 0 or h == 0 or w == 0:  # empty batch: nothing to launch (torch's convs return empty too)
+            return out
         strides = (ctypes.c_int64 * 16)(*[s for t in ins for s in t.stride()])
         nbytes = self.lib.wn_forward_workspace_bytes(n, h, w, mode)
         ws = self._workspace("forward", nbytes)
@@ -160,17 +162,22 @@ class Engine:
         _lib.check(rc, "wn_forward_train")
         return out, ws
 
-    def backward(self, grad_out: torch.Tensor, saved_ws: torch.Tensor, shapes):
-        """d(loss)/d(out) + the workspace of forward_train -> the 34 parameter gradients (state-dict order)."""
+    def backward(self, grad_out: torch.Tensor, saved_ws: torch.Tensor, shapes, want_input_grads: bool = False):
+        """d(loss)/d(out) + the workspace of forward_train -> the 34 parameter gradients (state-dict order)
+        and, on request, the gradients of the four input images."""
         g = grad_out.detach().to(self.device, torch.float32).contiguous()
         n, _, h, w = g.shape
         grads = [torch.empty(tuple(s), dtype=torch.float32, device=self.device) for s in shapes]
         arr = (ctypes.c_void_p * _lib.NUM_PARAMS)(*[t.data_ptr() for t in grads])
+        gin, gin_arr = None, None
+        if want_input_grads:
+            gin = [torch.empty((n, 3, h, w), dtype=torch.float32, device=self.device) for _ in range(4)]
+            gin_arr = (ctypes.c_void_p * 4)(*[t.data_ptr() for t in gin])
         with torch.cuda.device(self.device):
-            rc = self.lib.wn_backward(self.handle, g.data_ptr(), arr, n, h, w, saved_ws.data_ptr(), saved_ws.numel(),
-                                      _stream_ptr(self.device))
+            rc = self.lib.wn_backward(self.handle, g.data_ptr(), arr, gin_arr, n, h, w, saved_ws.data_ptr(),
+                                      saved_ws.numel(), _stream_ptr(self.device))
         _lib.check(rc, "wn_backward")
-        return grads
+        return (grads, gin) if want_input_grads else grads
 
     # ---- preprocess / postprocess ----------------------------------------------
     def preprocess(self, rgb_u8: torch.Tensor, tensors: bool = True, images: bool = False):
@@ -182,6 +189,13 @@ class Engine:
             raise ValueError(f"expected uint8 (N,H,W,3), got {rgb_u8.dtype} {tuple(rgb_u8.shape)}")
         rgb_u8 = rgb_u8.to(self.device).contiguous()
         n, h, w, _ = rgb_u8.shape
+        if n == 0 or h == 0 or w == 0:
+            res = {}
+            if tensors:
+                res.update({k: torch.empty((n, 3, h, w), dtype=torch.float32, device=self.device) for k in ("x", "wb", "he", "gc")})
+            if images:
+                res.update({k: torch.empty((n, h, w, 3), dtype=torch.uint8, device=self.device) for k in ("wb_u8", "he_u8", "gc_u8")})
+            return res
         res = {}
         ptr = {k: None for k in ("x", "wb", "he", "gc", "wb_u8", "he_u8", "gc_u8")}
         if tensors:
@@ -207,6 +221,8 @@ class Engine:
         if c != 3:
             raise ValueError("expected (N,3,H,W)")
         res = torch.empty((n, h, w, 3), dtype=torch.uint8, device=self.device)
+        if res.numel() == 0:
+            return res
         with torch.cuda.device(self.device):
             rc = self.lib.wn_postprocess_u8(self.handle, out.data_ptr(), res.data_ptr(), n, h, w,
                                             _stream_ptr(self.device))
@@ -222,6 +238,8 @@ class Engine:
         n, h, w, _ = rgb_u8.shape
         if out_u8 is None:
             out_u8 = torch.empty((n, h, w, 3), dtype=torch.uint8, device=self.device)
+        if out_u8.numel() == 0:
+            return out_u8
         ws = self._workspace("enhance", self.lib.wn_enhance_workspace_bytes(n, h, w, mode))
         with torch.cuda.device(self.device):
             rc = self.lib.wn_enhance_u8(self.handle, rgb_u8.data_ptr(), out_u8.data_ptr(),

@@ -10,9 +10,9 @@ reference's checkpoints load with strict ``load_state_dict`` and callers
   raise.
 * When autograd needs a graph (training, ``train.py:100-133``), forward values and
   the 34 parameter gradients both come from the CUDA library (``wn_forward_train`` /
-  ``wn_backward``: tensor-core data-gradient and weight-gradient kernels).  Only when
-  an *input image* requires grad, or in the fp32 CUDA-core mode, the backward pass
-  re-evaluates the network with torch ops.
+  ``wn_backward``: tensor-core data-gradient and weight-gradient kernels), including
+  gradients of the input images when they require grad.  Only the fp32 CUDA-core mode
+  re-evaluates the network with torch ops for its backward pass.
 """
 from __future__ import annotations
 
@@ -79,16 +79,16 @@ class Refiner(_ConvStack):
 
 
 class _KernelForward(torch.autograd.Function):
-    """Forward values AND parameter gradients from the CUDA library (wn_forward_train / wn_backward).
-
-    Gradients with respect to the four input images are not produced by the kernels; when an input
-    requires grad the backward pass re-evaluates the torch graph instead.
+    """Forward values and all gradients (34 parameters, and the four input images when they require
+    grad) from the CUDA library (wn_forward_train / wn_backward).  Only the fp32 CUDA-core mode obtains
+    its gradients by re-evaluating the torch graph.
     """
 
     @staticmethod
     def forward(ctx, model, mode, x, wb, ce, gc, *params):
         ctx.model = model
-        ctx.native = not any(t.requires_grad for t in (x, wb, ce, gc)) and mode != _lib.MODE_FP32_SIMT
+        ctx.native = mode != _lib.MODE_FP32_SIMT
+        ctx.input_needs_grad = [t.requires_grad for t in (x, wb, ce, gc)]
         if ctx.native:
             eng = model._engine_with_weights(x)
             out, ws = eng.forward_train(x, wb, ce, gc)
@@ -106,10 +106,13 @@ class _KernelForward(torch.autograd.Function):
             eng = ctx.engine
             if eng._weights_key != ctx.weights_key:  # parameters changed between forward and backward
                 raise RuntimeError("model parameters were modified between forward and backward")
-            grads = eng.backward(grad_out, ctx.saved_ws, [p.shape for p in params])
+            want_in = any(ctx.input_needs_grad)
+            res = eng.backward(grad_out, ctx.saved_ws, [p.shape for p in params], want_input_grads=want_in)
+            grads, gin = res if want_in else (res, [None] * 4)
             ctx.saved_ws = None
             gpar = [g if p.requires_grad else None for g, p in zip(grads, params)]
-            return (None, None, None, None, None, None, *gpar)
+            gin = [g if need else None for g, need in zip(gin, ctx.input_needs_grad)]
+            return (None, None, *gin, *gpar)
         x, wb, ce, gc = ctx.saved_tensors
         with torch.enable_grad():
             ins = [t.detach().requires_grad_(t.requires_grad) for t in (x, wb, ce, gc)]

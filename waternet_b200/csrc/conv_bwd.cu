@@ -577,7 +577,7 @@ int backward(wn_handle* h, const float* grad_out, float* const* grads, float* co
   if ((rc = launch_wgrad<3, 64, 8>(h, t.ga, 64, t.f.a[6], t.dense, n, H, W, stream))) return rc;
   if ((rc = extract(h, t.dense, gw(6), 64, 64, 3, 64, 0, 64, 0, 0, 1.f, stream))) return rc;
   if ((rc = bias_grad(h, t.ga, 8, 64, gb(6), n, hw, stream))) return rc;
-  if ((rc = launch_dgrad<3, 64, 64, 2, 2, 1, 1, 3>(h, kD7, t.ga, t.gb, 64, t.f.a[6], n, H, W, stream))) return rc;
+  if ((rc = launch_dgrad<3, 64, 64, 2, 2, 1, 1, 9>(h, kD7, t.ga, t.gb, 64, t.f.a[6], n, H, W, stream))) return rc;
   // conv6 (5x5): g = gb
   if ((rc = launch_wgrad<5, 64, 8>(h, t.gb, 64, t.f.a[5], t.dense, n, H, W, stream))) return rc;
   if ((rc = extract(h, t.dense, gw(5), 64, 64, 5, 64, 0, 64, 0, 0, 1.f, stream))) return rc;

@@ -81,11 +81,15 @@ enum UmmaLayer {
   kR3,        // three refiner conv3 as block-diagonal 96 -> 9 (pad 16), ReLU, gated sum
   kNumUmmaLayers
 };
+// A/B knob: conv2/conv3 as CONCAT (one N=256 MMA for a_hi x [w_hi|w_lo]; accumulators single-buffered)
+#ifndef WN_C23_CONCAT
+#define WN_C23_CONCAT 0
+#endif
 struct UmmaLayerSpec {
   int ks, cinpad, npad, cout, slot, concat, nblk;  // npad = output columns per diagonal block
 };
 static const UmmaLayerSpec kSpecs[kNumUmmaLayers] = {
-    {7, 16, 224, 224, 0, 0, 1}, {5, 128, 128, 128, 1, 0, 1}, {3, 128, 128, 128, 2, 0, 1}, {1, 128, 64, 64, 3, 1, 1},
+    {7, 16, 224, 224, 0, 0, 1}, {5, 128, 128, 128, 1, WN_C23_CONCAT, 1}, {3, 128, 128, 128, 2, WN_C23_CONCAT, 1}, {1, 128, 64, 64, 3, 1, 1},
     {7, 64, 64, 64, 4, 1, 1},   {5, 64, 64, 64, 5, 1, 1},    {3, 64, 64, 64, 6, 1, 1},    {3, 64, 16, 3, 7, 1, 1},
     {5, 96, 32, 96, 9, 1, 3},   {3, 96, 16, 9, 10, 1, 1}};
 
@@ -171,6 +175,20 @@ size_t umma_forward_workspace_bytes(int n, int h, int w) {
   return (size_t)umma_chunk(n, h, w) * h * w * kUmmaBytesPerPixel + 4096;
 }
 
+// taps per weight stage of the layers where it is a tuning knob (A/B builds override with -D)
+#ifndef WN_L1_TPS
+#define WN_L1_TPS 4
+#endif
+#ifndef WN_C3_TPS
+#define WN_C3_TPS 3
+#endif
+#ifndef WN_C7_TPS
+#define WN_C7_TPS 9
+#endif
+#ifndef WN_R2_TPS
+#define WN_R2_TPS 5
+#endif
+
 template <int KS, int CIN_PAD, int NPAD, int S, int AS, int EPI, int CONCAT = 0, int NBLK = 1, int TPS = 1>
 static int launch_umma(wn_handle* h, int li, void* in_base, ConvArgs a, cudaStream_t stream) {
   const UmmaLayerSpec& spec = kSpecs[li];
@@ -232,14 +250,14 @@ int umma_forward_layers(wn_handle* h, const float* const in[4], const int64_t st
   // L1: 16 -> 128 (cmg) + 96 (refiners)
   act(b.a[1], 128, b.r[1], 96);
   a.skip_lo = b.exact_flag;
-  if ((rc = launch_umma<7, 16, 224, 2, 1, kEpiAct>(h, kL1, b.act0, a, stream))) return rc;
+  if ((rc = launch_umma<7, 16, 224, 2, 1, kEpiAct, 0, 1, WN_L1_TPS>(h, kL1, b.act0, a, stream))) return rc;
   a.skip_lo = nullptr;
   if (dump(0, b.a[1], 128) || dump(8, b.r[1], 96)) return WN_OK;
   act(b.a[2], 128, nullptr, 0);
-  if ((rc = launch_umma<5, 128, 128, 2, 2, kEpiAct, 0, 1, 5>(h, kC2, b.a[1], a, stream))) return rc;
+  if ((rc = launch_umma<5, 128, 128, 2, WN_C23_CONCAT ? 1 : 2, kEpiAct, WN_C23_CONCAT, 1, 5>(h, kC2, b.a[1], a, stream))) return rc;
   if (dump(1, b.a[2], 128)) return WN_OK;
   act(b.a[3], 128, nullptr, 0);
-  if ((rc = launch_umma<3, 128, 128, 2, 2, kEpiAct, 0, 1, 3>(h, kC3, b.a[2], a, stream))) return rc;
+  if ((rc = launch_umma<3, 128, 128, 2, WN_C23_CONCAT ? 1 : 2, kEpiAct, WN_C23_CONCAT, 1, WN_C3_TPS>(h, kC3, b.a[2], a, stream))) return rc;
   if (dump(2, b.a[3], 128)) return WN_OK;
   act(b.a[4], 64, nullptr, 0);
   if ((rc = launch_umma<1, 128, 64, 2, 2, kEpiAct, 1>(h, kC4, b.a[3], a, stream))) return rc;
@@ -251,13 +269,13 @@ int umma_forward_layers(wn_handle* h, const float* const in[4], const int64_t st
   if ((rc = launch_umma<5, 64, 64, 2, 2, kEpiAct, 1, 1, 5>(h, kC6, b.a[5], a, stream))) return rc;
   if (dump(5, b.a[6], 64)) return WN_OK;
   act(b.a[7], 64, nullptr, 0);
-  if ((rc = launch_umma<3, 64, 64, 2, 2, kEpiAct, 1, 1, 3>(h, kC7, b.a[6], a, stream))) return rc;
+  if ((rc = launch_umma<3, 64, 64, 2, 2, kEpiAct, 1, 1, WN_C7_TPS>(h, kC7, b.a[6], a, stream))) return rc;
   if (dump(6, b.a[7], 64)) return WN_OK;
   a.out_f32 = dbg_layer == 7 ? dbg_dst : b.cm;
   if ((rc = launch_umma<3, 64, 16, 4, 2, kEpiSigmoid, 1, 1, 9>(h, kC8, b.a[7], a, stream))) return rc;
   if (dbg_layer == 7) return WN_OK;
   act(b.r[2], 96, nullptr, 0);
-  if ((rc = launch_umma<5, 96, 32, 2, 1, kEpiAct, 1, 3, 5>(h, kR2, b.r[1], a, stream))) return rc;
+  if ((rc = launch_umma<5, 96, 32, 2, 1, kEpiAct, 1, 3, WN_R2_TPS>(h, kR2, b.r[1], a, stream))) return rc;
   if (dump(9, b.r[2], 96)) return WN_OK;
   a.out_f32 = out;
   a.cm = b.cm;

@@ -168,17 +168,21 @@ struct UmmaCfg {
   static constexpr int A_STAGE = (4 * PLANE_BYTES + 1023) / 1024 * 1024;  // hi k0, hi k1, lo k0, lo k1
   static constexpr int B_TAP = NPAD * 64;                                  // one tap: [hi|lo][k8 0|1][NPAD][16 B]
   static constexpr int B_STAGE = TPS * B_TAP;
+  // WRAP: TPS does not divide the tap count (single-chunk layers only): weight stages are groups of TPS
+  // consecutive taps of the endless tap stream (tile after tile), so a group may straddle two tiles
+  static constexpr bool WRAP = (KS * KS) % TPS != 0;
   static constexpr int NSTAGE_PER_CHUNK = KS * KS / TPS;
   static constexpr int BUDGET = 225 * 1024 - 2048;
   // halo ring: enough stages to prefetch the next chunk (or the next tile when there is one chunk)
-  static constexpr int NA_WANT = NCHUNK == 1 ? 2 : 3;
+  // (a 1x1 layer is HBM-bound and its stages are small: keep more loads in flight)
+  static constexpr int NA_WANT = NCHUNK == 1 ? 2 : KS == 1 ? 6 : 3;
   // weight ring: whatever is left after the halo ring, 2..8 stages; deep rings hide the L2 latency of
   // the bulk copies when a stage carries only a few MMAs (first layer: 14 KB per 4-6 MMAs)
   static constexpr int NB_FIT = (BUDGET - NA_WANT * A_STAGE) / B_STAGE;
   static constexpr int NB = NB_FIT > 8 ? 8 : NB_FIT < 2 ? 2 : NB_FIT;
   static constexpr int NA_FIT = (BUDGET - NB * B_STAGE) / A_STAGE;
   static constexpr int NA = NA_FIT > NA_WANT ? NA_WANT : NA_FIT;
-  static_assert((KS * KS) % TPS == 0, "taps per stage must divide the tap count");
+  static_assert(!WRAP || (CIN_PAD == 16 && TPS < KS * KS), "wrapping tap groups need a single-chunk layer");
   static constexpr int CPB = NCHUNK / NBLK;                // chunks per diagonal block
   static constexpr int N1 = CONCAT ? 2 * NPAD : NPAD;      // UMMA N of the a_hi pass
   static constexpr int BLK_COLS = N1;                      // accumulator columns per block
@@ -303,7 +307,24 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
     }
   } else if (warp == kWarpB) {
     // ===================== B producer: packed weight stages =====================
-    if (lane == 0) {
+    if (lane == 0 && C::WRAP) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const int my_tiles = (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+      const int groups = (my_tiles * KS * KS + TPS - 1) / TPS;  // the last one may run past the end: harmless
+      int t0 = 0;                                                 // first tap of the group, modulo KS*KS
+      for (int gi = 0; gi < groups; gi++) {
+        mbar_wait(&b_empty[stage], phase ^ 1);
+        mbar_expect_tx(&b_full[stage], C::B_STAGE);
+        uint8_t* dst = b_stages + stage * C::B_STAGE;
+        const int head = min(TPS, KS * KS - t0);
+        bulk_load(dst, g.wpk + (size_t)t0 * C::B_TAP, head * C::B_TAP, &b_full[stage]);
+        if (head < TPS) bulk_load(dst + head * C::B_TAP, g.wpk, (TPS - head) * C::B_TAP, &b_full[stage]);
+        t0 += TPS;
+        if (t0 >= KS * KS) t0 -= KS * KS;
+        if (++stage == C::NB) { stage = 0; phase ^= 1; }
+      }
+    } else if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -335,6 +356,68 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
       uint32_t aphase = 0, bphase = 0, tphase = 0;
       const bool skip_lo = (g.skip_lo != nullptr && *g.skip_lo != 0) || (g.dbg & 4);
       bool b_ready = false;  // result of the early probe of the upcoming weight stage
+      if constexpr (C::WRAP) {
+        int slot = 0;  // position of the next tap inside its weight group
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+          mbar_wait(&t_empty[acc], tphase ^ 1);
+          mbar_wait(&a_full[astage], aphase);
+          tc_fence_after();
+          const uint32_t d_tile = (uint32_t)(acc * S * C::SUB_COLS);
+          const uint32_t a_lo32 = (smem_u32(a_stages + astage * C::A_STAGE) >> 4) | ((uint32_t)(C::PLANE_BYTES >> 4) << 16);
+          int tap = 0, ky = 0, kx = 0;
+          while (tap < KS * KS) {  // one segment = the taps of this tile inside one weight group
+            if (slot == 0) {
+              mbar_wait(&b_full[bstage], bphase);
+              tc_fence_after();
+            }
+            const int seg = min(TPS - slot, KS * KS - tap);
+            const uint32_t b_stage32 = (smem_u32(b_stages + bstage * C::B_STAGE) >> 4) | ((b_lbo >> 4) << 16);
+            if (elect_one_sync()) {
+              constexpr uint32_t a_lo_off = (uint32_t)(2 * C::PLANE_BYTES >> 4);
+              uint32_t b_lo32 = b_stage32 + (uint32_t)(slot * (C::B_TAP >> 4));
+              int yy = ky, xx = kx;
+              for (int j = 0; j < seg; j++) {
+                const uint32_t a_tap = a_lo32 + (uint32_t)(yy * C::HALO_W + xx);
+                const uint32_t first = (tap + j) == 0 ? 0u : 1u;
+#pragma unroll
+                for (int sb = 0; sb < S; sb++)
+                  umma_bf16_split(d_tile + (uint32_t)(sb * C::SUB_COLS), a_tap + (uint32_t)(sb * kSubW), a_hi32, b_lo32,
+                                  b_hi32, idesc1, first);
+                if (!skip_lo) {
+#pragma unroll
+                  for (int sb = 0; sb < S; sb++)
+                    umma_bf16_split(d_tile + (uint32_t)(sb * C::SUB_COLS), a_tap + (uint32_t)(sb * kSubW) + a_lo_off,
+                                    a_hi32, b_lo32, b_hi32, idesc2, 1u);
+                }
+                if (!CONCAT && !(g.dbg & 4)) {
+#pragma unroll
+                  for (int sb = 0; sb < S; sb++)
+                    umma_bf16_split(d_tile + (uint32_t)(sb * C::SUB_COLS), a_tap + (uint32_t)(sb * kSubW), a_hi32,
+                                    b_lo32 + (uint32_t)(2 * NPAD * 16 >> 4), b_hi32, idesc2, 1u);
+                }
+                b_lo32 += (uint32_t)(C::B_TAP >> 4);
+                if (++xx == KS) { xx = 0; ++yy; }
+              }
+              if (slot + seg == TPS) umma_commit(&b_empty[bstage]);
+              if (tap + seg == KS * KS) {
+                umma_commit(&a_empty[astage]);
+                umma_commit(&t_full[acc]);
+              }
+            }
+            __syncwarp();
+            tap += seg;
+            kx += seg;
+            while (kx >= KS) { kx -= KS; ++ky; }
+            slot += seg;
+            if (slot == TPS) {
+              slot = 0;
+              if (++bstage == C::NB) { bstage = 0; bphase ^= 1; }
+            }
+          }
+          if (++astage == C::NA) { astage = 0; aphase ^= 1; }
+          if (++acc == AS) { acc = 0; tphase ^= 1; }
+        }
+      } else
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         mbar_wait(&t_empty[acc], tphase ^ 1);
         tc_fence_after();

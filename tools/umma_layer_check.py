@@ -17,7 +17,7 @@ eng.pack_weights(m._ordered_params())
 torch.cuda.synchronize()
 names = ["cmg.conv1", "cmg.conv2", "cmg.conv3", "cmg.conv4", "cmg.conv5", "cmg.conv6", "cmg.conv7", "cm(sigmoid)",
          "refiner conv1 x3", "refiner conv2 x3"]
-for shape in [(1, 32, 48), (2, 37, 53), (1, 300, 500)]:  # the last one: several tiles per CTA
+for shape in [(1, 32, 48), (2, 37, 53), (1, 40, 40), (1, 300, 500)]:  # odd tile count; several tiles per CTA  # the last one: several tiles per CTA
     n, h, w = shape
     ins = [torch.rand(n, 3, h, w, device="cuda") for _ in range(4)]
     print("shape", shape)

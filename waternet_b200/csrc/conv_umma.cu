@@ -85,13 +85,26 @@ enum UmmaLayer {
 #ifndef WN_C23_CONCAT
 #define WN_C23_CONCAT 0
 #endif
+// The tensor-bound confidence-map layers (conv2, conv3, conv5..7) run as CTA pairs (cta_group::2);
+// -DWN_CG=1 builds the single-CTA form for same-box A/B runs (profiles/r1_ab_cta_pairs.log).
+#ifndef WN_CG
+#define WN_CG 2
+#endif
 struct UmmaLayerSpec {
   int ks, cinpad, npad, cout, slot, concat, nblk;  // npad = output columns per diagonal block
+  int cg;                                           // CTAs per MMA: 2 = weight rows split over a CTA pair
 };
 static const UmmaLayerSpec kSpecs[kNumUmmaLayers] = {
-    {7, 16, 224, 224, 0, 0, 1}, {5, 128, 128, 128, 1, WN_C23_CONCAT, 1}, {3, 128, 128, 128, 2, WN_C23_CONCAT, 1}, {1, 128, 64, 64, 3, 1, 1},
-    {7, 64, 64, 64, 4, 1, 1},   {5, 64, 64, 64, 5, 1, 1},    {3, 64, 64, 64, 6, 1, 1},    {3, 64, 16, 3, 7, 1, 1},
-    {5, 96, 32, 96, 9, 1, 3},   {3, 96, 16, 9, 10, 1, 1}};
+    {7, 16, 224, 224, 0, 0, 1, 1},
+    {5, 128, 128, 128, 1, WN_C23_CONCAT, 1, WN_CG},
+    {3, 128, 128, 128, 2, WN_C23_CONCAT, 1, WN_CG},
+    {1, 128, 64, 64, 3, 1, 1, 1},
+    {7, 64, 64, 64, 4, 1, 1, WN_CG},
+    {5, 64, 64, 64, 5, 1, 1, WN_CG},
+    {3, 64, 64, 64, 6, 1, 1, WN_CG},
+    {3, 64, 16, 3, 7, 1, 1, 1},
+    {5, 96, 32, 96, 9, 1, 3, 1},
+    {3, 96, 16, 9, 10, 1, 1, 1}};
 
 struct UmmaWeights {
   uint8_t* stages[kNumUmmaLayers];
@@ -100,6 +113,8 @@ struct UmmaWeights {
 };
 
 static size_t stage_bytes_total(const UmmaLayerSpec& s) {
+  if (s.cg == 2)  // two per-rank images (UmmaCfg::B_TAP per tap each)
+    return (size_t)2 * (s.cinpad / 16) * s.ks * s.ks * s.npad * (s.concat ? 48 : 32);
   return (size_t)(s.cinpad / 16) * s.ks * s.ks * s.npad * 64;  // one block's rows per stage
 }
 
@@ -143,8 +158,12 @@ int umma_pack_weights(wn_handle* h, const float* const* params, cudaStream_t str
       for (int r = 0; r < 3 && !rc; r++) rc = scatter(8 + 3 * r + 2, 3, 32, 3 * r, 32, 32 * r, 0);
     }
     if (rc) return rc;
-    pack_stages_kernel<<<256, 256, 0, stream>>>(u->dense, (__nv_bfloat16*)u->stages[li], s.npad, s.cinpad, kk,
-                                                s.concat, s.nblk);
+    if (s.cg == 2)
+      pack_stages_cg2_kernel<<<256, 256, 0, stream>>>(u->dense, (__nv_bfloat16*)u->stages[li], s.npad, s.cinpad, kk,
+                                                      s.concat);
+    else
+      pack_stages_kernel<<<256, 256, 0, stream>>>(u->dense, (__nv_bfloat16*)u->stages[li], s.npad, s.cinpad, kk,
+                                                  s.concat, s.nblk);
     WN_LAUNCH_CHECK(h);
   }
   return WN_OK;
@@ -189,14 +208,15 @@ size_t umma_forward_workspace_bytes(int n, int h, int w) {
 #define WN_R2_TPS 5
 #endif
 
-template <int KS, int CIN_PAD, int NPAD, int S, int AS, int EPI, int CONCAT = 0, int NBLK = 1, int TPS = 1>
+template <int KS, int CIN_PAD, int NPAD, int S, int AS, int EPI, int CONCAT = 0, int NBLK = 1, int TPS = 1, int CG = 1>
 static int launch_umma(wn_handle* h, int li, void* in_base, ConvArgs a, cudaStream_t stream) {
   const UmmaLayerSpec& spec = kSpecs[li];
-  if (spec.ks != KS || spec.cinpad != CIN_PAD || spec.npad != NPAD || spec.concat != CONCAT || spec.nblk != NBLK) {
+  if (spec.ks != KS || spec.cinpad != CIN_PAD || spec.npad != NPAD || spec.concat != CONCAT || spec.nblk != NBLK ||
+      spec.cg != CG) {
     set_error("internal: launch configuration of layer %d does not match its packed weights", li);
     return WN_E_STATE;
   }
-  return launch_conv<KS, CIN_PAD, NPAD, S, AS, EPI, CONCAT, NBLK, TPS>(h, spec.slot, h->umma->stages[li],
+  return launch_conv<KS, CIN_PAD, NPAD, S, AS, EPI, CONCAT, NBLK, TPS, CG>(h, spec.slot, h->umma->stages[li],
                                                                        h->umma->bias[li], in_base, a, stream);
 }
 
@@ -254,22 +274,22 @@ int umma_forward_layers(wn_handle* h, const float* const in[4], const int64_t st
   a.skip_lo = nullptr;
   if (dump(0, b.a[1], 128) || dump(8, b.r[1], 96)) return WN_OK;
   act(b.a[2], 128, nullptr, 0);
-  if ((rc = launch_umma<5, 128, 128, 2, WN_C23_CONCAT ? 1 : 2, kEpiAct, WN_C23_CONCAT, 1, 5>(h, kC2, b.a[1], a, stream))) return rc;
+  if ((rc = launch_umma<5, 128, 128, 2, WN_C23_CONCAT ? 1 : 2, kEpiAct, WN_C23_CONCAT, 1, 5, WN_CG>(h, kC2, b.a[1], a, stream))) return rc;
   if (dump(1, b.a[2], 128)) return WN_OK;
   act(b.a[3], 128, nullptr, 0);
-  if ((rc = launch_umma<3, 128, 128, 2, WN_C23_CONCAT ? 1 : 2, kEpiAct, WN_C23_CONCAT, 1, WN_C3_TPS>(h, kC3, b.a[2], a, stream))) return rc;
+  if ((rc = launch_umma<3, 128, 128, 2, WN_C23_CONCAT ? 1 : 2, kEpiAct, WN_C23_CONCAT, 1, WN_C3_TPS, WN_CG>(h, kC3, b.a[2], a, stream))) return rc;
   if (dump(2, b.a[3], 128)) return WN_OK;
   act(b.a[4], 64, nullptr, 0);
   if ((rc = launch_umma<1, 128, 64, 2, 2, kEpiAct, 1>(h, kC4, b.a[3], a, stream))) return rc;
   if (dump(3, b.a[4], 64)) return WN_OK;
   act(b.a[5], 64, nullptr, 0);
-  if ((rc = launch_umma<7, 64, 64, 2, 2, kEpiAct, 1, 1, 7>(h, kC5, b.a[4], a, stream))) return rc;
+  if ((rc = launch_umma<7, 64, 64, 2, 2, kEpiAct, 1, 1, 7, WN_CG>(h, kC5, b.a[4], a, stream))) return rc;
   if (dump(4, b.a[5], 64)) return WN_OK;
   act(b.a[6], 64, nullptr, 0);
-  if ((rc = launch_umma<5, 64, 64, 2, 2, kEpiAct, 1, 1, 5>(h, kC6, b.a[5], a, stream))) return rc;
+  if ((rc = launch_umma<5, 64, 64, 2, 2, kEpiAct, 1, 1, 5, WN_CG>(h, kC6, b.a[5], a, stream))) return rc;
   if (dump(5, b.a[6], 64)) return WN_OK;
   act(b.a[7], 64, nullptr, 0);
-  if ((rc = launch_umma<3, 64, 64, 2, 2, kEpiAct, 1, 1, WN_C7_TPS>(h, kC7, b.a[6], a, stream))) return rc;
+  if ((rc = launch_umma<3, 64, 64, 2, 2, kEpiAct, 1, 1, WN_C7_TPS, WN_CG>(h, kC7, b.a[6], a, stream))) return rc;
   if (dump(6, b.a[7], 64)) return WN_OK;
   a.out_f32 = dbg_layer == 7 ? dbg_dst : b.cm;
   if ((rc = launch_umma<3, 64, 16, 4, 2, kEpiSigmoid, 1, 1, 9>(h, kC8, b.a[7], a, stream))) return rc;

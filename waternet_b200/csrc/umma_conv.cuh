@@ -48,6 +48,24 @@ __device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
       : "memory");
   return done != 0;
 }
+// CTA-pair kernels: arrival on the barrier at the same shared-memory offset in CTA `rank` of the cluster.
+// Waiters use the plain mbar_wait: what they order is asynchronous-proxy work (TMA writes that have
+// completed on a barrier before the arrival was sent; MMAs issued after the wait), and a cluster-scope
+// acquire on every stage costs the issuer ~600 cycles (measured: 3x3 layers got 30 % slower with it).
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(rank));
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -109,6 +127,37 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                    smem_u32(bar))
                : "memory");
 }
+// CTA-pair forms: one M=256 MMA over both CTAs' shared memory / TMEM (issued by the leader CTA only);
+// the commit arrives on the barrier at this offset in BOTH CTAs.
+__device__ __forceinline__ void umma2_bf16_split(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                                 uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_commit(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"((uint16_t)3)
+      : "memory");
+}
+template <int CG>
+__device__ __forceinline__ void umma_issue(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                           uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  if constexpr (CG == 2) umma2_bf16_split(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, accumulate);
+  else umma_bf16_split(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, accumulate);
+}
+template <int CG>
+__device__ __forceinline__ void umma_done(uint64_t* bar) {
+  if constexpr (CG == 2) umma2_commit(bar);
+  else umma_commit(bar);
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -159,14 +208,21 @@ constexpr int kWarpA = 8, kWarpB = 9, kWarpTmem = 10, kWarpMma = 11;
 //        chunk c only feeds block c / (NCHUNK / NBLK), so only that block's weights are staged.
 // TPS    filter taps per weight stage: small-N layers batch a kernel row (or all taps) per stage so
 //        that the per-stage pipeline cost (barrier wait, commit, bulk-copy latency) is amortised.
-template <int KS, int CIN_PAD, int NPAD, int S, int AS, int CONCAT = 0, int NBLK = 1, int TPS = 1>
+// CG     CTAs per MMA (tcgen05 cta_group).  2: a cluster of two CTAs works on two adjacent tiles; the leader
+//        issues M=256 MMAs over both CTAs' halo tiles, and each CTA stages only HALF of the weight rows
+//        (the N dimension is split over the pair) -- the shared-memory operand traffic per MMA, which
+//        bounds N<=128 layers (tools/umma_rate_probe.cu), drops from 128+N to 128+N/2 rows.
+template <int KS, int CIN_PAD, int NPAD, int S, int AS, int CONCAT = 0, int NBLK = 1, int TPS = 1, int CG = 1>
 struct UmmaCfg {
   static constexpr int TILE_W = kSubW * S, TILE_H = kSubH;
   static constexpr int HALO_W = TILE_W + KS - 1, HALO_H = TILE_H + KS - 1;
   static constexpr int NCHUNK = CIN_PAD / 16;
   static constexpr int PLANE_BYTES = HALO_W * HALO_H * 16;
   static constexpr int A_STAGE = (4 * PLANE_BYTES + 1023) / 1024 * 1024;  // hi k0, hi k1, lo k0, lo k1
-  static constexpr int B_TAP = NPAD * 64;                                  // one tap: [hi|lo][k8 0|1][NPAD][16 B]
+  // one tap of weights.  CG=1: [hi|lo][k8 0|1][NPAD][16 B] (CONCAT: [k8][hi rows | lo rows]).
+  // CG=2, per CTA: [hi|lo][k8][NPAD/2 rows of this rank]; CONCAT: [k8][NPAD rows (rank 0: w_hi, rank 1:
+  // w_lo) | NPAD/2 rows of w_hi for the a_lo pass] -- the same descriptor serves both CTAs.
+  static constexpr int B_TAP = CG == 1 ? NPAD * 64 : CONCAT ? NPAD * 48 : NPAD * 32;
   static constexpr int B_STAGE = TPS * B_TAP;
   // WRAP: TPS does not divide the tap count (single-chunk layers only): weight stages are groups of TPS
   // consecutive taps of the endless tap stream (tile after tile), so a group may straddle two tiles
@@ -178,11 +234,17 @@ struct UmmaCfg {
   static constexpr int NA_WANT = NCHUNK == 1 ? 2 : KS == 1 ? 6 : 3;
   // weight ring: whatever is left after the halo ring, 2..8 stages; deep rings hide the L2 latency of
   // the bulk copies when a stage carries only a few MMAs (first layer: 14 KB per 4-6 MMAs)
-  static constexpr int NB_FIT = (BUDGET - NA_WANT * A_STAGE) / B_STAGE;
+  // CTA pairs: a halo stage is handed to the leader through one more hop (the peer's relay warp), and a
+  // chunk of a 3x3 layer lasts only ~2k cycles -- up to 6 halo stages after 4 weight stages are set aside
+  static constexpr int NA_PAIR_FIT = (BUDGET - 4 * B_STAGE) / A_STAGE;
+  static constexpr int NA_PAIR = NA_PAIR_FIT > 6 ? 6 : NA_PAIR_FIT < 2 ? 2 : NA_PAIR_FIT;
+  static constexpr int NA_TARGET = CG == 2 ? NA_PAIR : NA_WANT;
+  static constexpr int NB_FIT = (BUDGET - NA_TARGET * A_STAGE) / B_STAGE;
   static constexpr int NB = NB_FIT > 8 ? 8 : NB_FIT < 2 ? 2 : NB_FIT;
   static constexpr int NA_FIT = (BUDGET - NB * B_STAGE) / A_STAGE;
-  static constexpr int NA = NA_FIT > NA_WANT ? NA_WANT : NA_FIT;
+  static constexpr int NA = NA_FIT > NA_TARGET ? NA_TARGET : NA_FIT;
   static_assert(!WRAP || (CIN_PAD == 16 && TPS < KS * KS), "wrapping tap groups need a single-chunk layer");
+  static_assert(CG == 1 || (CG == 2 && NBLK == 1 && !WRAP && NPAD % 32 == 0), "CTA pairs: plain layers only");
   static constexpr int CPB = NCHUNK / NBLK;                // chunks per diagonal block
   static constexpr int N1 = CONCAT ? 2 * NPAD : NPAD;      // UMMA N of the a_hi pass
   static constexpr int BLK_COLS = N1;                      // accumulator columns per block
@@ -244,10 +306,10 @@ __device__ __forceinline__ void split_bf16x2(float f0, float f1, uint32_t& hi, u
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
-template <int KS, int CIN_PAD, int NPAD, int S, int AS, int EPI, int CONCAT, int NBLK, int TPS>
+template <int KS, int CIN_PAD, int NPAD, int S, int AS, int EPI, int CONCAT, int NBLK, int TPS, int CG = 1>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) {
-  using C = UmmaCfg<KS, CIN_PAD, NPAD, S, AS, CONCAT, NBLK, TPS>;
+  using C = UmmaCfg<KS, CIN_PAD, NPAD, S, AS, CONCAT, NBLK, TPS, CG>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* a_stages = smem;
@@ -259,27 +321,42 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
   uint64_t* b_empty = b_full + C::NB;
   uint64_t* t_full = b_empty + C::NB;
   uint64_t* t_empty = t_full + AS;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + AS);
+  uint64_t* a_full_peer = t_empty + AS;        // CG=2, leader: "the peer CTA's stage is full too"
+  uint64_t* b_full_peer = a_full_peer + C::NA;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_full_peer + C::NB);
   float* s_bias = reinterpret_cast<float*>(tail + 512);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int num_tiles = g.tiles_x * g.tiles_y * g.N;
+  // a cluster of CG CTAs takes CG adjacent tiles at a time; an odd tail repeats the last tile in the
+  // peer CTA (computed, not stored) so that both CTAs walk the same pipeline sequence
+  const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
+  const int cid = (int)blockIdx.x / CG, ncl = (int)gridDim.x / CG;
+  const int num_ptiles = (num_tiles + CG - 1) / CG;
 
   if (tid == 0) {
-    for (int i = 0; i < C::NA; i++) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-    for (int i = 0; i < C::NB; i++) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-    for (int i = 0; i < AS; i++) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 8); }
+    for (int i = 0; i < C::NA; i++) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); mbar_init(&a_full_peer[i], 1); }
+    for (int i = 0; i < C::NB; i++) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); mbar_init(&b_full_peer[i], 1); }
+    for (int i = 0; i < AS; i++) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 8 * CG); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int i = tid; i < NBLK * NPAD; i += kThreads) s_bias[i] = g.bias[i];
   if (warp == kWarpTmem) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"((uint32_t)C::TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (CG == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"((uint32_t)C::TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"((uint32_t)C::TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();  // the peer's barriers are initialised before anyone arrives on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (tmem_base != 0) __trap();  // see the MMA issuer: accumulators are addressed from column 0
@@ -289,7 +366,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int pt = cid; pt < num_ptiles; pt += ncl) {
+        const int tile = min(pt * CG + (int)rank, num_tiles - 1);
         const int n = tile / (g.tiles_x * g.tiles_y);
         const int rem = tile - n * g.tiles_x * g.tiles_y;
         const int ty = rem / g.tiles_x, tx = rem - ty * g.tiles_x;
@@ -327,16 +405,38 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
     } else if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      // CG=2: this rank's half of the weight rows (second image right after the first)
+      const uint8_t* wpk = g.wpk + (size_t)rank * ((size_t)C::NCHUNK * C::NSTAGE_PER_CHUNK * C::B_STAGE);
+      for (int pt = cid; pt < num_ptiles; pt += ncl) {
         for (int it = 0; it < C::NCHUNK * C::NSTAGE_PER_CHUNK; it++) {
           mbar_wait(&b_empty[stage], phase ^ 1);
-          if ((g.dbg & 2) && (phase || tile != (int)blockIdx.x)) {
+          if ((g.dbg & 2) && (phase || pt != cid)) {
             mbar_arrive(&b_full[stage]);  // bring-up: reuse whatever the stage holds
           } else {
             mbar_expect_tx(&b_full[stage], C::B_STAGE);
-            bulk_load(b_stages + stage * C::B_STAGE, g.wpk + (size_t)it * C::B_STAGE, C::B_STAGE, &b_full[stage]);
+            bulk_load(b_stages + stage * C::B_STAGE, wpk + (size_t)it * C::B_STAGE, C::B_STAGE, &b_full[stage]);
           }
           if (++stage == C::NB) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == kWarpMma && CG == 2 && rank != 0) {
+    // ===================== peer CTA of a pair: relay "stage full" to the leader =====================
+    // The leader issues the MMAs for both CTAs; it learns that THIS CTA's halo / weight stage has landed
+    // from an arrival on its a_full_peer / b_full_peer barrier, sent here in the leader's consumption order.
+    if (lane == 0) {
+      int astage = 0, bstage = 0;
+      uint32_t aphase = 0, bphase = 0;
+      for (int pt = cid; pt < num_ptiles; pt += ncl) {
+        for (int c = 0; c < C::NCHUNK; c++) {
+          mbar_wait(&a_full[astage], aphase);
+          mbar_arrive_remote(&a_full_peer[astage], 0);
+          for (int tg = 0; tg < C::NSTAGE_PER_CHUNK; tg++) {
+            mbar_wait(&b_full[bstage], bphase);
+            mbar_arrive_remote(&b_full_peer[bstage], 0);
+            if (++bstage == C::NB) { bstage = 0; bphase ^= 1; }
+          }
+          if (++astage == C::NA) { astage = 0; aphase ^= 1; }
         }
       }
     }
@@ -345,13 +445,19 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
     // The whole warp walks the pipeline (converged, so every operand stays in uniform registers);
     // one elected lane issues the MMAs and commits.
     {
-      constexpr uint32_t idesc1 = make_idesc(128, C::N1);  // a_hi pass
-      constexpr uint32_t idesc2 = make_idesc(128, NPAD);   // a_lo x w_hi (and a_hi x w_lo without CONCAT)
+      constexpr uint32_t idesc1 = make_idesc(128 * CG, C::N1);  // a_hi pass
+      constexpr uint32_t idesc2 = make_idesc(128 * CG, NPAD);   // a_lo x w_hi (and a_hi x w_lo without CONCAT)
       // descriptor halves: hi = SBO | version, lo = start address | LBO
       constexpr uint32_t a_hi32 = ((uint32_t)(C::HALO_W * 16) >> 4) | (1u << 14);
       constexpr uint32_t b_hi32 = (128u >> 4) | (1u << 14);
       // weight stage: CONCAT [k8][hi rows | lo rows][16 B] (LBO = 2*NPAD*16), else [hi|lo][k8][rows][16 B]
-      constexpr uint32_t b_lbo = (uint32_t)((CONCAT ? 2 * NPAD : NPAD) * 16);
+      // CG=2 (per CTA): CONCAT [k8][NPAD rows | NPAD/2 rows of w_hi][16 B], else [hi|lo][k8][NPAD/2 rows][16 B]
+      constexpr uint32_t b_lbo =
+          CG == 2 ? (uint32_t)((CONCAT ? NPAD * 24 : NPAD * 8)) : (uint32_t)((CONCAT ? 2 * NPAD : NPAD) * 16);
+      // start of the rows the a_lo pass multiplies (16-byte units, inside a tap)
+      constexpr uint32_t b_lopass_off = (CG == 2 && CONCAT) ? (uint32_t)NPAD : 0u;
+      // start of the w_lo rows for the a_hi x w_lo pass without CONCAT (16-byte units)
+      constexpr uint32_t b_wlo_off = CG == 2 ? (uint32_t)NPAD : (uint32_t)(2 * NPAD * 16 >> 4);
       int astage = 0, bstage = 0, acc = 0;
       uint32_t aphase = 0, bphase = 0, tphase = 0;
       const bool skip_lo = (g.skip_lo != nullptr && *g.skip_lo != 0) || (g.dbg & 4);
@@ -418,20 +524,23 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
           if (++acc == AS) { acc = 0; tphase ^= 1; }
         }
       } else
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        mbar_wait(&t_empty[acc], tphase ^ 1);
+      for (int pt = cid; pt < num_ptiles; pt += ncl) {
+        if constexpr (CG == 2) mbar_wait(&t_empty[acc], tphase ^ 1);  // both CTAs' epilogues arrive here
+        else mbar_wait(&t_empty[acc], tphase ^ 1);
         tc_fence_after();
         // TMEM addresses are compile-time column offsets: this CTA is alone on its SM (shared memory
         // footprint) and owns the allocation at column 0 (checked after the allocation).
         const uint32_t d_tile = (uint32_t)(acc * S * C::SUB_COLS);
         for (int c = 0; c < C::NCHUNK; c++) {
           mbar_wait(&a_full[astage], aphase);
+          if constexpr (CG == 2) mbar_wait(&a_full_peer[astage], aphase);
           tc_fence_after();
           const uint32_t a_lo32 = (smem_u32(a_stages + astage * C::A_STAGE) >> 4) | ((uint32_t)(C::PLANE_BYTES >> 4) << 16);
           const int blk = NBLK > 1 ? c / C::CPB : 0;
           const uint32_t d_base = d_tile + (uint32_t)(blk * C::BLK_COLS);
           for (int tg = 0; tg < C::NSTAGE_PER_CHUNK; tg++) {
             if (!b_ready) mbar_wait(&b_full[bstage], bphase);
+            if constexpr (CG == 2) mbar_wait(&b_full_peer[bstage], bphase);
             tc_fence_after();
             {  // probe the next stage's barrier now; its latency overlaps the MMA issue below
               const int nstage = bstage + 1 == C::NB ? 0 : bstage + 1;
@@ -450,25 +559,25 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
                 // pass-major order: consecutive MMAs target different accumulators
 #pragma unroll
                 for (int s = 0; s < S; s++)  // a_hi x w_hi (CONCAT: x [w_hi | w_lo])
-                  umma_bf16_split(d_base + (uint32_t)(s * C::SUB_COLS), a_tap + (uint32_t)(s * kSubW), a_hi32, b_lo32,
-                                  b_hi32, idesc1, first);
+                  umma_issue<CG>(d_base + (uint32_t)(s * C::SUB_COLS), a_tap + (uint32_t)(s * kSubW), a_hi32, b_lo32,
+                                 b_hi32, idesc1, first);
                 if (!skip_lo) {
 #pragma unroll
                   for (int s = 0; s < S; s++)  // a_lo x w_hi
-                    umma_bf16_split(d_base + (uint32_t)(s * C::SUB_COLS), a_tap + (uint32_t)(s * kSubW) + a_lo_off,
-                                    a_hi32, b_lo32, b_hi32, idesc2, 1u);
+                    umma_issue<CG>(d_base + (uint32_t)(s * C::SUB_COLS), a_tap + (uint32_t)(s * kSubW) + a_lo_off,
+                                   a_hi32, b_lo32 + b_lopass_off, b_hi32, idesc2, 1u);
                 }
                 if (!CONCAT && !(g.dbg & 4)) {
 #pragma unroll
                   for (int s = 0; s < S; s++)  // a_hi x w_lo
-                    umma_bf16_split(d_base + (uint32_t)(s * C::SUB_COLS), a_tap + (uint32_t)(s * kSubW), a_hi32,
-                                    b_lo32 + (uint32_t)(2 * NPAD * 16 >> 4), b_hi32, idesc2, 1u);
+                    umma_issue<CG>(d_base + (uint32_t)(s * C::SUB_COLS), a_tap + (uint32_t)(s * kSubW), a_hi32,
+                                   b_lo32 + b_wlo_off, b_hi32, idesc2, 1u);
                 }
               }
-              umma_commit(&b_empty[bstage]);
+              umma_done<CG>(&b_empty[bstage]);
               if (tg == C::NSTAGE_PER_CHUNK - 1) {
-                umma_commit(&a_empty[astage]);
-                if (c == C::NCHUNK - 1) umma_commit(&t_full[acc]);
+                umma_done<CG>(&a_empty[astage]);
+                if (c == C::NCHUNK - 1) umma_done<CG>(&t_full[acc]);
               }
             }
             __syncwarp();
@@ -488,7 +597,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
     const int row = quarter * 32 + lane;      // TMEM lane == pixel row of the sub-tile
     const int px = row & 7, py = row >> 3;
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int pt = cid; pt < num_ptiles; pt += ncl) {
+      const bool tile_valid = pt * CG + (int)rank < num_tiles;  // the odd tail's repeat is not stored
+      const int tile = min(pt * CG + (int)rank, num_tiles - 1);
       const int n = tile / (g.tiles_x * g.tiles_y);
       const int rem = tile - n * g.tiles_x * g.tiles_y;
       const int ty = rem / g.tiles_x, tx = rem - ty * g.tiles_x;
@@ -498,7 +609,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
 #pragma unroll 1
       for (int s = egroup; s < S; s += 2) {
         const int gx = tx * C::TILE_W + s * kSubW + px;
-        const bool inside = gx < g.W && gy < g.H;
+        const bool inside = gx < g.W && gy < g.H && tile_valid;
         const uint32_t t_addr = tmem_base + lane_base + (uint32_t)((acc * S + s) * C::SUB_COLS);
         // Issue the TMEM loads of NC accumulator columns starting at output channel ch0 (+ the
         // a_hi x w_lo half when CONCAT); the caller waits once, later, so loads overlap ALU work.
@@ -602,18 +713,27 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&t_empty[acc]);
+      if (lane == 0) {
+        if constexpr (CG == 2) mbar_arrive_remote(&t_empty[acc], 0);  // the leader's barrier counts both CTAs
+        else mbar_arrive(&t_empty[acc]);
+      }
       if (++acc == AS) { acc = 0; tphase ^= 1; }
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();  // nobody leaves (or frees TMEM) while the pair still works
   if (warp == kWarpTmem) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                 "r"((uint32_t)C::TMEM_COLS)
-                 : "memory");
+    if constexpr (CG == 2)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                   "r"((uint32_t)C::TMEM_COLS)
+                   : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                   "r"((uint32_t)C::TMEM_COLS)
+                   : "memory");
   }
 }
 
@@ -666,6 +786,38 @@ static __global__ void pack_stages_kernel(const float* __restrict__ dense, __nv_
   }
 }
 
+// CTA-pair (CG=2) weight stages: two images, one per cluster rank, each holding that rank's half of the
+// N dimension per (chunk, tap) -- see UmmaCfg::B_TAP.  dense is [npad][cinpad][kk] (single block).
+static __global__ void pack_stages_cg2_kernel(const float* __restrict__ dense, __nv_bfloat16* __restrict__ out,
+                                              int npad, int cinpad, int kk, int concat) {
+  const int nchunk = cinpad / 16;
+  const int rows = concat ? npad + npad / 2 : npad / 2;        // rows per k8 group (per hi/lo part)
+  const int parts = concat ? 1 : 2;                            // non-concat: hi part then lo part
+  const size_t per_rank = (size_t)nchunk * kk * parts * 2 * rows * 8;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < 2 * per_rank; i += (size_t)gridDim.x * blockDim.x) {
+    const int rank = (int)(i / per_rank);
+    size_t r = i % per_rank;
+    const int e = (int)(r % 8); r /= 8;
+    const int q = (int)(r % rows); r /= rows;
+    const int k8 = (int)(r % 2); r /= 2;
+    const int part = (int)(r % parts); r /= parts;
+    const int tap = (int)(r % kk);
+    const int chunk = (int)(r / kk);
+    int row, lo;
+    if (concat) {
+      if (q < npad) { row = q; lo = rank; }                      // hi pass: rank 0 supplies w_hi, rank 1 w_lo
+      else { row = rank * (npad / 2) + (q - npad); lo = 0; }     // a_lo pass: this rank's half of w_hi
+    } else {
+      row = rank * (npad / 2) + q;
+      lo = part;
+    }
+    const int cin = chunk * 16 + k8 * 8 + e;
+    const float w = dense[((size_t)row * cinpad + cin) * kk + tap];
+    const __nv_bfloat16 hi = __float2bfloat16_rn(w);
+    out[i] = lo == 0 ? hi : __float2bfloat16_rn(w - __bfloat162float(hi));
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // Host helpers
 // ------------------------------------------------------------------------------------------
@@ -704,10 +856,10 @@ static int make_tmap(CUtensorMap* tm, void* base, int planes_total, int N, int H
 }
 
 // Launch one convolution.  `slot` is the timing slot (common.cuh).
-template <int KS, int CIN_PAD, int NPAD, int S, int AS, int EPI, int CONCAT = 0, int NBLK = 1, int TPS = 1>
+template <int KS, int CIN_PAD, int NPAD, int S, int AS, int EPI, int CONCAT = 0, int NBLK = 1, int TPS = 1, int CG = 1>
 static int launch_conv(wn_handle* h, int slot, const uint8_t* wpk, const float* bias, void* in_base, ConvArgs a,
                        cudaStream_t stream) {
-  using C = UmmaCfg<KS, CIN_PAD, NPAD, S, AS, CONCAT, NBLK, TPS>;
+  using C = UmmaCfg<KS, CIN_PAD, NPAD, S, AS, CONCAT, NBLK, TPS, CG>;
   int rc = get_encoder();
   if (rc) return rc;
   CUtensorMap tm;
@@ -720,11 +872,29 @@ static int launch_conv(wn_handle* h, int slot, const uint8_t* wpk, const float* 
   a.tiles_x = (a.W + C::TILE_W - 1) / C::TILE_W;
   a.tiles_y = (a.H + C::TILE_H - 1) / C::TILE_H;
   const long long tiles = (long long)a.tiles_x * a.tiles_y * a.N;
-  auto kern = conv_umma_kernel<KS, CIN_PAD, NPAD, S, AS, EPI, CONCAT, NBLK, TPS>;
+  auto kern = conv_umma_kernel<KS, CIN_PAD, NPAD, S, AS, EPI, CONCAT, NBLK, TPS, CG>;
   WN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-  int grid = (int)(tiles < h->sm_count ? tiles : h->sm_count);
   TimedScope ts(h, slot, stream);
-  kern<<<grid, kThreads, C::SMEM_BYTES, stream>>>(tm, a);
+  if constexpr (CG == 2) {  // clusters of two CTAs (one TPC each); every pair takes two adjacent tiles at a time
+    const long long pairs = (tiles + 1) / 2;
+    const int max_pairs = h->sm_count / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(2 * (pairs < max_pairs ? pairs : max_pairs)));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = C::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    WN_CUDA(cudaLaunchKernelEx(&cfg, kern, tm, a));
+  } else {
+    int grid = (int)(tiles < h->sm_count ? tiles : h->sm_count);
+    kern<<<grid, kThreads, C::SMEM_BYTES, stream>>>(tm, a);
+  }
   WN_LAUNCH_CHECK(h);
   return WN_OK;
 }

@@ -90,12 +90,16 @@ enum UmmaLayer {
 #ifndef WN_CG
 #define WN_CG 2
 #endif
+// ... and so do the first layer and the refiners' conv2 (-DWN_CG_L1R2=1: single-CTA form)
+#ifndef WN_CG_L1R2
+#define WN_CG_L1R2 2
+#endif
 struct UmmaLayerSpec {
   int ks, cinpad, npad, cout, slot, concat, nblk;  // npad = output columns per diagonal block
   int cg;                                           // CTAs per MMA: 2 = weight rows split over a CTA pair
 };
 static const UmmaLayerSpec kSpecs[kNumUmmaLayers] = {
-    {7, 16, 224, 224, 0, 0, 1, 1},
+    {7, 16, 224, 224, 0, 0, 1, WN_CG_L1R2},
     {5, 128, 128, 128, 1, WN_C23_CONCAT, 1, WN_CG},
     {3, 128, 128, 128, 2, WN_C23_CONCAT, 1, WN_CG},
     {1, 128, 64, 64, 3, 1, 1, 1},
@@ -103,7 +107,7 @@ static const UmmaLayerSpec kSpecs[kNumUmmaLayers] = {
     {5, 64, 64, 64, 5, 1, 1, WN_CG},
     {3, 64, 64, 64, 6, 1, 1, WN_CG},
     {3, 64, 16, 3, 7, 1, 1, 1},
-    {5, 96, 32, 96, 9, 1, 3, 1},
+    {5, 96, 32, 96, 9, 1, 3, WN_CG_L1R2},
     {3, 96, 16, 9, 10, 1, 1, 1}};
 
 struct UmmaWeights {
@@ -160,7 +164,7 @@ int umma_pack_weights(wn_handle* h, const float* const* params, cudaStream_t str
     if (rc) return rc;
     if (s.cg == 2)
       pack_stages_cg2_kernel<<<256, 256, 0, stream>>>(u->dense, (__nv_bfloat16*)u->stages[li], s.npad, s.cinpad, kk,
-                                                      s.concat);
+                                                      s.concat, s.nblk);
     else
       pack_stages_kernel<<<256, 256, 0, stream>>>(u->dense, (__nv_bfloat16*)u->stages[li], s.npad, s.cinpad, kk,
                                                   s.concat, s.nblk);
@@ -270,7 +274,7 @@ int umma_forward_layers(wn_handle* h, const float* const in[4], const int64_t st
   // L1: 16 -> 128 (cmg) + 96 (refiners)
   act(b.a[1], 128, b.r[1], 96);
   a.skip_lo = b.exact_flag;
-  if ((rc = launch_umma<7, 16, 224, 2, 1, kEpiAct, 0, 1, WN_L1_TPS>(h, kL1, b.act0, a, stream))) return rc;
+  if ((rc = launch_umma<7, 16, 224, 2, 1, kEpiAct, 0, 1, WN_CG_L1R2 == 2 ? 7 : WN_L1_TPS, WN_CG_L1R2>(h, kL1, b.act0, a, stream))) return rc;
   a.skip_lo = nullptr;
   if (dump(0, b.a[1], 128) || dump(8, b.r[1], 96)) return WN_OK;
   act(b.a[2], 128, nullptr, 0);
@@ -295,7 +299,7 @@ int umma_forward_layers(wn_handle* h, const float* const in[4], const int64_t st
   if ((rc = launch_umma<3, 64, 16, 4, 2, kEpiSigmoid, 1, 1, 9>(h, kC8, b.a[7], a, stream))) return rc;
   if (dbg_layer == 7) return WN_OK;
   act(b.r[2], 96, nullptr, 0);
-  if ((rc = launch_umma<5, 96, 32, 2, 1, kEpiAct, 1, 3, WN_R2_TPS>(h, kR2, b.r[1], a, stream))) return rc;
+  if ((rc = launch_umma<5, 96, 32, 2, 1, kEpiAct, 1, 3, WN_R2_TPS, WN_CG_L1R2>(h, kR2, b.r[1], a, stream))) return rc;
   if (dump(9, b.r[2], 96)) return WN_OK;
   a.out_f32 = out;
   a.cm = b.cm;

@@ -244,7 +244,7 @@ struct UmmaCfg {
   static constexpr int NA_FIT = (BUDGET - NB * B_STAGE) / A_STAGE;
   static constexpr int NA = NA_FIT > NA_TARGET ? NA_TARGET : NA_FIT;
   static_assert(!WRAP || (CIN_PAD == 16 && TPS < KS * KS), "wrapping tap groups need a single-chunk layer");
-  static_assert(CG == 1 || (CG == 2 && NBLK == 1 && !WRAP && NPAD % 32 == 0), "CTA pairs: plain layers only");
+  static_assert(CG == 1 || (CG == 2 && !WRAP && NPAD % 32 == 0), "CTA pairs: no wrapping tap groups");
   static constexpr int CPB = NCHUNK / NBLK;                // chunks per diagonal block
   static constexpr int N1 = CONCAT ? 2 * NPAD : NPAD;      // UMMA N of the a_hi pass
   static constexpr int BLK_COLS = N1;                      // accumulator columns per block
@@ -787,10 +787,11 @@ static __global__ void pack_stages_kernel(const float* __restrict__ dense, __nv_
 }
 
 // CTA-pair (CG=2) weight stages: two images, one per cluster rank, each holding that rank's half of the
-// N dimension per (chunk, tap) -- see UmmaCfg::B_TAP.  dense is [npad][cinpad][kk] (single block).
+// N dimension per (chunk, tap) -- see UmmaCfg::B_TAP.  dense is [nblk*npad][cinpad][kk]; a chunk only
+// carries the rows of the diagonal block it feeds.
 static __global__ void pack_stages_cg2_kernel(const float* __restrict__ dense, __nv_bfloat16* __restrict__ out,
-                                              int npad, int cinpad, int kk, int concat) {
-  const int nchunk = cinpad / 16;
+                                              int npad, int cinpad, int kk, int concat, int nblk) {
+  const int nchunk = cinpad / 16, cpb = nchunk / nblk;
   const int rows = concat ? npad + npad / 2 : npad / 2;        // rows per k8 group (per hi/lo part)
   const int parts = concat ? 1 : 2;                            // non-concat: hi part then lo part
   const size_t per_rank = (size_t)nchunk * kk * parts * 2 * rows * 8;
@@ -812,7 +813,7 @@ static __global__ void pack_stages_cg2_kernel(const float* __restrict__ dense, _
       lo = part;
     }
     const int cin = chunk * 16 + k8 * 8 + e;
-    const float w = dense[((size_t)row * cinpad + cin) * kk + tap];
+    const float w = dense[((size_t)((chunk / cpb) * npad + row) * cinpad + cin) * kk + tap];
     const __nv_bfloat16 hi = __float2bfloat16_rn(w);
     out[i] = lo == 0 ? hi : __float2bfloat16_rn(w - __bfloat162float(hi));
   }

@@ -94,6 +94,12 @@ enum UmmaLayer {
 #ifndef WN_CG_L1R2
 #define WN_CG_L1R2 2
 #endif
+// Sub-tiles per CTA tile of the first layer: its 224 accumulator columns fill TMEM at S=2, so the epilogue
+// could not overlap the next tile; S=1 double-buffers them (21.7 -> 17.8 ms per batch; the refiners'
+// conv2, in the same situation, is slower that way: profiles/r1_ab_cta_pairs.log)
+#ifndef WN_L1_S
+#define WN_L1_S 1
+#endif
 struct UmmaLayerSpec {
   int ks, cinpad, npad, cout, slot, concat, nblk;  // npad = output columns per diagonal block
   int cg;                                           // CTAs per MMA: 2 = weight rows split over a CTA pair
@@ -274,7 +280,7 @@ int umma_forward_layers(wn_handle* h, const float* const in[4], const int64_t st
   // L1: 16 -> 128 (cmg) + 96 (refiners)
   act(b.a[1], 128, b.r[1], 96);
   a.skip_lo = b.exact_flag;
-  if ((rc = launch_umma<7, 16, 224, 2, 1, kEpiAct, 0, 1, WN_CG_L1R2 == 2 ? 7 : WN_L1_TPS, WN_CG_L1R2>(h, kL1, b.act0, a, stream))) return rc;
+  if ((rc = launch_umma<7, 16, 224, WN_L1_S, WN_L1_S == 1 ? 2 : 1, kEpiAct, 0, 1, WN_CG_L1R2 == 2 ? 7 : WN_L1_TPS, WN_CG_L1R2>(h, kL1, b.act0, a, stream))) return rc;
   a.skip_lo = nullptr;
   if (dump(0, b.a[1], 128) || dump(8, b.r[1], 96)) return WN_OK;
   act(b.a[2], 128, nullptr, 0);

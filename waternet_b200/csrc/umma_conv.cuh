@@ -606,8 +606,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
       mbar_wait(&t_full[acc], tphase);
       tc_fence_after();
       const int gy = ty * C::TILE_H + py;
+      // the two epilogue groups take alternate sub-tiles; a single sub-tile (S == 1) is split by channel
+      // groups instead (a warp may read any columns of its own 32 TMEM lanes)
+      static_assert(S > 1 || EPI == kEpiAct || EPI == kEpiDgrad, "S == 1 needs the channel-group split");
 #pragma unroll 1
-      for (int s = egroup; s < S; s += 2) {
+      for (int s = (S == 1 ? 0 : egroup); s < S; s += 2) {
         const int gx = tx * C::TILE_W + s * kSubW + px;
         const bool inside = gx < g.W && gy < g.H && tile_valid;
         const uint32_t t_addr = tmem_base + lane_base + (uint32_t)((acc * S + s) * C::SUB_COLS);
@@ -628,17 +631,23 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
           constexpr int GC = 32;  // channels per group
           constexpr int NG = NBLK * NPAD / GC;
           static_assert((NBLK * NPAD) % GC == 0 && (NBLK == 1 || NPAD % GC == 0), "channel groups of 32");
+          auto act_groups = [&](auto first_tag) {
+          constexpr int FIRST = decltype(first_tag)::value;
+          constexpr int STEP = S == 1 ? 2 : 1;
+          constexpr int CNT = (NG - FIRST + STEP - 1) / STEP;
           uint32_t vb[2][GC], wb[2][CONCAT ? GC : 1];
-          issue_cols(0, vb[0], wb[0], std::integral_constant<int, GC>{});
+          if constexpr (CNT > 0) issue_cols(FIRST * GC, vb[0], wb[0], std::integral_constant<int, GC>{});
 #pragma unroll
-          for (int gi = 0; gi < NG; gi++) {
+          for (int k = 0; k < CNT; k++) {
+            const int gi = FIRST + k * STEP;
             const int c0 = gi * GC;
             tmem_ld_wait();
-            if (gi + 1 < NG) issue_cols(c0 + GC, vb[(gi + 1) & 1], wb[(gi + 1) & 1], std::integral_constant<int, GC>{});
+            if (k + 1 < CNT)
+              issue_cols(c0 + STEP * GC, vb[(k + 1) & 1], wb[(k + 1) & 1], std::integral_constant<int, GC>{});
             float f[GC];
 #pragma unroll
             for (int j = 0; j < GC; j++)
-              f[j] = __uint_as_float(vb[gi & 1][j]) + (CONCAT ? __uint_as_float(wb[gi & 1][CONCAT ? j : 0]) : 0.f);
+              f[j] = __uint_as_float(vb[k & 1][j]) + (CONCAT ? __uint_as_float(wb[k & 1][CONCAT ? j : 0]) : 0.f);
             if (c0 < g.cout && inside && !(g.dbg & 64)) {
               const size_t pix = (size_t)gy * g.W + gx;
               const size_t hw = (size_t)g.H * g.W;
@@ -680,6 +689,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
                 }
               }
             }
+          }
+          };  // act_groups
+          if constexpr (S == 1) {
+            if (egroup == 0) act_groups(std::integral_constant<int, 0>{});
+            else act_groups(std::integral_constant<int, 1>{});
+          } else {
+            act_groups(std::integral_constant<int, 0>{});
           }
         } else {
           uint32_t v16[16], w16[CONCAT ? 16 : 1];

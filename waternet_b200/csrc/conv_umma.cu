@@ -100,6 +100,9 @@ enum UmmaLayer {
 #ifndef WN_L1_S
 #define WN_L1_S 1
 #endif
+#ifndef WN_R2_S
+#define WN_R2_S 2
+#endif
 struct UmmaLayerSpec {
   int ks, cinpad, npad, cout, slot, concat, nblk;  // npad = output columns per diagonal block
   int cg;                                           // CTAs per MMA: 2 = weight rows split over a CTA pair
@@ -305,7 +308,7 @@ int umma_forward_layers(wn_handle* h, const float* const in[4], const int64_t st
   if ((rc = launch_umma<3, 64, 16, 4, 2, kEpiSigmoid, 1, 1, 9>(h, kC8, b.a[7], a, stream))) return rc;
   if (dbg_layer == 7) return WN_OK;
   act(b.r[2], 96, nullptr, 0);
-  if ((rc = launch_umma<5, 96, 32, 2, 1, kEpiAct, 1, 3, WN_R2_TPS, WN_CG_L1R2>(h, kR2, b.r[1], a, stream))) return rc;
+  if ((rc = launch_umma<5, 96, 32, WN_R2_S, WN_R2_S == 1 ? 2 : 1, kEpiAct, 1, 3, WN_R2_TPS, WN_CG_L1R2>(h, kR2, b.r[1], a, stream))) return rc;
   if (dump(9, b.r[2], 96)) return WN_OK;
   a.out_f32 = out;
   a.cm = b.cm;

@@ -2,6 +2,7 @@
 
     python tools/summarize_ncu.py full  gpurun_out/prof.ncu-rep   profiles/r1_xxx_kernels.csv
     python tools/summarize_ncu.py list  gpurun_out/launches.csv   profiles/r1_xxx_launches.csv
+    python tools/summarize_ncu.py traffic profiles/r1_umma_kernels_1080p_n1.csv profiles/r1_traffic.json
 """
 import collections
 import csv
@@ -79,5 +80,27 @@ def launch_list(path, out):
     print(open(out).read())
 
 
+# the ten tensor-core launches of one forward pass, in launch order (conv_umma.cu: umma_forward_layers)
+FORWARD_LAUNCHES = ["cmg.conv1+refiner.conv1x3", "cmg.conv2", "cmg.conv3", "cmg.conv4", "cmg.conv5", "cmg.conv6",
+                    "cmg.conv7", "cmg.conv8", "refiner.conv2x3", "refiner.conv3x3+gate"]
+
+
+def traffic(kernels_csv, out):
+    """DRAM bytes per launch of each forward kernel (one 1080p image per launch) -> the JSON bench.py reads
+    for roofline.traffic.  Input: the CSV written by `full` from a capture of exactly one forward pass."""
+    import json
+    rows = list(csv.DictReader(open(kernels_csv)))
+    assert len(rows) == len(FORWARD_LAUNCHES), f"expected one forward pass ({len(FORWARD_LAUNCHES)} launches), got {len(rows)}"
+    doc = {"source": f"ncu --set full, one 1920x1080 image per launch ({kernels_csv}): "
+                     "dram__bytes_read.sum + dram__bytes_write.sum",
+           "height": 1080, "width": 1920, "kernels": {}}
+    for name, r in zip(FORWARD_LAUNCHES, rows):
+        doc["kernels"][name] = {"dram_bytes_per_image": (float(r["dram_read_GB"]) + float(r["dram_write_GB"])) * 1e9,
+                                "kernel": r["kernel"]}
+    with open(out, "w") as f:
+        json.dump(doc, f, indent=1)
+    print(json.dumps(doc, indent=1))
+
+
 if __name__ == "__main__":
-    {"full": full, "list": launch_list}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"full": full, "list": launch_list, "traffic": traffic}[sys.argv[1]](sys.argv[2], sys.argv[3])

@@ -45,7 +45,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--mode", choices=["default", "fp32", "bf16x3"], default="default")
+    ap.add_argument("--mode", choices=["default", "fp32", "bf16x3", "bf16_fp8"], default="default")
     ap.add_argument("--batch", type=int, default=16, help="images per GPU per step")
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--width", type=int, default=1920)
@@ -312,7 +312,9 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None,
-            "dtype": "f32" if mode == _lib.MODE_FP32_SIMT else "bf16x3 (3-term bf16 split operands, fp32 accumulate)",
+            "dtype": {_lib.MODE_FP32_SIMT: "f32", _lib.MODE_BF16X3: "bf16x3 (3-term bf16 split operands, fp32 accumulate)"}.get(
+                mode, "bf16 + fp8 corrections (v = hi + lo: hi x hi in bf16, both correction terms of the heavy "
+                      "layers as one e4m3 MMA; fp32 accumulate; 3-term bf16 elsewhere)"),
             "data": "synthetic",
             "config": {"workload": f"batch {B} x {W}x{H} RGB uint8 per GPU: WB/GC/HE preprocess + WaterNet forward + "
                                    "uint8 postprocess (BASELINE configs[2])",

@@ -47,7 +47,8 @@ extern "C" {
 /* Arithmetic used for the 17 convolutions of wn_forward. */
 #define WN_MODE_FP32_SIMT 0 /* fp32 FMA on CUDA cores (bit-for-bit independent of tensor cores) */
 #define WN_MODE_BF16X3 1    /* tcgen05 tensor cores, 3-term bf16 split operands, fp32 accumulate */
-#define WN_MODE_DEFAULT (-1) /* the library's fastest mode that meets the 1e-3 parity bar */
+#define WN_MODE_BF16_FP8 2  /* same, the two correction terms of the tensor-bound layers as one fp8 MMA */
+#define WN_MODE_DEFAULT (-1) /* the library's fastest mode that meets the 1e-3 parity bar: WN_MODE_BF16_FP8 */
 
 #define WN_NUM_PARAMS 34
 

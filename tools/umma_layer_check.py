@@ -7,6 +7,8 @@ from waternet_b200 import _lib
 from waternet_b200.engine import get_engine
 from waternet_b200.net import WaterNet
 
+# WN_CHECK_MODE=bf16_fp8 checks the fp8-correction scheme instead of plain bf16x3
+TENSOR_MODE = {"bf16x3": _lib.MODE_BF16X3, "bf16_fp8": _lib.MODE_BF16_FP8}[os.environ.get("WN_CHECK_MODE", "bf16x3")]
 torch.manual_seed(0)
 eng = get_engine("cuda:0")
 m = WaterNet().cuda().eval()
@@ -24,7 +26,7 @@ for shape in [(1, 32, 48), (2, 37, 53), (1, 40, 40), (1, 300, 500)]:  # odd tile
     for layer in [0, 8, 1, 2, 3, 4, 5, 6, 7, 9]:
         try:
             a = eng.debug_layer(*ins, layer=layer, mode=_lib.MODE_FP32_SIMT)
-            b = eng.debug_layer(*ins, layer=layer, mode=_lib.MODE_BF16X3)
+            b = eng.debug_layer(*ins, layer=layer, mode=TENSOR_MODE)
             torch.cuda.synchronize()
             err = (a - b).abs().max().item() / max(a.abs().max().item(), 1e-30)
             bad = ((a - b).abs() > 1e-3 * a.abs().max()).float().mean().item()
@@ -38,6 +40,6 @@ for shape in [(1, 32, 48), (2, 37, 53), (1, 40, 40), (1, 300, 500)]:  # odd tile
             print(f"  layer {layer} FAILED: {e}")
             sys.exit(1)
     out_a = eng.forward(*ins, mode=_lib.MODE_FP32_SIMT)
-    out_b = eng.forward(*ins, mode=_lib.MODE_BF16X3)
+    out_b = eng.forward(*ins, mode=TENSOR_MODE)
     torch.cuda.synchronize()
     print("  final rel err", ((out_a - out_b).abs().max() / out_a.abs().max()).item())

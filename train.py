@@ -29,7 +29,7 @@ def main():
     ap.add_argument("--weights", type=str, help="(Optional) Starting weights for training")
     ap.add_argument("--seed", type=int, default=None, help="(Optional) Seed for torch, defaults to None")
     ap.add_argument("--synthetic", action="store_true", help="Use UIEB-shaped synthetic pairs (no dataset offline)")
-    ap.add_argument("--precision", default="default", choices=["default", "fp32", "bf16x3"])
+    ap.add_argument("--precision", default="default", choices=["default", "fp32", "bf16x3", "bf16_fp8"])
     ap.add_argument("--loader", default="gpu", choices=["gpu", "torch"],
                     help="gpu: batches augmented + preprocessed on the device in one call; torch: the reference's "
                          "per-item DataLoader path")

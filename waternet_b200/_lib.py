@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_PKG_DIR, "libwaternet_b200.so")
 
 MODE_FP32_SIMT = 0
 MODE_BF16X3 = 1
+MODE_BF16_FP8 = 2
 MODE_DEFAULT = -1
 NUM_PARAMS = 34
 NUM_TIMING_SLOTS = 23

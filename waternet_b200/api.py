@@ -29,7 +29,8 @@ class Enhancer:
         self.engine: Engine = get_engine(device if device is not None else next(model.parameters()).device)
         self.model = model.to(self.engine.device)
         self.mode = model._mode() if precision is None else {
-            "default": _lib.MODE_DEFAULT, "fp32": _lib.MODE_FP32_SIMT, "bf16x3": _lib.MODE_BF16X3}[precision]
+            "default": _lib.MODE_DEFAULT, "fp32": _lib.MODE_FP32_SIMT, "bf16x3": _lib.MODE_BF16X3,
+                 "bf16_fp8": _lib.MODE_BF16_FP8}[precision]
         self._pin_in = None
         self._pin_out = None
         self._dev_in = None

@@ -17,7 +17,7 @@ void set_error(const char* fmt, ...) {
 }
 
 static int resolve_mode(int mode) {
-  if (mode == WN_MODE_DEFAULT) return WN_MODE_BF16X3;
+  if (mode == WN_MODE_DEFAULT) return WN_MODE_BF16_FP8;
   return mode;
 }
 
@@ -141,7 +141,8 @@ size_t wn_forward_workspace_bytes(int n, int h, int w, int mode) {
   if (n <= 0 || h <= 0 || w <= 0) return 0;
   switch (resolve_mode(mode)) {
     case WN_MODE_FP32_SIMT: return simt_forward_workspace_bytes(n, h, w);
-    case WN_MODE_BF16X3: return umma_forward_workspace_bytes(n, h, w);
+    case WN_MODE_BF16X3:
+    case WN_MODE_BF16_FP8: return umma_forward_workspace_bytes(n, h, w);
   }
   return 0;
 }
@@ -169,7 +170,10 @@ int wn_forward(wn_handle* h, const float* x, const float* wb, const float* he, c
                           (cudaStream_t)stream);
     case WN_MODE_BF16X3:
       return umma_forward(h, in, in_strides, out, n, height, width, workspace, workspace_bytes,
-                          (cudaStream_t)stream);
+                          (cudaStream_t)stream, 0);
+    case WN_MODE_BF16_FP8:
+      return umma_forward(h, in, in_strides, out, n, height, width, workspace, workspace_bytes,
+                          (cudaStream_t)stream, 1);
   }
   set_error("wn_forward: unknown mode %d", mode);
   return WN_E_INVALID;
@@ -328,7 +332,7 @@ int wn_debug_forward_layer(wn_handle* h, const float* x, const float* wb, const 
     return simt_debug_layer(h, in, in_strides, n, height, width, layer, dst, workspace, workspace_bytes,
                             (cudaStream_t)stream);
   return umma_debug_layer(h, in, in_strides, n, height, width, layer, dst, workspace, workspace_bytes,
-                          (cudaStream_t)stream);
+                          (cudaStream_t)stream, resolve_mode(mode) == WN_MODE_BF16_FP8 ? 1 : 0);
 }
 
 int wn_enable_timing(wn_handle* h, int on) {

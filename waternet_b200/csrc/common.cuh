@@ -148,16 +148,16 @@ struct FwdBuffers {
 };
 int umma_forward_layers(wn_handle* h, const float* const in[4], const int64_t st[4][4], float* out, int n,
                         int height, int width, const FwdBuffers& b, cudaStream_t stream, int dbg_layer = -1,
-                        float* dbg_dst = nullptr);
+                        float* dbg_dst = nullptr, int scheme = 0);  // scheme 1 = fp8 correction passes
 int umma_debug_layer(wn_handle* h, const float* const in[4], const int64_t in_strides[4][4], int n,
                      int height, int width, int layer, float* dst, void* workspace,
-                     size_t workspace_bytes, cudaStream_t stream);
+                     size_t workspace_bytes, cudaStream_t stream, int scheme = 0);
 int umma_pack_weights(wn_handle* h, const float* const* params, cudaStream_t stream);
 void umma_free(wn_handle* h);
 size_t umma_forward_workspace_bytes(int n, int h, int w);
 int umma_forward(wn_handle* h, const float* const in[4], const int64_t in_strides[4][4], float* out,
                  int n, int height, int width, void* workspace, size_t workspace_bytes,
-                 cudaStream_t stream);
+                 cudaStream_t stream, int scheme = 0);
 
 // conv_bwd.cu
 int bwd_pack_weights(wn_handle* h, const float* const* params, cudaStream_t stream);

@@ -103,6 +103,11 @@ enum UmmaLayer {
 #ifndef WN_R2_S
 #define WN_R2_S 2
 #endif
+// fp8-correction scheme: sub-tiles per CTA tile of conv2/conv3 (two accumulator halves of 128 columns each:
+// S=1 double-buffers them, S=2 fills TMEM)
+#ifndef WN_F8_C23_S
+#define WN_F8_C23_S 1
+#endif
 struct UmmaLayerSpec {
   int ks, cinpad, npad, cout, slot, concat, nblk;  // npad = output columns per diagonal block
   int cg;                                           // CTAs per MMA: 2 = weight rows split over a CTA pair
@@ -119,7 +124,14 @@ static const UmmaLayerSpec kSpecs[kNumUmmaLayers] = {
     {5, 96, 32, 96, 9, 1, 3, WN_CG_L1R2},
     {3, 96, 16, 9, 10, 1, 1, 1}};
 
+// layers that have an fp8-correction form (UmmaCfg FMT bit 0): the tensor-bound CTA-pair layers
+static bool has_f8_form(int li) { return li == kC2 || li == kC3 || li == kC5 || li == kC6 || li == kC7 || li == kR2; }
+static size_t stage8_bytes_total(const UmmaLayerSpec& s) {
+  return (size_t)2 * (s.cinpad / 16) * s.ks * s.ks * (s.npad / 2) * 64;  // two per-rank images
+}
 struct UmmaWeights {
+  uint8_t* stages8[kNumUmmaLayers];  // fp8-correction weight images (has_f8_form layers)
+  float* scale8[kNumUmmaLayers];     // {ws, 2^-9 / ws}
   uint8_t* stages[kNumUmmaLayers];
   float* bias[kNumUmmaLayers];
   float* dense;  // scratch for packing
@@ -136,6 +148,10 @@ int umma_pack_weights(wn_handle* h, const float* const* params, cudaStream_t str
   for (int i = 0; i < kNumUmmaLayers; i++) {  // (re)allocate whatever an earlier, failed call left unallocated
     if (!h->umma->stages[i]) WN_CUDA(cudaMalloc(&h->umma->stages[i], stage_bytes_total(kSpecs[i])));
     if (!h->umma->bias[i]) WN_CUDA(cudaMalloc(&h->umma->bias[i], kSpecs[i].npad * kSpecs[i].nblk * sizeof(float)));
+    if (has_f8_form(i)) {
+      if (!h->umma->stages8[i]) WN_CUDA(cudaMalloc(&h->umma->stages8[i], stage8_bytes_total(kSpecs[i])));
+      if (!h->umma->scale8[i]) WN_CUDA(cudaMalloc(&h->umma->scale8[i], 2 * sizeof(float)));
+    }
   }
   if (!h->umma->dense) WN_CUDA(cudaMalloc(&h->umma->dense, (size_t)224 * 128 * 49 * sizeof(float)));
   UmmaWeights* u = h->umma;
@@ -178,6 +194,13 @@ int umma_pack_weights(wn_handle* h, const float* const* params, cudaStream_t str
       pack_stages_kernel<<<256, 256, 0, stream>>>(u->dense, (__nv_bfloat16*)u->stages[li], s.npad, s.cinpad, kk,
                                                   s.concat, s.nblk);
     WN_LAUNCH_CHECK(h);
+    if (has_f8_form(li)) {
+      f8_scale_kernel<<<1, 256, 0, stream>>>(u->dense, (size_t)rows * s.cinpad * kk, u->scale8[li]);
+      WN_LAUNCH_CHECK(h);
+      pack_stages_f8_cg2_kernel<<<256, 256, 0, stream>>>(u->dense, u->stages8[li], u->scale8[li], s.npad, s.cinpad, kk,
+                                                         s.nblk);
+      WN_LAUNCH_CHECK(h);
+    }
   }
   return WN_OK;
 }
@@ -187,6 +210,8 @@ void umma_free(wn_handle* h) {
   for (int i = 0; i < kNumUmmaLayers; i++) {
     if (h->umma->stages[i]) cudaFree(h->umma->stages[i]);
     if (h->umma->bias[i]) cudaFree(h->umma->bias[i]);
+    if (h->umma->stages8[i]) cudaFree(h->umma->stages8[i]);
+    if (h->umma->scale8[i]) cudaFree(h->umma->scale8[i]);
   }
   if (h->umma->dense) cudaFree(h->umma->dense);
   free(h->umma);
@@ -221,24 +246,50 @@ size_t umma_forward_workspace_bytes(int n, int h, int w) {
 #define WN_R2_TPS 5
 #endif
 
-template <int KS, int CIN_PAD, int NPAD, int S, int AS, int EPI, int CONCAT = 0, int NBLK = 1, int TPS = 1, int CG = 1>
+template <int KS, int CIN_PAD, int NPAD, int S, int AS, int EPI, int CONCAT = 0, int NBLK = 1, int TPS = 1, int CG = 1,
+          int FMT = 0>
 static int launch_umma(wn_handle* h, int li, void* in_base, ConvArgs a, cudaStream_t stream) {
   const UmmaLayerSpec& spec = kSpecs[li];
+  if constexpr ((FMT & kFmtIn8) != 0) {  // fp8-correction form: its own weight images, [hi | fp8] layout, CTA pairs
+    if (spec.ks != KS || spec.cinpad != CIN_PAD || spec.npad != NPAD || spec.nblk != NBLK || !has_f8_form(li)) {
+      set_error("internal: fp8 launch configuration of layer %d does not match its packed weights", li);
+      return WN_E_STATE;
+    }
+    a.f8_scale = h->umma->scale8[li] + 1;
+    return launch_conv<KS, CIN_PAD, NPAD, S, AS, EPI, 0, NBLK, TPS, 2, FMT>(h, spec.slot, h->umma->stages8[li],
+                                                                           h->umma->bias[li], in_base, a, stream);
+  }
   if (spec.ks != KS || spec.cinpad != CIN_PAD || spec.npad != NPAD || spec.concat != CONCAT || spec.nblk != NBLK ||
       spec.cg != CG) {
     set_error("internal: launch configuration of layer %d does not match its packed weights", li);
     return WN_E_STATE;
   }
-  return launch_conv<KS, CIN_PAD, NPAD, S, AS, EPI, CONCAT, NBLK, TPS, CG>(h, spec.slot, h->umma->stages[li],
+  return launch_conv<KS, CIN_PAD, NPAD, S, AS, EPI, CONCAT, NBLK, TPS, CG, FMT>(h, spec.slot, h->umma->stages[li],
                                                                        h->umma->bias[li], in_base, a, stream);
 }
 
 // bf16 hi/lo planes -> fp32 NCHW (test aid)
-__global__ void decode_planes_kernel(const uint4* __restrict__ src, float* __restrict__ dst, int planes_half, int hw) {
+__global__ void decode_planes_kernel(const uint4* __restrict__ src, float* __restrict__ dst, int planes_half, int hw,
+                                     int f8) {
   const int n = blockIdx.z, plane = blockIdx.y;
   const int pix = blockIdx.x * blockDim.x + threadIdx.x;
   if (pix >= hw) return;
   const uint4 h4 = src[((size_t)n * 2 * planes_half + plane) * hw + pix];
+  if (f8) {  // hi planes + per 16 channels {e4m3((v - hi) * 2^9), e4m3(v)}: v ~ hi + lo8 / 512
+    const uint4 l4 = src[((size_t)n * 2 * planes_half + planes_half + 2 * (plane >> 1)) * hw + pix];
+    const uint32_t hs[4] = {h4.x, h4.y, h4.z, h4.w}, ls[4] = {l4.x, l4.y, l4.z, l4.w};
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const float hi = __uint_as_float(((hs[j >> 1] >> ((j & 1) * 16)) & 0xffffu) << 16);
+      const int byte = (plane & 1) * 8 + j;
+      const uint32_t b8 = (ls[byte >> 2] >> ((byte & 3) * 8)) & 0xffu;  // e4m3: sign, 4 exponent bits (bias 7), 3 mantissa
+      const int e = (int)((b8 >> 3) & 15), m = (int)(b8 & 7);
+      const float mag = e == 0 ? ldexpf((float)m, -9) : ldexpf((float)(8 + m), e - 10);
+      const float lo = ((b8 & 0x80u) ? -mag : mag) * (1.f / 512.f);
+      dst[((size_t)n * planes_half * 8 + plane * 8 + j) * hw + pix] = hi + lo;
+    }
+    return;
+  }
   const uint4 l4 = src[((size_t)n * 2 * planes_half + planes_half + plane) * hw + pix];
   const uint32_t hs[4] = {h4.x, h4.y, h4.z, h4.w}, ls[4] = {l4.x, l4.y, l4.z, l4.w};
 #pragma unroll
@@ -252,7 +303,7 @@ __global__ void decode_planes_kernel(const uint4* __restrict__ src, float* __res
 // Where every layer's output lives.  Inference ping-pongs two buffers per stack; the training
 // forward (conv_bwd.cu) gives every activation its own buffer because the backward pass needs them.
 int umma_forward_layers(wn_handle* h, const float* const in[4], const int64_t st[4][4], float* out, int n, int H,
-                        int W, const FwdBuffers& b, cudaStream_t stream, int dbg_layer, float* dbg_dst) {
+                        int W, const FwdBuffers& b, cudaStream_t stream, int dbg_layer, float* dbg_dst, int scheme) {
   PackInArgs pa;
   for (int t = 0; t < 4; t++) {
     pa.p[t] = in[t];
@@ -268,10 +319,10 @@ int umma_forward_layers(wn_handle* h, const float* const in[4], const int64_t st
   memset(&a, 0, sizeof(a));
   a.N = n; a.H = H; a.W = W;
   int rc;
-  auto dump = [&](int layer, const uint4* buf, int channels) -> bool {
+  auto dump = [&](int layer, const uint4* buf, int channels, int f8 = 0) -> bool {
     if (dbg_layer != layer) return false;
     decode_planes_kernel<<<dim3((H * W + 255) / 256, channels / 8, n), 256, 0, stream>>>(buf, dbg_dst, channels / 8,
-                                                                                     H * W);
+                                                                                     H * W, f8);
     h->launches++;
     return true;
   };
@@ -280,6 +331,45 @@ int umma_forward_layers(wn_handle* h, const float* const in[4], const int64_t st
     a.dst1.base = d1; a.dst1.planes_half = c1 / 8;
     a.split_c = c0; a.cout = c0 + c1;
   };
+  if (scheme == 1) {
+    // fp8-correction scheme (inference): the tensor-bound layers replace the two bf16 correction passes by one
+    // fp8 MMA (UmmaCfg FMT); a layer whose consumer is such a layer writes the hi + fp8-planes format
+    constexpr int IN8 = kFmtIn8, OUT8 = kFmtOut8;
+    act(b.a[1], 128, b.r[1], 96);
+    a.skip_lo = b.exact_flag;
+    if ((rc = launch_umma<7, 16, 224, 1, 2, kEpiAct, 0, 1, 7, 2, OUT8>(h, kL1, b.act0, a, stream))) return rc;
+    a.skip_lo = nullptr;
+    if (dump(0, b.a[1], 128, 1) || dump(8, b.r[1], 96, 1)) return WN_OK;
+    act(b.a[2], 128, nullptr, 0);
+    if ((rc = launch_umma<5, 128, 128, WN_F8_C23_S, WN_F8_C23_S == 1 ? 2 : 1, kEpiAct, 0, 1, 5, 2, IN8 | OUT8>(h, kC2, b.a[1], a, stream))) return rc;
+    if (dump(1, b.a[2], 128, 1)) return WN_OK;
+    act(b.a[3], 128, nullptr, 0);
+    if ((rc = launch_umma<3, 128, 128, WN_F8_C23_S, WN_F8_C23_S == 1 ? 2 : 1, kEpiAct, 0, 1, 9, 2, IN8>(h, kC3, b.a[2], a, stream))) return rc;
+    if (dump(2, b.a[3], 128)) return WN_OK;
+    act(b.a[4], 64, nullptr, 0);
+    if ((rc = launch_umma<1, 128, 64, 2, 2, kEpiAct, 1, 1, 1, 1, OUT8>(h, kC4, b.a[3], a, stream))) return rc;
+    if (dump(3, b.a[4], 64, 1)) return WN_OK;
+    act(b.a[5], 64, nullptr, 0);
+    if ((rc = launch_umma<7, 64, 64, 2, 2, kEpiAct, 0, 1, 7, 2, IN8 | OUT8>(h, kC5, b.a[4], a, stream))) return rc;
+    if (dump(4, b.a[5], 64, 1)) return WN_OK;
+    act(b.a[6], 64, nullptr, 0);
+    if ((rc = launch_umma<5, 64, 64, 2, 2, kEpiAct, 0, 1, 5, 2, IN8 | OUT8>(h, kC6, b.a[5], a, stream))) return rc;
+    if (dump(5, b.a[6], 64, 1)) return WN_OK;
+    act(b.a[7], 64, nullptr, 0);
+    if ((rc = launch_umma<3, 64, 64, 2, 2, kEpiAct, 0, 1, 9, 2, IN8>(h, kC7, b.a[6], a, stream))) return rc;
+    if (dump(6, b.a[7], 64)) return WN_OK;
+    a.out_f32 = dbg_layer == 7 ? dbg_dst : b.cm;
+    if ((rc = launch_umma<3, 64, 16, 4, 2, kEpiSigmoid, 1, 1, 9>(h, kC8, b.a[7], a, stream))) return rc;
+    if (dbg_layer == 7) return WN_OK;
+    act(b.r[2], 96, nullptr, 0);
+    if ((rc = launch_umma<5, 96, 32, 2, 1, kEpiAct, 0, 3, 5, 2, IN8>(h, kR2, b.r[1], a, stream))) return rc;
+    if (dump(9, b.r[2], 96)) return WN_OK;
+    a.out_f32 = out;
+    a.cm = b.cm;
+    a.refined_out = b.refined;
+    if ((rc = launch_umma<3, 96, 16, 4, 2, kEpiGate, 1, 1, 9>(h, kR3, b.r[2], a, stream))) return rc;
+    return WN_OK;
+  }
   // L1: 16 -> 128 (cmg) + 96 (refiners)
   act(b.a[1], 128, b.r[1], 96);
   a.skip_lo = b.exact_flag;
@@ -318,7 +408,7 @@ int umma_forward_layers(wn_handle* h, const float* const in[4], const int64_t st
 }
 
 static int umma_forward_chunk(wn_handle* h, const float* const in[4], const int64_t st[4][4], float* out, int n,
-                              int H, int W, void* workspace, cudaStream_t stream, int dbg_layer = -1,
+                              int H, int W, void* workspace, cudaStream_t stream, int scheme, int dbg_layer = -1,
                               float* dbg_dst = nullptr) {
   const size_t px = (size_t)n * H * W;
   uint8_t* ws = (uint8_t*)(((uintptr_t)workspace + 1023) / 1024 * 1024);
@@ -336,22 +426,22 @@ static int umma_forward_chunk(wn_handle* h, const float* const in[4], const int6
   for (int l = 1; l <= 7; l++) b.a[l] = cmgAB[(l - 1) & 1];
   b.r[1] = refAB[0];
   b.r[2] = refAB[1];
-  return umma_forward_layers(h, in, st, out, n, H, W, b, stream, dbg_layer, dbg_dst);
+  return umma_forward_layers(h, in, st, out, n, H, W, b, stream, dbg_layer, dbg_dst, scheme);
 }
 
 int umma_debug_layer(wn_handle* h, const float* const in[4], const int64_t in_strides[4][4], int n, int H, int W,
-                     int layer, float* dst, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+                     int layer, float* dst, void* workspace, size_t workspace_bytes, cudaStream_t stream, int scheme) {
   if (!h->umma || umma_chunk(n, H, W) != n || workspace_bytes < umma_forward_workspace_bytes(n, H, W)) {
     set_error("debug layer dump: weights not packed, batch too large for one pass or workspace too small");
     return WN_E_WORKSPACE;
   }
   int rc = get_encoder();
   if (rc) return rc;
-  return umma_forward_chunk(h, in, in_strides, nullptr, n, H, W, workspace, stream, layer, dst);
+  return umma_forward_chunk(h, in, in_strides, nullptr, n, H, W, workspace, stream, scheme, layer, dst);
 }
 
 int umma_forward(wn_handle* h, const float* const in[4], const int64_t in_strides[4][4], float* out, int n, int H,
-                 int W, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+                 int W, void* workspace, size_t workspace_bytes, cudaStream_t stream, int scheme) {
   if (!h->umma) {
     set_error("tensor-core weights have not been packed");
     return WN_E_STATE;
@@ -367,7 +457,7 @@ int umma_forward(wn_handle* h, const float* const in[4], const int64_t in_stride
     const int cur = n - n0 < nb ? n - n0 : nb;
     const float* sub[4];
     for (int t = 0; t < 4; t++) sub[t] = in[t] + (long long)n0 * in_strides[t][0];
-    rc = umma_forward_chunk(h, sub, in_strides, out + (size_t)n0 * 3 * H * W, cur, H, W, workspace, stream);
+    rc = umma_forward_chunk(h, sub, in_strides, out + (size_t)n0 * 3 * H * W, cur, H, W, workspace, stream, scheme);
     if (rc) return rc;
   }
   return WN_OK;

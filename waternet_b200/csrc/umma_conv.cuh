@@ -153,6 +153,49 @@ __device__ __forceinline__ void umma_issue(uint32_t d_tmem, uint32_t a_lo, uint3
   if constexpr (CG == 2) umma2_bf16_split(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, accumulate);
   else umma_bf16_split(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, accumulate);
 }
+// kind::f8f6f4 (K = 32 fp8 values per instruction): the fp8 correction pass.  Same descriptors as the bf16
+// form -- a core-matrix row is 16 bytes either way (8 bf16 or 16 fp8 values).
+template <int CG>
+__device__ __forceinline__ void umma_issue_f8(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                              uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  if constexpr (CG == 2)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// instruction descriptor of the fp8 pass: A = B = e4m3 (format 0), D = f32.  (e5m2 activations -- format 1,
+// range-safe like fp16 -- were measured too: twice the error, 4.4-7.2e-4 at the network output with the stress
+// weights; with e4m3 an activation above 448 merely saturates its *correction* term, i.e. degrades that
+// element to single-pass bf16 accuracy, and one below 2^-9 loses a correction of < 4e-6 absolute.)
+__host__ __device__ constexpr uint32_t make_idesc_f8(int M, int N) {
+  return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// four floats -> four e4m3 bytes, f0 at the lowest address
+__device__ __forceinline__ uint32_t pack_e4m3x4(float f0, float f1, float f2, float f3) {
+  uint16_t lo, hi;
+  asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(lo) : "f"(f1), "f"(f0));
+  asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(hi) : "f"(f3), "f"(f2));
+  return (uint32_t)lo | ((uint32_t)hi << 16);
+}
+__device__ __forceinline__ uint16_t pack_e4m3x2(float f0, float f1) {
+  uint16_t v;
+  asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(v) : "f"(f1), "f"(f0));
+  return v;
+}
 template <int CG>
 __device__ __forceinline__ void umma_done(uint64_t* bar) {
   if constexpr (CG == 2) umma2_commit(bar);
@@ -212,8 +255,18 @@ constexpr int kWarpA = 8, kWarpB = 9, kWarpTmem = 10, kWarpMma = 11;
 //        issues M=256 MMAs over both CTAs' halo tiles, and each CTA stages only HALF of the weight rows
 //        (the N dimension is split over the pair) -- the shared-memory operand traffic per MMA, which
 //        bounds N<=128 layers (tools/umma_rate_probe.cu), drops from 128+N to 128+N/2 rows.
-template <int KS, int CIN_PAD, int NPAD, int S, int AS, int CONCAT = 0, int NBLK = 1, int TPS = 1, int CG = 1>
+// FMT    bit 0 (kFmtIn8): fp8 correction scheme on the input side.  v = hi (bf16) + lo; instead of the two
+//        bf16 correction passes (a_lo x w_hi, a_hi x w_lo) ONE kind::f8f6f4 MMA of K = 32 multiplies
+//        [e4m3(lo * 2^9) | e4m3(v)] (the two fp8 planes the producing layer wrote where the bf16 lo planes
+//        used to be) by [e4m3(w * ws) ; e4m3(w_lo * ws * 2^9)] into a second accumulator that the epilogue
+//        scales by 2^-9 / ws: 2 pass-equivalents instead of 3 at half the operand bytes.
+//        bit 1 (kFmtOut8): the epilogue writes that hi + fp8-planes format (its consumer has bit 0 set).
+constexpr int kFmtIn8 = 1, kFmtOut8 = 2;
+template <int KS, int CIN_PAD, int NPAD, int S, int AS, int CONCAT = 0, int NBLK = 1, int TPS = 1, int CG = 1,
+          int FMT = 0>
 struct UmmaCfg {
+  static constexpr bool F8IN = (FMT & kFmtIn8) != 0;
+  static constexpr bool DUAL = CONCAT || F8IN;  // two accumulator halves per block
   static constexpr int TILE_W = kSubW * S, TILE_H = kSubH;
   static constexpr int HALO_W = TILE_W + KS - 1, HALO_H = TILE_H + KS - 1;
   static constexpr int NCHUNK = CIN_PAD / 16;
@@ -245,9 +298,10 @@ struct UmmaCfg {
   static constexpr int NA = NA_FIT > NA_TARGET ? NA_TARGET : NA_FIT;
   static_assert(!WRAP || (CIN_PAD == 16 && TPS < KS * KS), "wrapping tap groups need a single-chunk layer");
   static_assert(CG == 1 || (CG == 2 && !WRAP && NPAD % 32 == 0), "CTA pairs: no wrapping tap groups");
+  static_assert(!F8IN || (CG == 2 && !CONCAT), "fp8 corrections: CTA-pair layers with the [hi | second part] layout");
   static constexpr int CPB = NCHUNK / NBLK;                // chunks per diagonal block
   static constexpr int N1 = CONCAT ? 2 * NPAD : NPAD;      // UMMA N of the a_hi pass
-  static constexpr int BLK_COLS = N1;                      // accumulator columns per block
+  static constexpr int BLK_COLS = DUAL ? 2 * NPAD : NPAD;   // accumulator columns per block
   static constexpr int SUB_COLS = NBLK * BLK_COLS;         // accumulator columns per sub-tile
   static constexpr int TMEM_COLS_USED = AS * S * SUB_COLS;
   static_assert(NCHUNK % NBLK == 0, "chunks must split evenly over the diagonal blocks");
@@ -286,6 +340,8 @@ struct ConvArgs {
   // kEpiDgrad: saved forward activation (planes) whose zeros gate the gradient
   const uint4* mask_base;
   int mask_planes_half;
+  // fp8 correction scheme (FMT bit 0): dequantisation factor 2^-9 / ws of the second accumulator
+  const float* f8_scale;
   // bring-up only (wn_debug_set_flags): bit 0 = epilogue skips its global stores (bit 6: also its arithmetic; bit 7: shared-memory stores instead), bit 1 = weight stages
   // are not re-fetched after the first ring fill, bit 2 = the a_lo / a_hi x w_lo passes are not issued,
   // bit 3 = no early probe of the next weight barrier.
@@ -306,10 +362,12 @@ __device__ __forceinline__ void split_bf16x2(float f0, float f1, uint32_t& hi, u
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
-template <int KS, int CIN_PAD, int NPAD, int S, int AS, int EPI, int CONCAT, int NBLK, int TPS, int CG = 1>
+template <int KS, int CIN_PAD, int NPAD, int S, int AS, int EPI, int CONCAT, int NBLK, int TPS, int CG = 1, int FMT = 0>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) {
-  using C = UmmaCfg<KS, CIN_PAD, NPAD, S, AS, CONCAT, NBLK, TPS, CG>;
+  using C = UmmaCfg<KS, CIN_PAD, NPAD, S, AS, CONCAT, NBLK, TPS, CG, FMT>;
+  constexpr bool F8IN = C::F8IN, DUAL = C::DUAL, OUT8 = (FMT & kFmtOut8) != 0;
+  static_assert(!OUT8 || EPI == kEpiAct, "fp8 planes are written by the activation epilogue only");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* a_stages = smem;
@@ -447,6 +505,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
     {
       constexpr uint32_t idesc1 = make_idesc(128 * CG, C::N1);  // a_hi pass
       constexpr uint32_t idesc2 = make_idesc(128 * CG, NPAD);   // a_lo x w_hi (and a_hi x w_lo without CONCAT)
+      constexpr uint32_t idesc8 = make_idesc_f8(128 * CG, NPAD);  // fp8 correction pass
       // descriptor halves: hi = SBO | version, lo = start address | LBO
       constexpr uint32_t a_hi32 = ((uint32_t)(C::HALO_W * 16) >> 4) | (1u << 14);
       constexpr uint32_t b_hi32 = (128u >> 4) | (1u << 14);
@@ -561,13 +620,18 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
                 for (int s = 0; s < S; s++)  // a_hi x w_hi (CONCAT: x [w_hi | w_lo])
                   umma_issue<CG>(d_base + (uint32_t)(s * C::SUB_COLS), a_tap + (uint32_t)(s * kSubW), a_hi32, b_lo32,
                                  b_hi32, idesc1, first);
-                if (!skip_lo) {
+                if constexpr (F8IN) {
+#pragma unroll
+                  for (int s = 0; s < S; s++)  // [e4m3(lo*2^9) | e4m3(v)] x [e4m3(w*ws) ; e4m3(w_lo*ws*2^9)], K = 32
+                    umma_issue_f8<CG>(d_base + (uint32_t)(s * C::SUB_COLS + NPAD), a_tap + (uint32_t)(s * kSubW) + a_lo_off,
+                                      a_hi32, b_lo32 + b_wlo_off, b_hi32, idesc8, first);
+                } else if (!skip_lo) {
 #pragma unroll
                   for (int s = 0; s < S; s++)  // a_lo x w_hi
                     umma_issue<CG>(d_base + (uint32_t)(s * C::SUB_COLS), a_tap + (uint32_t)(s * kSubW) + a_lo_off,
                                    a_hi32, b_lo32 + b_lopass_off, b_hi32, idesc2, 1u);
                 }
-                if (!CONCAT && !(g.dbg & 4)) {
+                if (!CONCAT && !F8IN && !(g.dbg & 4)) {
 #pragma unroll
                   for (int s = 0; s < S; s++)  // a_hi x w_lo
                     umma_issue<CG>(d_base + (uint32_t)(s * C::SUB_COLS), a_tap + (uint32_t)(s * kSubW), a_hi32,
@@ -597,6 +661,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
     const int row = quarter * 32 + lane;      // TMEM lane == pixel row of the sub-tile
     const int px = row & 7, py = row >> 3;
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    const float dscale = F8IN ? *g.f8_scale : 1.f;
     for (int pt = cid; pt < num_ptiles; pt += ncl) {
       const bool tile_valid = pt * CG + (int)rank < num_tiles;  // the odd tail's repeat is not stored
       const int tile = min(pt * CG + (int)rank, num_tiles - 1);
@@ -622,7 +687,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
           const uint32_t col = (uint32_t)(blk * C::BLK_COLS + (NBLK > 1 ? ch0 % NPAD : ch0));
 #pragma unroll
           for (int q = 0; q < NC; q += 16) tmem_ld16(t_addr + col + q, v + q);
-          if constexpr (CONCAT) {
+          if constexpr (DUAL) {
 #pragma unroll
             for (int q = 0; q < NC; q += 16) tmem_ld16(t_addr + col + NPAD + q, w + q);
           }
@@ -635,7 +700,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
           constexpr int FIRST = decltype(first_tag)::value;
           constexpr int STEP = S == 1 ? 2 : 1;
           constexpr int CNT = (NG - FIRST + STEP - 1) / STEP;
-          uint32_t vb[2][GC], wb[2][CONCAT ? GC : 1];
+          uint32_t vb[2][GC], wb[2][DUAL ? GC : 1];
           if constexpr (CNT > 0) issue_cols(FIRST * GC, vb[0], wb[0], std::integral_constant<int, GC>{});
 #pragma unroll
           for (int k = 0; k < CNT; k++) {
@@ -647,10 +712,47 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
             float f[GC];
 #pragma unroll
             for (int j = 0; j < GC; j++)
-              f[j] = __uint_as_float(vb[k & 1][j]) + (CONCAT ? __uint_as_float(wb[k & 1][CONCAT ? j : 0]) : 0.f);
+              f[j] = F8IN ? fmaf(__uint_as_float(wb[k & 1][DUAL ? j : 0]), dscale, __uint_as_float(vb[k & 1][j]))
+                          : __uint_as_float(vb[k & 1][j]) + (DUAL ? __uint_as_float(wb[k & 1][DUAL ? j : 0]) : 0.f);
             if (c0 < g.cout && inside && !(g.dbg & 64)) {
               const size_t pix = (size_t)gy * g.W + gx;
               const size_t hw = (size_t)g.H * g.W;
+              if constexpr (OUT8) {
+                // hi planes as usual; where the bf16 lo planes would be: per 16 channels one plane of
+                // e4m3((v - hi) * 2^9) and one of e4m3(v) -- the K = 32 operand of the consumer's fp8 pass
+#pragma unroll
+                for (int q = 0; q < GC; q += 16) {
+                  const int ch = c0 + q;
+                  uint32_t hi[8], l8[4], h8[4];
+#pragma unroll
+                  for (int j = 0; j < 16; j += 4) {
+                    float v[4], r[4];
+#pragma unroll
+                    for (int t = 0; t < 4; t++) v[t] = fmaxf(f[q + j + t] + s_bias[ch + j + t], 0.f);
+#pragma unroll
+                    for (int t = 0; t < 4; t += 2) {
+                      const __nv_bfloat162 h = __floats2bfloat162_rn(v[t], v[t + 1]);
+                      const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h);
+                      hi[(j + t) >> 1] = hb;
+                      r[t] = (v[t] - __uint_as_float(hb << 16)) * 512.f;
+                      r[t + 1] = (v[t + 1] - __uint_as_float(hb & 0xffff0000u)) * 512.f;
+                    }
+                    l8[j >> 2] = pack_e4m3x4(r[0], r[1], r[2], r[3]);
+                    h8[j >> 2] = pack_e4m3x4(v[0], v[1], v[2], v[3]);
+                  }
+                  const bool second = ch >= g.split_c;
+                  const ActDst& d = second ? g.dst1 : g.dst0;
+                  const int chl = second ? ch - g.split_c : ch;
+                  uint4* p_hi = d.base + ((size_t)n * 2 * d.planes_half + (chl >> 3)) * hw + pix;
+                  uint4* p_f8 = d.base + ((size_t)n * 2 * d.planes_half + d.planes_half + 2 * (chl >> 4)) * hw + pix;
+                  if (!(g.dbg & 1) || hi[0] == 0x7fc07fc0u) {
+                    p_hi[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                    p_hi[hw] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+                    p_f8[0] = make_uint4(l8[0], l8[1], l8[2], l8[3]);
+                    p_f8[hw] = make_uint4(h8[0], h8[1], h8[2], h8[3]);
+                  }
+                }
+              } else {
 #pragma unroll
               for (int q = 0; q < GC; q += 8) {  // one 8-channel plane at a time
                 const int ch = c0 + q;
@@ -688,6 +790,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
                   p_hi[(size_t)d.planes_half * hw] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                 }
               }
+              }
             }
           }
           };  // act_groups
@@ -698,12 +801,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
             act_groups(std::integral_constant<int, 0>{});
           }
         } else {
-          uint32_t v16[16], w16[CONCAT ? 16 : 1];
+          uint32_t v16[16], w16[DUAL ? 16 : 1];
           issue_cols(0, v16, w16, std::integral_constant<int, 16>{});
           tmem_ld_wait();
           float f[16];
 #pragma unroll
-          for (int j = 0; j < 16; j++) f[j] = __uint_as_float(v16[j]) + (CONCAT ? __uint_as_float(w16[CONCAT ? j : 0]) : 0.f);
+          for (int j = 0; j < 16; j++)
+            f[j] = F8IN ? fmaf(__uint_as_float(w16[DUAL ? j : 0]), dscale, __uint_as_float(v16[j]))
+                        : __uint_as_float(v16[j]) + (DUAL ? __uint_as_float(w16[DUAL ? j : 0]) : 0.f);
           if (inside) {
             const size_t hw = (size_t)g.H * g.W;
             const size_t o = (size_t)n * 3 * hw + (size_t)gy * g.W + gx;
@@ -835,6 +940,67 @@ static __global__ void pack_stages_cg2_kernel(const float* __restrict__ dense, _
   }
 }
 
+// fp8 correction scheme (UmmaCfg FMT bit 0), CTA pairs: per rank, per (chunk, tap):
+//   part 0  [k8 0|1][rows][8 bf16]            w_hi                         (K = 16 bf16 MMA)
+//   part 1  [k16 0|1][rows][16 fp8 (e4m3)]    w * ws  |  w_lo * ws * 2^9   (K = 32 fp8 MMA)
+// with rows = npad/2 of this rank.  scale[0] = ws (a power of two placing max|w| in [112, 224]),
+// scale[1] = 2^-9 / ws (what the epilogue multiplies the second accumulator with).
+static __global__ void f8_scale_kernel(const float* __restrict__ dense, size_t n, float* __restrict__ scale) {
+  __shared__ float smax[256];
+  float m = 0.f;
+  for (size_t i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, fabsf(dense[i]));
+  smax[threadIdx.x] = m;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) smax[threadIdx.x] = fmaxf(smax[threadIdx.x], smax[threadIdx.x + o]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const float mx = fmaxf(smax[0], 1e-30f);
+    const float ws = exp2f(floorf(log2f(224.f / mx)));
+    scale[0] = ws;
+    scale[1] = 1.f / (512.f * ws);
+  }
+}
+static __global__ void pack_stages_f8_cg2_kernel(const float* __restrict__ dense, uint8_t* __restrict__ out,
+                                                 const float* __restrict__ scale, int npad, int cinpad, int kk,
+                                                 int nblk) {
+  const int nchunk = cinpad / 16, cpb = nchunk / nblk, rows = npad / 2;
+  const size_t tap_bytes = (size_t)rows * 64;
+  const size_t per_rank = (size_t)nchunk * kk * tap_bytes;
+  const float ws = scale[0];
+  // one thread per (rank, chunk, tap, row, channel pair of the chunk)
+  const size_t total = (size_t)2 * nchunk * kk * rows * 8;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    size_t r = i;
+    const int cp = (int)(r % 8); r /= 8;            // channels 2cp, 2cp+1 of the chunk
+    const int row = (int)(r % rows); r /= rows;
+    const int tap = (int)(r % kk); r /= kk;
+    const int chunk = (int)(r % nchunk);
+    const int rank = (int)(r / nchunk);
+    const int wrow = (chunk / cpb) * npad + rank * rows + row;
+    float w[2], wl[2];
+    uint16_t hb[2];
+#pragma unroll
+    for (int t = 0; t < 2; t++) {
+      w[t] = dense[((size_t)wrow * cinpad + chunk * 16 + 2 * cp + t) * kk + tap];
+      const __nv_bfloat16 h = __float2bfloat16_rn(w[t]);
+      hb[t] = __bfloat16_as_ushort(h);
+      wl[t] = w[t] - __bfloat162float(h);
+    }
+    uint8_t* base = out + (size_t)rank * per_rank + ((size_t)chunk * kk + tap) * tap_bytes;
+    // part 0: channel c = 2cp+t -> k8 = c / 8, element c % 8
+    const int c = 2 * cp;
+    *reinterpret_cast<uint32_t*>(base + ((size_t)(c / 8) * rows + row) * 16 + (c % 8) * 2) =
+        (uint32_t)hb[0] | ((uint32_t)hb[1] << 16);
+    // part 1: K half 0 = e4m3(w * ws), K half 1 = e4m3(w_lo * ws * 512), 16 channels per row
+    uint8_t* p1 = base + (size_t)rows * 32;
+    *reinterpret_cast<uint16_t*>(p1 + ((size_t)0 * rows + row) * 16 + c) = pack_e4m3x2(w[0] * ws, w[1] * ws);
+    *reinterpret_cast<uint16_t*>(p1 + ((size_t)1 * rows + row) * 16 + c) =
+        pack_e4m3x2(wl[0] * ws * 512.f, wl[1] * ws * 512.f);
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // Host helpers
 // ------------------------------------------------------------------------------------------
@@ -873,10 +1039,11 @@ static int make_tmap(CUtensorMap* tm, void* base, int planes_total, int N, int H
 }
 
 // Launch one convolution.  `slot` is the timing slot (common.cuh).
-template <int KS, int CIN_PAD, int NPAD, int S, int AS, int EPI, int CONCAT = 0, int NBLK = 1, int TPS = 1, int CG = 1>
+template <int KS, int CIN_PAD, int NPAD, int S, int AS, int EPI, int CONCAT = 0, int NBLK = 1, int TPS = 1, int CG = 1,
+          int FMT = 0>
 static int launch_conv(wn_handle* h, int slot, const uint8_t* wpk, const float* bias, void* in_base, ConvArgs a,
                        cudaStream_t stream) {
-  using C = UmmaCfg<KS, CIN_PAD, NPAD, S, AS, CONCAT, NBLK, TPS, CG>;
+  using C = UmmaCfg<KS, CIN_PAD, NPAD, S, AS, CONCAT, NBLK, TPS, CG, FMT>;
   int rc = get_encoder();
   if (rc) return rc;
   CUtensorMap tm;
@@ -889,7 +1056,7 @@ static int launch_conv(wn_handle* h, int slot, const uint8_t* wpk, const float* 
   a.tiles_x = (a.W + C::TILE_W - 1) / C::TILE_W;
   a.tiles_y = (a.H + C::TILE_H - 1) / C::TILE_H;
   const long long tiles = (long long)a.tiles_x * a.tiles_y * a.N;
-  auto kern = conv_umma_kernel<KS, CIN_PAD, NPAD, S, AS, EPI, CONCAT, NBLK, TPS, CG>;
+  auto kern = conv_umma_kernel<KS, CIN_PAD, NPAD, S, AS, EPI, CONCAT, NBLK, TPS, CG, FMT>;
   WN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
   TimedScope ts(h, slot, stream);
   if constexpr (CG == 2) {  // clusters of two CTAs (one TPC each); every pair takes two adjacent tiles at a time

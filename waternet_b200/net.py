@@ -132,7 +132,9 @@ class WaterNet(nn.Module):
         model = WaterNet().cuda()
         out = model(x, wb, he, gc)      # four (N,3,H,W) tensors -> (N,3,H,W)
 
-    ``precision``: ``"default"`` (tensor cores, bf16x3 split, <=1e-3 parity bar),
+    ``precision``: ``"default"`` = ``"bf16_fp8"`` (tensor cores: bf16 products of the operands' high parts,
+    the two correction terms of the heavy layers as one fp8 MMA; ~4e-4 of the fp32 result, inside the 1e-3
+    parity bar), ``"bf16x3"`` (all three terms in bf16, ~3e-5; what training always uses),
     ``"fp32"`` (CUDA-core fp32 FMA).
     """
 
@@ -146,7 +148,8 @@ class WaterNet(nn.Module):
 
     # -- plumbing -----------------------------------------------------------------
     def _mode(self) -> int:
-        table = {"default": _lib.MODE_DEFAULT, "fp32": _lib.MODE_FP32_SIMT, "bf16x3": _lib.MODE_BF16X3}
+        table = {"default": _lib.MODE_DEFAULT, "fp32": _lib.MODE_FP32_SIMT, "bf16x3": _lib.MODE_BF16X3,
+                 "bf16_fp8": _lib.MODE_BF16_FP8}
         if self.precision not in table:
             raise ValueError(f"unknown precision {self.precision!r}; choose from {sorted(table)}")
         return table[self.precision]

@@ -214,12 +214,14 @@ def test_enhance_u8_end_to_end(eng, precision):
     sd = ofw.synthetic_state_dict(0, 3.0)
     m = _model(0, 3.0, precision)
     eng.pack_weights(m._ordered_params())
-    mode = {"fp32": _lib.MODE_FP32_SIMT, "bf16x3": _lib.MODE_BF16X3}[precision]
+    mode = {"fp32": _lib.MODE_FP32_SIMT, "bf16x3": _lib.MODE_BF16X3, "bf16_fp8": _lib.MODE_BF16_FP8}[precision]
     got = eng.enhance(torch.from_numpy(rgbs).cuda(), mode=mode).cpu().numpy()
     ref = opre.ten2arr(ofw.waternet_forward(sd, *_inputs_from_rgb(rgbs)).numpy())
     diff = np.abs(got.astype(int) - ref.astype(int))
     assert diff.max() <= 1, "truncating cast may flip one level at most"
-    assert (diff != 0).mean() < 0.01
+    # a value within the forward error of a level boundary truncates to the neighbouring level: the share of
+    # such pixels is ~255 x the mean error (3e-5-class modes: < 1 %; fp8 corrections, ~10x the error: < 10 %)
+    assert (diff != 0).mean() < (0.10 if precision == "bf16_fp8" else 0.01)
 
 
 def test_hub_api_roundtrip():

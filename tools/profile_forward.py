@@ -7,7 +7,8 @@ from waternet_b200.engine import get_engine
 from waternet_b200.net import WaterNet
 
 n, h, w = (int(v) for v in (sys.argv[1:4] if len(sys.argv) >= 4 else (1, 1080, 1920)))
-mode = {"fp32": _lib.MODE_FP32_SIMT, "bf16x3": _lib.MODE_BF16X3}[sys.argv[4] if len(sys.argv) > 4 else "bf16x3"]
+mode = {"fp32": _lib.MODE_FP32_SIMT, "bf16x3": _lib.MODE_BF16X3, "bf16_fp8": _lib.MODE_BF16_FP8,
+        "default": _lib.MODE_DEFAULT}[sys.argv[4] if len(sys.argv) > 4 else "default"]
 torch.manual_seed(0)
 eng = get_engine("cuda:0")
 m = WaterNet().cuda().eval()

@@ -1,11 +1,13 @@
-// Tensor-core path of WaterNet.forward (WN_MODE_BF16X3): tcgen05 implicit-GEMM convolutions.
+// Tensor-core path of WaterNet.forward (WN_MODE_BF16X3, WN_MODE_BF16_FP8): tcgen05 implicit-GEMM convolutions.
 //
 // Replaces /root/reference/waternet/net.py:45-56, :75-80, :99-108.  Every
 // convolution is a dense contraction, so it runs on the 5th-gen
 // tensor cores -- but the 1e-3 parity bar rules out single-pass bf16/tf32 operands
-// (SURVEY.md section 0).  Each fp32 operand is split into bf16 hi + lo and three
-// MMAs (hi*hi + lo*hi + hi*lo) accumulate in fp32 in TMEM ("bf16x3", ~2^-16
-// relative operand error).
+// (SURVEY.md section 0).  Each fp32 operand is split into bf16 hi + lo and
+// hi*hi + lo*w + hi*w_lo accumulates in fp32 in TMEM: as three bf16 MMAs ("bf16x3",
+// ~2^-16 relative operand error), or -- the default for the tensor-bound layers -- as
+// one bf16 MMA plus ONE fp8 (e4m3) MMA of K = 32 for both correction terms
+// (UmmaCfg FMT in umma_conv.cuh).
 //
 // Data layout in HBM: activations are bf16 planes of 8 channels,
 //     act[n][plane][y][x][8]   planes [0, C/8) = hi parts, [C/8, 2C/8) = lo parts,
@@ -16,13 +18,15 @@
 // tile: the activations are read from L2/HBM once per tile, not once per tap, and
 // out-of-image pixels come back as zeros from the TMA (padding="same").
 //
-// One persistent CTA per SM, warp-specialised:
+// One persistent CTA per SM (most layers: clusters of two CTAs that share every MMA, cta_group::2, each
+// staging half of the weight rows), warp-specialised:
 //   warps 0-7  epilogue, two groups that split a tile's sub-tiles
 //              (TMEM -> registers -> bias/act -> bf16 hi/lo planes or fp32)
 //   warp 8     A producer (TMA halo tiles, one 16-channel chunk per stage)
 //   warp 9     B producer (bulk copies of pre-packed weight stages, 1-9 taps of a chunk per stage)
 //   warp 10    TMEM allocator
-//   warp 11    MMA issuer (converged warp, one elected lane issues; highest warp id = scheduling priority)
+//   warp 11    MMA issuer (converged warp, one elected lane issues; highest warp id = scheduling priority);
+//              in the peer CTA of a pair: relays "stage full" to the leader's barriers
 // A CTA tile is S sub-tiles of 8x16 pixels (M = 128 each) sharing every weight stage.
 #include "umma_conv.cuh"
 

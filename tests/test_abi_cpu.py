@@ -113,3 +113,15 @@ def test_reference_module_paths_resolve():
         assert hasattr(tu, name)
     import hubconf
     assert callable(hubconf.waternet) and "torch" in hubconf.dependencies
+
+
+def test_mode_constants_match_the_header():
+    """include/waternet_b200.h and the ctypes binding agree on the forward modes."""
+    import re
+    from waternet_b200 import _lib
+    text = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include",
+                             "waternet_b200.h")).read()
+    defs = {m.group(1): int(m.group(2).strip("()")) for m in
+            re.finditer(r"#define\s+WN_MODE_(\w+)\s+(\(?-?\d+\)?)", text)}
+    assert defs == {"FP32_SIMT": _lib.MODE_FP32_SIMT, "BF16X3": _lib.MODE_BF16X3, "BF16_FP8": _lib.MODE_BF16_FP8,
+                    "DEFAULT": _lib.MODE_DEFAULT}

@@ -135,7 +135,7 @@ static size_t stage8_bytes_total(const UmmaLayerSpec& s) {
 }
 struct UmmaWeights {
   uint8_t* stages8[kNumUmmaLayers];  // fp8-correction weight images (has_f8_form layers)
-  float* scale8[kNumUmmaLayers];     // {ws, 2^-9 / ws}
+  float* scale8[kNumUmmaLayers];     // {ws, 2^-9 / ws, max|w|, -}
   uint8_t* stages[kNumUmmaLayers];
   float* bias[kNumUmmaLayers];
   float* dense;  // scratch for packing
@@ -154,7 +154,7 @@ int umma_pack_weights(wn_handle* h, const float* const* params, cudaStream_t str
     if (!h->umma->bias[i]) WN_CUDA(cudaMalloc(&h->umma->bias[i], kSpecs[i].npad * kSpecs[i].nblk * sizeof(float)));
     if (has_f8_form(i)) {
       if (!h->umma->stages8[i]) WN_CUDA(cudaMalloc(&h->umma->stages8[i], stage8_bytes_total(kSpecs[i])));
-      if (!h->umma->scale8[i]) WN_CUDA(cudaMalloc(&h->umma->scale8[i], 2 * sizeof(float)));
+      if (!h->umma->scale8[i]) WN_CUDA(cudaMalloc(&h->umma->scale8[i], 4 * sizeof(float)));
     }
   }
   if (!h->umma->dense) WN_CUDA(cudaMalloc(&h->umma->dense, (size_t)224 * 128 * 49 * sizeof(float)));
@@ -199,7 +199,10 @@ int umma_pack_weights(wn_handle* h, const float* const* params, cudaStream_t str
                                                   s.concat, s.nblk);
     WN_LAUNCH_CHECK(h);
     if (has_f8_form(li)) {
-      f8_scale_kernel<<<1, 256, 0, stream>>>(u->dense, (size_t)rows * s.cinpad * kk, u->scale8[li]);
+      WN_CUDA(cudaMemsetAsync(u->scale8[li], 0, 4 * sizeof(float), stream));
+      f8_absmax_kernel<<<64, 256, 0, stream>>>(u->dense, (size_t)rows * s.cinpad * kk, u->scale8[li]);
+      WN_LAUNCH_CHECK(h);
+      f8_scale_finish_kernel<<<1, 1, 0, stream>>>(u->scale8[li]);
       WN_LAUNCH_CHECK(h);
       pack_stages_f8_cg2_kernel<<<256, 256, 0, stream>>>(u->dense, u->stages8[li], u->scale8[li], s.npad, s.cinpad, kk,
                                                          s.nblk);

@@ -944,23 +944,27 @@ static __global__ void pack_stages_cg2_kernel(const float* __restrict__ dense, _
 //   part 0  [k8 0|1][rows][8 bf16]            w_hi                         (K = 16 bf16 MMA)
 //   part 1  [k16 0|1][rows][16 fp8 (e4m3)]    w * ws  |  w_lo * ws * 2^9   (K = 32 fp8 MMA)
 // with rows = npad/2 of this rank.  scale[0] = ws (a power of two placing max|w| in [112, 224]),
-// scale[1] = 2^-9 / ws (what the epilogue multiplies the second accumulator with).
-static __global__ void f8_scale_kernel(const float* __restrict__ dense, size_t n, float* __restrict__ scale) {
+// scale[1] = 2^-9 / ws (what the epilogue multiplies the second accumulator with); scale[2] = max|w|.
+// scale[2] (as unsigned bits) accumulates max|w| over the grid (bit patterns of non-negative floats are
+// ordered like the floats); f8_scale_finish_kernel turns it into scale[0], scale[1].
+static __global__ void f8_absmax_kernel(const float* __restrict__ dense, size_t n, float* __restrict__ scale) {
   __shared__ float smax[256];
   float m = 0.f;
-  for (size_t i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, fabsf(dense[i]));
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    m = fmaxf(m, fabsf(dense[i]));
   smax[threadIdx.x] = m;
   __syncthreads();
   for (int o = 128; o > 0; o >>= 1) {
     if ((int)threadIdx.x < o) smax[threadIdx.x] = fmaxf(smax[threadIdx.x], smax[threadIdx.x + o]);
     __syncthreads();
   }
-  if (threadIdx.x == 0) {
-    const float mx = fmaxf(smax[0], 1e-30f);
-    const float ws = exp2f(floorf(log2f(224.f / mx)));
-    scale[0] = ws;
-    scale[1] = 1.f / (512.f * ws);
-  }
+  if (threadIdx.x == 0) atomicMax(reinterpret_cast<unsigned int*>(scale + 2), __float_as_uint(smax[0]));
+}
+static __global__ void f8_scale_finish_kernel(float* __restrict__ scale) {
+  const float mx = fmaxf(scale[2], 1e-30f);
+  const float ws = exp2f(floorf(log2f(224.f / mx)));
+  scale[0] = ws;
+  scale[1] = 1.f / (512.f * ws);
 }
 static __global__ void pack_stages_f8_cg2_kernel(const float* __restrict__ dense, uint8_t* __restrict__ out,
                                                  const float* __restrict__ scale, int npad, int cinpad, int kk,

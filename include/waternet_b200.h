@@ -157,13 +157,6 @@ int wn_debug_set_flags(wn_handle* h, int flags);
 /* Number of kernels the library has launched on this handle since creation. */
 uint64_t wn_launch_count(const wn_handle* h);
 
-/* WN_MODE_BF16_FP8 keeps the correction terms of an activation in e4m3 (|v| <= 448).  If a forward pass
- * ever produces a larger activation -- far outside what the reference's [0,1] images and trained weights
- * give -- a sticky flag is raised, reaches the host with the completion of that call, and the handle uses
- * the WN_MODE_BF16X3 kernels from the next call on until wn_pack_weights is called again.  Returns the
- * host-side value of the flag (0/1). */
-int wn_f8_overflowed(const wn_handle* h);
-
 #ifdef __cplusplus
 }
 #endif

@@ -41,7 +41,6 @@ _SIGNATURES = {
     "wn_enhance_u8": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                               c_void_p, c_size_t, c_void_p]),
     "wn_launch_count": (c_uint64, [c_void_p]),
-    "wn_f8_overflowed": (c_int, [c_void_p]),
     "wn_debug_set_flags": (c_int, [c_void_p, c_int]),
     "wn_train_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "wn_forward_train": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, POINTER(c_int64), c_void_p,

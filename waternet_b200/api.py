@@ -73,8 +73,7 @@ class Enhancer:
             return
         def key():  # everything a captured launch sequence has baked in
             ws = eng._ws.get("enhance")
-            return (shape, self.mode, eng.f8_overflowed(), self._dev_in.data_ptr(), self._dev_out.data_ptr(),
-                    eng._weights_key,
+            return (shape, self.mode, self._dev_in.data_ptr(), self._dev_out.data_ptr(), eng._weights_key,
                     None if ws is None else (ws.data_ptr(), ws.numel()))
 
         if self._graph is None or self._graph_key != key():

@@ -256,8 +256,6 @@ int wn_enhance_u8(wn_handle* h, const uint8_t* rgb, uint8_t* out_nhwc, float* ou
 
 uint64_t wn_launch_count(const wn_handle* h) { return h ? h->launches : 0; }
 
-int wn_f8_overflowed(const wn_handle* h) { return h ? umma_f8_overflowed(h) : 0; }
-
 int wn_debug_set_flags(wn_handle* h, int flags) {
   if (!h) {
     set_error("wn_debug_set_flags: null handle");

@@ -153,7 +153,6 @@ int umma_debug_layer(wn_handle* h, const float* const in[4], const int64_t in_st
                      int height, int width, int layer, float* dst, void* workspace,
                      size_t workspace_bytes, cudaStream_t stream, int scheme = 0);
 int umma_pack_weights(wn_handle* h, const float* const* params, cudaStream_t stream);
-int umma_f8_overflowed(const wn_handle* h);
 void umma_free(wn_handle* h);
 size_t umma_forward_workspace_bytes(int n, int h, int w);
 int umma_forward(wn_handle* h, const float* const in[4], const int64_t in_strides[4][4], float* out,

@@ -136,8 +136,6 @@ static size_t stage8_bytes_total(const UmmaLayerSpec& s) {
 struct UmmaWeights {
   uint8_t* stages8[kNumUmmaLayers];  // fp8-correction weight images (has_f8_form layers)
   float* scale8[kNumUmmaLayers];     // {ws, 2^-9 / ws, max|w|, -}
-  int* overflow_dev;                 // sticky: an activation left the e4m3 range in the fp8-correction mode
-  int* overflow_host;                // pinned mirror, refreshed after every forward of that mode
   uint8_t* stages[kNumUmmaLayers];
   float* bias[kNumUmmaLayers];
   float* dense;  // scratch for packing
@@ -160,11 +158,7 @@ int umma_pack_weights(wn_handle* h, const float* const* params, cudaStream_t str
     }
   }
   if (!h->umma->dense) WN_CUDA(cudaMalloc(&h->umma->dense, (size_t)224 * 128 * 49 * sizeof(float)));
-  if (!h->umma->overflow_dev) WN_CUDA(cudaMalloc(&h->umma->overflow_dev, sizeof(int)));
-  if (!h->umma->overflow_host) WN_CUDA(cudaHostAlloc(&h->umma->overflow_host, sizeof(int), cudaHostAllocDefault));
   UmmaWeights* u = h->umma;
-  *u->overflow_host = 0;  // new weights: the fp8-correction mode gets a fresh chance
-  WN_CUDA(cudaMemsetAsync(u->overflow_dev, 0, sizeof(int), stream));
   auto W = [&](int conv) { return params[2 * conv]; };
   auto B = [&](int conv) { return params[2 * conv + 1]; };
   for (int li = 0; li < kNumUmmaLayers; li++) {
@@ -227,8 +221,6 @@ void umma_free(wn_handle* h) {
     if (h->umma->scale8[i]) cudaFree(h->umma->scale8[i]);
   }
   if (h->umma->dense) cudaFree(h->umma->dense);
-  if (h->umma->overflow_dev) cudaFree(h->umma->overflow_dev);
-  if (h->umma->overflow_host) cudaFreeHost(h->umma->overflow_host);
   free(h->umma);
   h->umma = nullptr;
 }
@@ -265,7 +257,6 @@ template <int KS, int CIN_PAD, int NPAD, int S, int AS, int EPI, int CONCAT = 0,
           int FMT = 0>
 static int launch_umma(wn_handle* h, int li, void* in_base, ConvArgs a, cudaStream_t stream) {
   const UmmaLayerSpec& spec = kSpecs[li];
-  if constexpr ((FMT & kFmtOut8) != 0) a.f8_overflow = h->umma->overflow_dev;
   if constexpr ((FMT & kFmtIn8) != 0) {  // fp8-correction form: its own weight images, [hi | fp8] layout, CTA pairs
     if (spec.ks != KS || spec.cinpad != CIN_PAD || spec.npad != NPAD || spec.nblk != NBLK || !has_f8_form(li)) {
       set_error("internal: fp8 launch configuration of layer %d does not match its packed weights", li);
@@ -468,9 +459,6 @@ int umma_forward(wn_handle* h, const float* const in[4], const int64_t in_stride
   }
   int rc = get_encoder();
   if (rc) return rc;
-  // fp8-correction mode: once an activation has left the e4m3 range (sticky flag, mirrored to the host
-  // after every call) this handle keeps to the bf16x3 kernels until new weights are packed
-  if (scheme == 1 && *h->umma->overflow_host) scheme = 0;
   const int nb = umma_chunk(n, H, W);
   for (int n0 = 0; n0 < n; n0 += nb) {
     const int cur = n - n0 < nb ? n - n0 : nb;
@@ -479,11 +467,7 @@ int umma_forward(wn_handle* h, const float* const in[4], const int64_t in_stride
     rc = umma_forward_chunk(h, sub, in_strides, out + (size_t)n0 * 3 * H * W, cur, H, W, workspace, stream, scheme);
     if (rc) return rc;
   }
-  if (scheme == 1)
-    WN_CUDA(cudaMemcpyAsync(h->umma->overflow_host, h->umma->overflow_dev, sizeof(int), cudaMemcpyDeviceToHost, stream));
   return WN_OK;
 }
-
-int umma_f8_overflowed(const wn_handle* h) { return h->umma && h->umma->overflow_host ? *h->umma->overflow_host : 0; }
 
 }  // namespace wn

@@ -342,9 +342,6 @@ struct ConvArgs {
   int mask_planes_half;
   // fp8 correction scheme (FMT bit 0): dequantisation factor 2^-9 / ws of the second accumulator
   const float* f8_scale;
-  // FMT bit 1: sticky flag raised when an activation leaves the e4m3 range (its correction term saturates);
-  // the host side then falls back to the bf16x3 kernels (api.cu)
-  int* f8_overflow;
   // bring-up only (wn_debug_set_flags): bit 0 = epilogue skips its global stores (bit 6: also its arithmetic; bit 7: shared-memory stores instead), bit 1 = weight stages
   // are not re-fetched after the first ring fill, bit 2 = the a_lo / a_hi x w_lo passes are not issued,
   // bit 3 = no early probe of the next weight barrier.
@@ -727,15 +724,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
                 for (int q = 0; q < GC; q += 16) {
                   const int ch = c0 + q;
                   uint32_t hi[8], l8[4], h8[4];
-                  float vmax = 0.f;
 #pragma unroll
                   for (int j = 0; j < 16; j += 4) {
                     float v[4], r[4];
 #pragma unroll
-                    for (int t = 0; t < 4; t++) {
-                      v[t] = fmaxf(f[q + j + t] + s_bias[ch + j + t], 0.f);
-                      vmax = fmaxf(vmax, v[t]);
-                    }
+                    for (int t = 0; t < 4; t++) v[t] = fmaxf(f[q + j + t] + s_bias[ch + j + t], 0.f);
 #pragma unroll
                     for (int t = 0; t < 4; t += 2) {
                       const __nv_bfloat162 h = __floats2bfloat162_rn(v[t], v[t + 1]);
@@ -747,7 +740,6 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
                     l8[j >> 2] = pack_e4m3x4(r[0], r[1], r[2], r[3]);
                     h8[j >> 2] = pack_e4m3x4(v[0], v[1], v[2], v[3]);
                   }
-                  if (!(vmax <= 448.f) && g.f8_overflow) atomicOr(g.f8_overflow, 1);  // also catches NaN
                   const bool second = ch >= g.split_c;
                   const ActDst& d = second ? g.dst1 : g.dst0;
                   const int chl = second ? ch - g.split_c : ch;

@@ -131,11 +131,6 @@ class Engine:
         _lib.check(rc, "wn_forward")
         return out
 
-    def f8_overflowed(self) -> bool:
-        """True once the fp8-correction mode saw an activation beyond the e4m3 range (the library then uses
-        the bf16x3 kernels for this handle until new weights are packed; wn_f8_overflowed)."""
-        return bool(self.lib.wn_f8_overflowed(self.handle))
-
     LAYER_CHANNELS = (128, 128, 128, 64, 64, 64, 64, 3, 96, 96)
 
     def debug_layer(self, x, wb, he, gc, layer: int, mode: int) -> torch.Tensor:

@@ -301,6 +301,13 @@ def main():
             "avg_launch_ms": avg_ms, "launches_timed": n_launch, "share_of_step": conv_ms[top] / (ms_per_step * args.steps),
             "forward_all_convs": {"achieved": 2.0 * TOTAL_MACS * H * W * B * args.steps / (conv_total * 1e-3) / 1e12,
                                   "unit": "TFLOP/s", "ms_per_step": conv_total / args.steps},
+            # BASELINE.json's "fused-fwd HBM GB/s vs roofline": the forward's API-faithful bytes (4 fp32 inputs +
+            # 1 fp32 output = 60 B/px) over the time of all convolutions.  The forward is a dense
+            # contraction (36 kFLOP/B), so this figure cannot come near the HBM roofline; reported for completeness.
+            "forward_hbm_algorithmic": {
+                "achieved": 60.0 * H * W * B * args.steps / (conv_total * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
+                "unit": "GB/s", "frac": 60.0 * H * W * B * args.steps / (conv_total * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                "bytes_per_px": 60, "note": "tensor-bound, not HBM-bound: see bound/frac above"},
             "preprocess_apply_hbm": None,
         }
         if slot_cnt[21]:

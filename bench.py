@@ -2,7 +2,7 @@
 """Headline benchmark: images/sec of the WaterNet hot path at 1080p, batch 16 per GPU.
 
     python bench.py --gpus 1 --steps K --warmup W              # this repo's CUDA path
-    python bench.py --impl reference --gpus 1 --steps K ...    # the reference's CPU algorithm (oracle port)
+    python bench.py --impl reference --gpus 1 --steps K ...    # the UNMODIFIED reference on the host cores (baseline/_ref)
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
 
 A "step" is one pass of the hot path over one batch: uint8 RGB images ->
@@ -10,9 +10,11 @@ WB/GC/HE preprocess -> gated-fusion forward -> uint8 enhanced images
 (BASELINE.json configs[2]: batch 16, 1920x1080, preprocess+forward end to end).
 `value` times that with the uint8 batch already resident in HBM; `e2e` times the
 public host-buffer call (pinned host uint8 in, uint8 out) with both copies inside
-the timed region.  At N>1 every rank processes its own batch (weak scaling) and
-the step ends with one NCCL all-gather of the uint8 output.
-Rank 0 prints ONE JSON line.
+the timed region (pipelined pass by pass on side streams).  At N>1 every rank
+processes its own batch (weak scaling) and all-gathers its uint8 output over NCCL,
+pass by pass under the next pass's kernels (waternet_b200.dist.PassGather).
+Before timing, image 0 of the batch is checked against the CPU reference (the line
+carries `parity`; the run fails above the 1e-3 bar).  Rank 0 prints ONE JSON line.
 """
 import argparse
 import json
@@ -31,6 +33,16 @@ if ROOT not in sys.path:
 
 METRIC = "images/sec at 1080p batch16 (preprocess + gated-fusion forward, uint8 in -> uint8 out)"
 UNIT = "images/s"
+
+
+def workload_config(args, world):
+    """`config` keys shared by both arms (same strings for the same command line)."""
+    return {"workload": f"batch {args.batch} x {args.width}x{args.height} RGB uint8 per GPU: WB/GC/HE preprocess + "
+                        "WaterNet forward + uint8 postprocess (BASELINE configs[2])",
+            "global_batch": world * args.batch, "weights": "random init (torch.manual_seed(0))",
+            "cache": "no L2 flush needed: each step streams GBs of inputs + intermediates (>> 126 MB L2)",
+            "sampled_images_per_step": "product arm: every image of the batch; reference arm: 1 image per step "
+                                       "(images are independent units, images/s does not depend on the batch)"}
 
 # multiply-accumulates per pixel of every convolution, state-dict order (SURVEY.md 2.1)
 CONV_MACS = [75264, 409600, 147456, 8192, 200704, 102400, 36864, 1728] + [9408, 25600, 864] * 3
@@ -121,42 +133,105 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------
-# reference arm / cpu baseline: the oracle port of the reference algorithm on the host cores
+# reference arm / cpu baseline: the unmodified reference (baseline/_ref, copied from /root/reference by
+# __graft_entry__.build()) on the host cores; the oracle port only when that copy or cv2 is missing
 # ------------------------------------------------------------------------------------------
-def cpu_reference_step(sd, rgb):
-    """One image through the reference algorithm on the CPU (numpy preprocess + torch-CPU forward)."""
-    from oracle import forward as ofw
-    from oracle import preprocess as opre
-    wb, gc, he = opre.transform(rgb)
-    ins = [torch.from_numpy(opre.arr2ten(a).copy()) for a in (rgb, wb, he, gc)]
-    out = ofw.waternet_forward(sd, *ins)
-    return opre.ten2arr(out.numpy())
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
+
+
+def load_reference():
+    """(transform, WaterNet class, arr2ten, ten2arr) of the unmodified reference, imported by file path under
+    private module names (the repo's own `waternet` package keeps its name).  None when unavailable."""
+    import importlib.util
+    import types
+    if not os.path.isfile(os.path.join(REF_DIR, "waternet", "net.py")):
+        return None, "baseline/_ref is absent (run __graft_entry__.build() where /root/reference exists)"
+    try:
+        import cv2  # noqa: F401  (waternet/data.py needs it)
+    except Exception as e:  # pragma: no cover
+        return None, f"cv2 unavailable: {e}"
+
+    def load(name, path):
+        spec = importlib.util.spec_from_file_location(name, path)
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[name] = mod
+        spec.loader.exec_module(mod)
+        return mod
+
+    sys.dont_write_bytecode = True
+    pkg = types.ModuleType("_wn_reference")
+    pkg.__path__ = [os.path.join(REF_DIR, "waternet")]
+    sys.modules["_wn_reference"] = pkg
+    data = load("_wn_reference.data", os.path.join(REF_DIR, "waternet", "data.py"))
+    net = load("_wn_reference.net", os.path.join(REF_DIR, "waternet", "net.py"))
+    hub = load("_wn_reference_hubconf", os.path.join(REF_DIR, "hubconf.py"))  # arr2ten / ten2arr helpers
+    return (data.transform, net.WaterNet, hub.arr2ten_noeinops, hub.ten2arr_noeinops), None
+
+
+class CpuReference:
+    """One image through the reference on the CPU: transform -> arr2ten x4 -> WaterNet -> ten2arr."""
+
+    def __init__(self, state_dict):
+        ref, why = load_reference()
+        self.kind = "reference" if ref else "port"
+        self.note = why
+        torch.set_num_threads(os.cpu_count() or 1)
+        if ref:
+            self.transform, net_cls, self.arr2ten, self.ten2arr = ref
+            self.model = net_cls()
+            self.model.load_state_dict(state_dict, strict=True)
+            self.model.eval()
+        else:
+            self.sd = state_dict
+
+    def step(self, rgb):
+        """rgb uint8 HWC -> (fp32 output (1,3,H,W) ndarray, uint8 output HWC)."""
+        if self.kind == "reference":
+            wb, gc, he = self.transform(rgb)
+            ins = [self.arr2ten(a) for a in (rgb, wb, he, gc)]
+            with torch.no_grad():
+                out = self.model(*ins)
+            return out.numpy(), self.ten2arr(out)[0]
+        from oracle import forward as ofw
+        from oracle import preprocess as opre
+        wb, gc, he = opre.transform(rgb)
+        ins = [torch.from_numpy(opre.arr2ten(a).copy()) for a in (rgb, wb, he, gc)]
+        out = ofw.waternet_forward(self.sd, *ins).numpy()
+        return out, opre.ten2arr(out)[0]
+
+
+def bench_state_dict():
+    """The weights both arms use: WaterNet() default init under torch.manual_seed(0), as a CPU state dict."""
+    from waternet_b200.net import WaterNet
+    torch.manual_seed(0)
+    return {k: v.detach().clone() for k, v in WaterNet().state_dict().items()}
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
-    from oracle import forward as ofw
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    sd = ofw.synthetic_state_dict(0, 1.0)
+    ref = CpuReference(bench_state_dict())
     frames = synthetic_batch(1, args.height, args.width, 0)
     for _ in range(args.warmup):
-        cpu_reference_step(sd, frames[0])
+        ref.step(frames[0])
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cpu_reference_step(sd, frames[0])
+        ref.step(frames[0])
     dt = (time.perf_counter() - t0) / max(args.steps, 1)
     value = 1.0 / dt
-    sample = f"1 image {args.width}x{args.height} per step (of the batch-{args.batch} workload), oracle port"
+    sample = (f"1 image {args.width}x{args.height} per step (of the batch-{args.batch} workload; images are independent, "
+              f"so images/s does not depend on the batch), "
+              + ("unmodified reference: waternet.data.transform (numpy+cv2) + WaterNet.forward (torch CPU fp32)"
+                 if ref.kind == "reference" else f"oracle port ({ref.note})"))
+    config = workload_config(args, world)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"batch {args.batch} x {args.width}x{args.height} RGB uint8, preprocess+forward e2e",
-                   "sampled_images_per_step": 1},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+        "config": config,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": ref.kind,
                          "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -188,53 +263,111 @@ def main():
 
     from waternet_b200 import _lib
     from waternet_b200.api import Enhancer
+    from waternet_b200.dist import PassGather
     from waternet_b200.net import WaterNet
 
-    torch.manual_seed(0)
-    model = WaterNet(precision=args.mode).to(device).eval()  # random init of the reference architecture
+    sd = bench_state_dict()  # random init of the reference architecture, the same tensors the reference arm loads
+    model = WaterNet(precision=args.mode)
+    model.load_state_dict(sd, strict=True)
+    model = model.to(device).eval()
     enh = Enhancer(model, device=device)
     eng = enh.engine
     mode = model._mode()
-    params = model._ordered_params()
-    eng.pack_weights(params, key=tuple((p.data_ptr(), p._version) for p in params))
 
     B, H, W = args.batch, args.height, args.width
     host = synthetic_batch(B, H, W, seed=rank)
     dev_in = torch.from_numpy(host).to(device)
     dev_out = torch.empty_like(dev_in)
-    gathered = torch.empty((world * B, H, W, 3), dtype=torch.uint8, device=device) if world > 1 else None
+    nb = eng.chunk_images(B, H, W)
+    gather = PassGather((B, H, W, 3), torch.uint8, device) if world > 1 else None
+    side = torch.cuda.Stream(device)
 
     def step_resident():
-        eng.enhance(dev_in, mode=mode, out_u8=dev_out)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, dev_out)
+        """One step with the batch resident in HBM: per pass, kernels on the compute stream and (N > 1) the
+        all-gather of that pass's output on a side stream, under the next pass's kernels."""
+        cur = torch.cuda.current_stream(device)
+        for a in range(0, B, nb):
+            b = min(B, a + nb)
+            eng.enhance(dev_in[a:b], mode=mode, out_u8=dev_out[a:b])
+            if gather is not None:
+                ev = torch.cuda.Event()
+                ev.record(cur)
+                with torch.cuda.stream(side):
+                    side.wait_event(ev)
+                    gather.on_pass(dev_out[a:b], a, b)
+        if gather is not None:
+            cur.wait_stream(side)
 
-    pin_in = torch.from_numpy(host).pin_memory()
-    pin_out = torch.empty_like(pin_in).pin_memory()
-
-    def gather_after(dev_result):
-        dist.all_gather_into_tensor(gathered, dev_result)
-
-    def step_e2e():  # the public host-buffer call: H2D + kernels (+ all-gather) + D2H + sync
-        enh.enhance_pinned(pin_in, pin_out, after_device=gather_after if world > 1 else None)
+    pins = [(torch.from_numpy(host).pin_memory(), torch.empty(host.shape, dtype=torch.uint8).pin_memory())
+            for _ in range(2)]
+    on_pass = gather.on_pass if gather is not None else None
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(step_fn, steps):
+    def timed(run, steps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(steps):
-            step_fn()
+        run(steps)
         e1.record()
         barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+        ms_local = e0.elapsed_time(e1)
         if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
+            every = torch.zeros(world, device=device)
+            every[rank] = ms_local
+            dist.all_reduce(every, op=dist.ReduceOp.SUM)
+            per_rank = [float(v) for v in every.tolist()]
+        else:
+            per_rank = [float(ms_local)]
+        return max(per_rank), per_rank
+
+    def run_resident(steps):
+        for _ in range(steps):
+            step_resident()
+
+    def run_e2e(steps):
+        """The public host-buffer call, as a video loop uses it: submit step i+1, then wait for step i.  Every
+        step's input is copied H2D from pinned memory and its result D2H inside the timed region."""
+        cur = torch.cuda.current_stream(device)
+        prev = None
+        for i in range(steps):
+            ticket = enh.submit(*pins[i % 2], on_pass=on_pass)
+            if prev is not None:
+                enh.wait(prev)
+            prev = ticket
+        enh.wait(prev)
+        cur.wait_stream(enh._s_out)
+
+    # ---- parity before timing: image 0 of rank 0's batch against the CPU reference (both outputs) ----
+    parity = None
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        ref = CpuReference(sd)
+        t0 = time.perf_counter()
+        ref_f32, ref_u8 = ref.step(host[0])
+        dt = time.perf_counter() - t0
+        cpu_baseline = {"value": 1.0 / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": ref.kind,
+                        "sample": f"1 image {W}x{H} of the batch ("
+                                  + ("unmodified reference from baseline/_ref: numpy+cv2 preprocess, torch-CPU fp32 forward"
+                                     if ref.kind == "reference" else f"oracle port: {ref.note}") + f"), {dt:.1f} s"}
+        got_f32 = torch.empty((B, 3, H, W), dtype=torch.float32, device=device)
+        for a in range(0, B, nb):  # the same pass structure as the timed step
+            eng.enhance(dev_in[a:min(B, a + nb)], mode=mode, out_u8=dev_out[a:min(B, a + nb)], out_f32=got_f32[a:min(B, a + nb)])
+        g32 = got_f32[0].cpu().numpy()
+        g8 = dev_out[0].cpu().numpy()
+        del got_f32
+        scale = float(np.max(np.abs(ref_f32)))
+        max_rel = float(np.max(np.abs(g32 - ref_f32[0])) / scale)
+        d8 = np.abs(g8.astype(np.int16) - ref_u8.astype(np.int16))
+        parity = {"against": cpu_baseline["kind"], "image": 0, "max_rel_err": max_rel, "tolerance": 1e-3,
+                  "u8_mismatch_frac": float((d8 != 0).mean()), "u8_max_abs_diff": int(d8.max()),
+                  "f8_overflowed": bool(eng.f8_overflowed())}
+        if not (max_rel <= 1e-3 and d8.max() <= 1):
+            print(json.dumps({"error": "parity check failed before timing", "parity": parity}), flush=True)
+            raise SystemExit(2)
 
     for _ in range(max(args.warmup, 3) if args.warmup > 0 else 0):
         step_resident()
@@ -243,14 +376,29 @@ def main():
         sampler.start()
     eng.enable_timing(True)
     launches0 = eng.launch_count
-    total_ms = timed(step_resident, args.steps)
+    total_ms, per_rank_ms = timed(run_resident, args.steps)
     launches = eng.launch_count - launches0
     slot_ms, slot_cnt = eng.read_timings()
     eng.enable_timing(False)
     clocks = sampler.stop() if rank == 0 else None
 
-    step_e2e()
-    e2e_ms = timed(step_e2e, args.steps)
+    # the collective's own cost: the same step without it, same box, right after
+    nogather_ms = None
+    if world > 1:
+        saved, gather = gather, None
+        nogather_ms, _ = timed(run_resident, args.steps)
+        gather = saved
+
+    run_e2e(2)
+    e2e_ms, e2e_per_rank = timed(run_e2e, args.steps)
+    if world > 1:  # what was gathered is what every rank computed: compare my block of rank 0's result with my own
+        mine = gather.gathered[rank]
+        same = torch.equal(mine, enh._slots[(enh._next - 1) % len(enh._slots)].dev_out)
+        flag = torch.tensor([1 if same else 0], device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        gather_ok = bool(flag.item())
+    else:
+        gather_ok = None
 
     ms_per_step = total_ms / args.steps
     value = world * B * args.steps / (total_ms / 1e3)
@@ -258,7 +406,6 @@ def main():
 
     if rank == 0:
         peaks = load_peaks()
-        px_per_launch_denominator = None
         conv_ms = slot_ms[:17]
         macs_by_slot = list(CONV_MACS)
         names_by_slot = list(CONV_NAMES)
@@ -279,24 +426,34 @@ def main():
         imgs_per_launch = args.steps * B / n_launch
         macs = macs_by_slot[top]
         fused = [names_by_slot[top]]
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
-        if mode != _lib.MODE_FP32_SIMT and os.path.exists(tpath):
-            with open(tpath) as f:
-                tj = json.load(f)
-            ent = tj["kernels"].get(fused[0])
-            if ent and (tj["height"], tj["width"]) == (H, W):  # measured per 1080p image; scales with images per launch
-                traffic = ent["dram_bytes_per_image"] * imgs_per_launch
+        traffic, traffic_total_per_image, traffic_src = None, None, None
+        for cand in ("r2_traffic.json", "r1_traffic.json"):
+            tpath = os.path.join(ROOT, "profiles", cand)
+            if mode != _lib.MODE_FP32_SIMT and os.path.exists(tpath):
+                with open(tpath) as f:
+                    tj = json.load(f)
+                ent = tj["kernels"].get(fused[0])
+                if ent and (tj["height"], tj["width"]) == (H, W):  # measured per 1080p image; scales with images per launch
+                    traffic = ent["dram_bytes_per_image"] * imgs_per_launch
+                    traffic_total_per_image = sum(k["dram_bytes_per_image"] for k in tj["kernels"].values())
+                    traffic_src = cand
+                    break
         flops = 2.0 * macs * H * W * imgs_per_launch
         achieved = flops / (avg_ms * 1e-3) / 1e12
         peak = peaks["tf_sustained"]
         conv_total = sum(conv_ms)
+        fwd_alg_bytes_per_image = 60.0 * H * W  # 4 fp32 inputs + 1 fp32 output
         roofline = {
             "bound": "tensor", "kernel": "+".join(fused), "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
             "frac": achieved / peak, "traffic": traffic,
-            "traffic_note": "DRAM bytes per launch from the committed ncu --set full capture (profiles/r1_traffic.json)",
-            "algorithmic_bytes_per_launch": 4.0 * H * W * imgs_per_launch * {
-                "cmg.conv2": 256, "cmg.conv3": 256, "cmg.conv5": 128, "cmg.conv6": 128}.get(fused[0], 0) or None,
+            "traffic_note": f"DRAM bytes per launch from the committed ncu --set full capture (profiles/{traffic_src})",
+            # FUSED definition: the whole forward is one logical op of 60 B/px; a layer's share is
+            # its share of the forward's FLOPs.  Everything above that is intermediate round trips through HBM.
+            "algorithmic_bytes_per_launch": fwd_alg_bytes_per_image * imgs_per_launch * macs / TOTAL_MACS,
+            "forward_dram_bytes_per_image": {"measured_ncu": traffic_total_per_image,
+                                             "algorithmic_fused": fwd_alg_bytes_per_image,
+                                             "ratio": (traffic_total_per_image / fwd_alg_bytes_per_image
+                                                       if traffic_total_per_image else None)},
             "peak_source": peaks["source"] + ", bf16 dense sustained (kernel timed inside a long step)",
             "avg_launch_ms": avg_ms, "launches_timed": n_launch, "share_of_step": conv_ms[top] / (ms_per_step * args.steps),
             "forward_all_convs": {"achieved": 2.0 * TOTAL_MACS * H * W * B * args.steps / (conv_total * 1e-3) / 1e12,
@@ -312,9 +469,14 @@ def main():
         }
         if slot_cnt[21]:
             apply_ms = slot_ms[21] / slot_cnt[21]
-            gbs = 51.0 * H * W * (args.steps * B / slot_cnt[21]) / (apply_ms * 1e-3) / 1e9
+            # folded path: 3 B/px read + 32 B/px of first-layer operand planes written (fp32 mode: 3 + 48)
+            bpp = 51.0 if mode == _lib.MODE_FP32_SIMT else 35.0
+            gbs = bpp * H * W * (args.steps * B / slot_cnt[21]) / (apply_ms * 1e-3) / 1e9
             roofline["preprocess_apply_hbm"] = {"achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                                                "frac": gbs / peaks["hbm_gbs"], "bytes_per_px": 51}
+                                                "frac": gbs / peaks["hbm_gbs"], "bytes_per_px": bpp}
+        config = workload_config(args, world)  # identical in both arms
+        detail = {"mode": args.mode, "images_per_pass": nb,
+                  "collective": "all_gather(uint8 output) per pass on a side stream (NCCL)" if world > 1 else "none"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -323,34 +485,30 @@ def main():
                 mode, "bf16 + fp8 corrections (v = hi + lo: hi x hi in bf16, both correction terms of the heavy "
                       "layers as one e4m3 MMA; fp32 accumulate; 3-term bf16 elsewhere)"),
             "data": "synthetic",
-            "config": {"workload": f"batch {B} x {W}x{H} RGB uint8 per GPU: WB/GC/HE preprocess + WaterNet forward + "
-                                   "uint8 postprocess (BASELINE configs[2])",
-                       "global_batch": world * B, "mode": args.mode, "weights": "random init (torch.manual_seed(0))",
-                       "cache": "no L2 flush needed: each step streams GBs of intermediates (>> 126 MB L2)",
-                       "collective": "all_gather(uint8 output)" if world > 1 else "none"},
+            "config": config,
+            "detail": detail,
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
-                    "h2d_bytes_per_step": int(pin_in.numel()), "d2h_bytes_per_step": int(pin_out.numel())},
+                    "h2d_bytes_per_step": int(pins[0][0].numel()), "d2h_bytes_per_step": int(pins[0][1].numel()),
+                    "api": "Enhancer.submit/wait (pinned host uint8 in/out; H2D, kernels, D2H pipelined per pass on three streams)"},
             "gpu_launches": int(launches),
+            "parity": parity,
             "roofline": roofline,
             "kernel_ms_per_step": {name: round(slot_ms[i] / args.steps, 4) for i, name in enumerate(
                 names_by_slot + ["pack", "gate", "pre_stats", "pre_luts", "pre_apply", "post"]) if slot_cnt[i]},
             "kernel_tflops": {name: round(2.0 * macs_by_slot[i] * H * W * B * args.steps / (slot_ms[i] * 1e-3) / 1e12, 1)
                               for i, name in enumerate(names_by_slot) if slot_cnt[i] and slot_ms[i] > 0},
+            "cpu_baseline": cpu_baseline,
         }
-        if world == 1 and not args.no_cpu_baseline:
-            from oracle import forward as ofw
-            cores = os.cpu_count() or 1
-            torch.set_num_threads(cores)
-            sd = ofw.synthetic_state_dict(0, 1.0)
-            t0 = time.perf_counter()
-            cpu_reference_step(sd, host[0])
-            dt = time.perf_counter() - t0
-            line["cpu_baseline"] = {"value": 1.0 / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                                    "sample": f"1 image {W}x{H} of the batch (numpy preprocess + torch-CPU fp32 forward), "
-                                              f"{dt:.1f} s"}
-        else:
-            line["cpu_baseline"] = None
+        if world > 1:
+            line["multi_gpu"] = {
+                "per_rank_ms_per_step": [round(v / args.steps, 3) for v in per_rank_ms],
+                "per_rank_ms_per_step_e2e": [round(v / args.steps, 3) for v in e2e_per_rank],
+                "ms_per_step_without_collective": nogather_ms / args.steps,
+                "collective_cost_ms_per_step": ms_per_step - nogather_ms / args.steps,
+                "gathered_equals_local": gather_ok,
+                "gather_bytes_received_per_step": int((world - 1) * B * H * W * 3),
+            }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

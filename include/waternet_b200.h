@@ -12,6 +12,9 @@
  *   wn_pack_weights       waternet/net.py:12-42,62-70,94-97  the 34-tensor state dict
  *                         (hubconf.py:83 / inference.py:111-120 load_state_dict)
  *   wn_forward            waternet/net.py:99-108   WaterNet.forward(x, wb, ce, gc)
+ *   wn_confidence_maps    waternet/net.py:45-56    ConfidenceMapGenerator.forward(x, wb, ce, gc)
+ *   wn_refine             waternet/net.py:75-80    Refiner.forward(x, xbar)
+ *   wn_resize_u8          waternet/training_utils.py:94-107  cv2.resize + BGR2RGB of the dataset items
  *   wn_postprocess_u8     hubconf.py:24-34         ten2arr_noeinops (clip, *255, truncate, NCHW->NHWC)
  *   wn_enhance_u8         hubconf.py:85-94 + net.py:99-108: preprocess -> model -> postprocess
  *                         (the per-frame body of inference.py:261-323)
@@ -35,7 +38,7 @@
 extern "C" {
 #endif
 
-#define WN_ABI_VERSION 1
+#define WN_ABI_VERSION 2
 
 #define WN_OK 0
 #define WN_E_INVALID (-1)   /* bad argument (NULL pointer, non-positive size, unknown mode) */
@@ -98,11 +101,41 @@ int wn_preprocess_u8(wn_handle* h, const uint8_t* rgb, int n, int height, int wi
                      float* wb, float* he, float* gc, uint8_t* wb_u8, uint8_t* he_u8,
                      uint8_t* gc_u8, void* workspace, size_t workspace_bytes, void* stream);
 
+/*
+ * Batched cv2.resize(img, (dst_w, dst_h)) of 8-bit 3-channel images, default INTER_LINEAR, as the training
+ * dataset applies it per item (waternet/training_utils.py:94-103) -- bit-exact OpenCV arithmetic.  src_dev,
+ * src_h, src_w are HOST arrays of n entries: device pointers to HWC uint8 images and their sizes.  dst_nhwc:
+ * (n, dst_h, dst_w, 3).  swap_rb != 0 also applies the BGR<->RGB swap that follows the resize
+ * (training_utils.py:106-107).
+ */
+int wn_resize_u8(wn_handle* h, const uint8_t* const* src_dev, const int* src_h, const int* src_w, int n,
+                 uint8_t* dst_nhwc, int dst_h, int dst_w, int swap_rb, void* stream);
+
 /* ten2arr: fp32 NCHW (N,3,H,W) -> uint8 NHWC, clip to [0,1], *255, truncate. */
 int wn_postprocess_u8(wn_handle* h, const float* out_nchw, uint8_t* out_nhwc, int n, int height,
                       int width, void* stream);
 
-/* preprocess -> forward -> postprocess without leaving the device. */
+/*
+ * The reference's callable sub-modules, evaluated with the weights of the packed state dict.
+ * wn_confidence_maps: the three sigmoid maps as one fp32 contiguous (N,3,H,W) tensor (channel r = the map
+ * net.py:55 returns as out<r+1>).  wn_refine: refiner `which` (0 = wb_refiner, 1 = ce_refiner, 2 = gc_refiner)
+ * applied to cat[x, xbar]; in_strides[0] / [1] are the element strides of x / xbar; out fp32 contiguous
+ * (N,3,H,W).  Both take the workspace of wn_submodule_workspace_bytes.
+ */
+size_t wn_submodule_workspace_bytes(int n, int h, int w, int mode);
+int wn_confidence_maps(wn_handle* h, const float* x, const float* wb, const float* he, const float* gc,
+                       const int64_t in_strides[4][4], float* out_maps, int n, int height, int width, int mode,
+                       void* workspace, size_t workspace_bytes, void* stream);
+int wn_refine(wn_handle* h, int which, const float* x, const float* xbar, const int64_t in_strides[2][4],
+              float* out, int n, int height, int width, int mode, void* workspace, size_t workspace_bytes,
+              void* stream);
+
+/*
+ * preprocess -> forward -> postprocess without leaving the device.  In the tensor-core modes nothing fp32 is
+ * materialised: the per-pixel preprocess kernel writes the first layer's operand planes (8-bit levels, the /255
+ * of arr2ten is folded into the first layer's weights) and the last launch's epilogue writes the uint8 image
+ * (and the fp32 output too when out_f32_or_null is given).
+ */
 size_t wn_enhance_workspace_bytes(int n, int h, int w, int mode);
 int wn_enhance_u8(wn_handle* h, const uint8_t* rgb, uint8_t* out_nhwc, float* out_f32_or_null,
                   int n, int height, int width, int mode, void* workspace, size_t workspace_bytes,
@@ -156,6 +189,26 @@ int wn_debug_set_flags(wn_handle* h, int flags);
 
 /* Number of kernels the library has launched on this handle since creation. */
 uint64_t wn_launch_count(const wn_handle* h);
+
+/*
+ * The tensor-core forward processes a batch in passes of at most 8 Mi pixels (workspace ~1.9 KB per pixel);
+ * wn_forward_chunk_images returns the number of images per pass for a batch of n (callers that pipeline
+ * host<->device copies or a collective against the passes split their batch at this granularity).
+ * wn_set_chunk_pixels lowers the cap (0 restores the default); it never raises the workspace need.
+ */
+int wn_forward_chunk_images(const wn_handle* h, int n, int height, int width);
+int wn_set_chunk_pixels(wn_handle* h, long long max_pixels);
+
+/*
+ * WN_MODE_BF16_FP8 keeps the correction terms of an activation in e4m3 (|v| <= 448).  A forward pass that
+ * produces a larger activation -- far outside what the reference's [0,1] images and trained weights give --
+ * raises a sticky device flag, and the batch that raised it is recomputed by the WN_MODE_BF16X3 kernels
+ * WITHIN THE SAME CALL (the re-run is enqueued behind every pass, its launches return at once while the flag
+ * is down).  The flag reaches the host with the completion of that call; from then on the handle goes
+ * straight to the WN_MODE_BF16X3 kernels until wn_pack_weights is called again.  Returns the host-side value
+ * of the flag (0/1).
+ */
+int wn_f8_overflowed(const wn_handle* h);
 
 #ifdef __cplusplus
 }

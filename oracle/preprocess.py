@@ -286,3 +286,63 @@ def ten2arr(ten: np.ndarray) -> np.ndarray:
     arr = np.clip(np.asarray(ten, dtype=np.float32), 0, 1)
     arr = (arr * 255).astype(np.uint8)
     return np.transpose(arr, (0, 2, 3, 1))
+
+
+# --------------------------------------------------------------------------
+# cv2.resize(img, (w, h)) on 8-bit images, default INTER_LINEAR  (training_utils.py:94-103)
+# --------------------------------------------------------------------------
+_RESIZE_COEF_BITS = 11  # INTER_RESIZE_COEF_BITS
+
+
+def _resize_coeffs(ssize: int, dsize: int, clamp: bool):
+    """Source index and the two 11-bit fixed-point weights of every destination coordinate.
+
+    OpenCV ``imgproc/src/resize.cpp`` (``cv::resize`` -> ``resizeGeneric_``, linear branch):
+    ``fx = (float)((dx + 0.5) * scale - 0.5); sx = cvFloor(fx); fx -= sx`` with ``scale = 1 / (dsize / ssize)`` in
+    double; along x an index outside ``[0, ssize-1)`` is clamped with weight (1, 0) (``clamp=True``), along y only
+    the ROW INDEX is clamped later and the weights keep the fractional part; the weights are
+    ``saturate_cast<short>(w * 2048)`` (round half to even).
+    """
+    scale = 1.0 / (float(dsize) / float(ssize))
+    idx = np.empty(dsize, np.int64)
+    w0 = np.empty(dsize, np.int64)
+    w1 = np.empty(dsize, np.int64)
+    for d in range(dsize):
+        f = np.float32((d + 0.5) * scale - 0.5)
+        s = int(np.floor(f))
+        f = np.float32(f - np.float32(s))
+        if clamp:
+            if s < 0:
+                f, s = np.float32(0), 0
+            if s >= ssize - 1:
+                f, s = np.float32(0), ssize - 1
+        idx[d] = s
+        w0[d] = int(np.rint(np.float32(np.float32(1.0) - f) * np.float32(2048)))
+        w1[d] = int(np.rint(f * np.float32(2048)))
+    return idx, w0, w1
+
+
+def resize_linear_u8(src: np.ndarray, dsize) -> np.ndarray:
+    """``cv2.resize(src, dsize)`` for uint8 HWC images, ``dsize = (width, height)`` like cv2.
+
+    Restates OpenCV 4.x ``resize.cpp``: horizontal pass ``S[x0]*a0 + S[x1]*a1`` in int32 (``HResizeLinear``),
+    vertical pass ``(((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2`` (``VResizeLinear`` for 8-bit).
+    An exact 2x reduction in both directions is silently switched to INTER_AREA by cv::resize
+    (``(a + b + c + d + 2) >> 2``); equal sizes are a copy.  Third-party arithmetic: the reference does not pin
+    OpenCV; checked bit-exact against the build image's cv2 4.13.0 in tests/test_oracle.py.
+    """
+    dw, dh = int(dsize[0]), int(dsize[1])
+    sh, sw = src.shape[:2]
+    if (sw, sh) == (dw, dh):
+        return src.copy()
+    s = src.astype(np.int64)
+    if sw == 2 * dw and sh == 2 * dh:
+        return ((s[0::2, 0::2] + s[0::2, 1::2] + s[1::2, 0::2] + s[1::2, 1::2] + 2) >> 2).astype(np.uint8)
+    xi, xa0, xa1 = _resize_coeffs(sw, dw, True)
+    yi, yb0, yb1 = _resize_coeffs(sh, dh, False)
+    xi1 = np.minimum(xi + 1, sw - 1)
+    rows = s[:, xi, :] * xa0[None, :, None] + s[:, xi1, :] * xa1[None, :, None]
+    r0 = rows[np.clip(yi, 0, sh - 1)]
+    r1 = rows[np.clip(yi + 1, 0, sh - 1)]
+    out = (((yb0[:, None, None] * (r0 >> 4)) >> 16) + ((yb1[:, None, None] * (r1 >> 4)) >> 16) + 2) >> 2
+    return np.clip(out, 0, 255).astype(np.uint8)

@@ -58,6 +58,8 @@ FWD_CASES = [
     ("c1_1x112x112", [(10, "smooth")], 112, 112, 0, 1.0),
     ("n2_112x112", [(11, "noise"), (12, "smooth")], 112, 112, 0, 1.0),
     ("gain3_1x40x56", [(13, "noise")], 40, 56, 1, 3.0),
+    # BASELINE.json configs[1]: batch 16, 112x112 (stress weights; mixed noise / smooth frames)
+    ("c2_16x112x112", [(100 + i, "noise" if i % 4 == 0 else "smooth") for i in range(16)], 112, 112, 2, 3.0),
 ]
 
 

@@ -32,7 +32,8 @@ def test_library_exports_every_declared_symbol(lib):
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/waternet_b200.h but not exported"
     assert sorted(_lib.EXPORTED_SYMBOLS) == declared, "ctypes binding and header disagree"
-    assert lib.wn_abi_version() == 1
+    assert lib.wn_abi_version() == _lib.ABI_VERSION == int(
+        re.search(r"#define\s+WN_ABI_VERSION\s+(\d+)", open(os.path.join(ROOT, "include", "waternet_b200.h")).read()).group(1))
 
 
 def test_constant_tables_match_oracle(lib):
@@ -60,6 +61,10 @@ def test_null_arguments_are_rejected_without_a_gpu(lib):
     assert lib.wn_forward_workspace_bytes(0, 10, 10, 0) == 0
     assert lib.wn_forward_workspace_bytes(2, 112, 112, 0) > 0
     assert lib.wn_preprocess_workspace_bytes(2, 112, 112) > 0
+    assert lib.wn_submodule_workspace_bytes(2, 112, 112, -1) > lib.wn_forward_workspace_bytes(2, 112, 112, -1)
+    assert lib.wn_enhance_workspace_bytes(2, 112, 112, -1) > 0
+    assert lib.wn_forward_chunk_images(None, 4, 8, 8) == 0 and lib.wn_f8_overflowed(None) == 0
+    assert lib.wn_set_chunk_pixels(None, 0) != 0
 
 
 def test_state_dict_is_reference_compatible():
@@ -99,6 +104,70 @@ def test_no_cpu_fallback_without_cuda():
         data.transform(ofw.synthetic_image(0, 16, 16))
     with pytest.raises(WaterNetLibraryError):
         waternet(pretrained=False)
+    # the reference's waternet(device=None) hands back a CPU model (hubconf.py:96); this build is CUDA-only and
+    # says so at the call instead of failing later (INTEGRATION.md "Differences")
+    with pytest.raises(WaterNetLibraryError, match="CUDA"):
+        waternet(pretrained=False, device=None)
+    with pytest.raises(WaterNetLibraryError):
+        waternet(pretrained=False, device="cpu")
+    # sub-modules and the model refuse CPU tensors the same way
+    from waternet_b200.net import ConfidenceMapGenerator, Refiner, WaterNet
+    t = torch.rand(1, 3, 8, 8)
+    with torch.no_grad():
+        for call in (lambda: WaterNet()(t, t, t, t), lambda: ConfidenceMapGenerator()(t, t, t, t),
+                     lambda: Refiner()(t, t)):
+            with pytest.raises(WaterNetLibraryError):
+                call()
+
+
+def test_packed_weight_cache_key_tracks_parameter_changes():
+    """Host logic of the packed-weight cache (advisor finding): the epoch advances on load_state_dict / .to() /
+    invalidate_packed_weights(), _version on in-place updates; deepcopy and pickling keep the parent binding."""
+    import copy
+    import io
+    from waternet_b200.net import WaterNet, _param_version
+    m = WaterNet()
+    e0 = getattr(m, "_pack_epoch", 0)
+    m.load_state_dict(ofw.synthetic_state_dict(0))
+    e1 = m._pack_epoch
+    assert e1 > e0 and m.cmg._pack_epoch >= 1
+    m.float()
+    assert m._pack_epoch > e1
+    v0 = _param_version(m.cmg.conv1.weight)
+    with torch.no_grad():
+        m.cmg.conv1.weight.mul_(2.0)
+    assert _param_version(m.cmg.conv1.weight) > v0
+    e2 = m._pack_epoch
+    m.cmg.conv1.weight.data.mul_(0.5)      # invisible to _version: the documented manual hook
+    m.invalidate_packed_weights()
+    assert m._pack_epoch > e2
+    twin = copy.deepcopy(m)
+    assert twin.cmg._parent_ref() is twin and twin.gc_refiner._slot == 2 and m.cmg._parent_ref() is m
+    buf = io.BytesIO()
+    torch.save(m, buf)
+    buf.seek(0)
+    again = torch.load(buf, weights_only=False)
+    assert again.wb_refiner._parent_ref() is again
+    with torch.inference_mode():
+        p = torch.nn.Parameter(torch.zeros(1))
+    assert isinstance(_param_version(p), int)
+
+
+def test_submodules_are_the_reference_graph_when_autograd_records():
+    """ConfidenceMapGenerator / Refiner are callable like the reference's (net.py:45-56, 75-80); with autograd
+    recording they evaluate the torch graph (CPU works), which must be the oracle's function."""
+    from waternet_b200.net import WaterNet
+    m = WaterNet()
+    sd = ofw.synthetic_state_dict(2, 3.0)
+    m.load_state_dict(sd)
+    torch.manual_seed(1)
+    x, wb, he, gc = [torch.rand(1, 3, 12, 14) for _ in range(4)]
+    maps = m.cmg(x, wb, he, gc)
+    assert isinstance(maps, tuple) and len(maps) == 3 and maps[0].shape == (1, 1, 12, 14) and maps[0].requires_grad
+    ref = ofw.confidence_maps(sd, x, wb, he, gc)
+    assert torch.allclose(torch.cat(maps, 1), ref, rtol=1e-5, atol=1e-6)
+    r = m.ce_refiner(x, he)
+    assert torch.allclose(r, ofw.refine(sd, "ce_refiner", x, he), rtol=1e-5, atol=1e-6)
 
 
 def test_reference_module_paths_resolve():

@@ -8,7 +8,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from waternet_b200.dist import all_gather_batch, run_sharded, shard_counts, shard_range
+from waternet_b200.dist import PassGather, all_gather_batch, run_sharded, shard_counts, shard_range
 
 
 def test_shard_range_covers_the_batch_exactly():
@@ -49,6 +49,14 @@ def _worker(rank, world, port, n, ret):
         counts = shard_counts(n, world)
         again = all_gather_batch(local, counts)
         ok = ok and torch.equal(again, full)
+        # the per-pass gather bench.py and Enhancer.submit(on_pass=...) use: equal batches, passes of 2 images
+        per = 3
+        mine = fn(batch[:per]) + rank  # rank-dependent content
+        pg = PassGather(tuple(mine.shape), mine.dtype, mine.device)
+        for a in range(0, per, 2):
+            pg.on_pass(mine[a:a + 2], a, min(per, a + 2))
+        want = torch.cat([fn(batch[:per]) + r for r in range(world)])
+        ok = ok and pg.calls == 2 and torch.equal(pg.result(), want)
         ret[rank] = bool(ok)
     finally:
         dist.destroy_process_group()

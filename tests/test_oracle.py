@@ -98,3 +98,15 @@ def test_clahe_matches_cv2(shape):
         plane = rng.integers(0, 256, shape, dtype=np.uint8)
         want = cv2.createCLAHE(clipLimit=clip, tileGridSize=(8, 8)).apply(plane)
         assert np.array_equal(opre.clahe_apply(plane, clip, 8), want)
+
+
+def test_resize_restatement_matches_cv2():
+    """oracle.preprocess.resize_linear_u8 == cv2.resize(img, (w, h)) (default INTER_LINEAR) bit for bit: the
+    training dataset's resize (training_utils.py:94-103) is third-party arithmetic like CLAHE."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(3)
+    cases = [(300, 400, 112, 112), (224, 224, 112, 112), (112, 112, 112, 112), (57, 91, 112, 112), (113, 225, 112, 112),
+             (641, 480, 320, 240), (1, 1, 8, 8), (2, 3, 112, 112), (700, 900, 256, 256), (225, 224, 112, 112)]
+    for sh, sw, dh, dw in cases:
+        src = rng.integers(0, 256, (sh, sw, 3), dtype=np.uint8)
+        assert np.array_equal(opre.resize_linear_u8(src, (dw, dh)), cv2.resize(src, (dw, dh))), (sh, sw, dh, dw)

@@ -19,7 +19,7 @@ MODE_BF16_FP8 = 2
 MODE_DEFAULT = -1
 NUM_PARAMS = 34
 NUM_TIMING_SLOTS = 23
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # name -> (restype, argtypes); mirrors include/waternet_b200.h one to one
 _SIGNATURES = {
@@ -36,11 +36,21 @@ _SIGNATURES = {
     "wn_preprocess_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "wn_preprocess_u8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "wn_resize_u8": (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_int), POINTER(c_int), c_int, c_void_p, c_int, c_int,
+                             c_int, c_void_p]),
     "wn_postprocess_u8": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "wn_enhance_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "wn_enhance_u8": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                               c_void_p, c_size_t, c_void_p]),
     "wn_launch_count": (c_uint64, [c_void_p]),
+    "wn_submodule_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "wn_confidence_maps": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, POINTER(c_int64), c_void_p,
+                                   c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "wn_refine": (c_int, [c_void_p, c_int, c_void_p, c_void_p, POINTER(c_int64), c_void_p, c_int, c_int, c_int,
+                          c_int, c_void_p, c_size_t, c_void_p]),
+    "wn_forward_chunk_images": (c_int, [c_void_p, c_int, c_int, c_int]),
+    "wn_set_chunk_pixels": (c_int, [c_void_p, ctypes.c_longlong]),
+    "wn_f8_overflowed": (c_int, [c_void_p]),
     "wn_debug_set_flags": (c_int, [c_void_p, c_int]),
     "wn_train_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "wn_forward_train": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, POINTER(c_int64), c_void_p,

@@ -1,22 +1,44 @@
 """Host-buffer convenience API: numpy uint8 images in, numpy uint8 images out.
 
 This is the per-frame body of the reference's ``inference.py:169-233,261-323``
-(preprocess -> model -> postprocess) as one call; the host<->device copies use
-pinned staging buffers and the current CUDA stream.
+(preprocess -> model -> postprocess) as one call.  Host<->device copies use pinned
+staging buffers on side streams and are pipelined against the kernels pass by
+pass (SURVEY.md 8f.2 "pinned-memory double-buffered H2D/D2H"):
+
+    copy-in stream   H2D pass k+1 | H2D pass k+2 | ...
+    compute stream        kernels pass k | kernels pass k+1 | ...
+    copy-out stream            (collective of pass k-1) D2H pass k-1 | ...
+
+``submit()`` enqueues one batch and returns a ticket; ``wait()`` blocks until that
+batch's result is in the caller's pinned buffer.  With two slots of device buffers a
+caller that submits batch i+1 before waiting for batch i (a video loop) keeps the
+copies of one batch entirely under the kernels of its neighbours.
 """
 from __future__ import annotations
 
-from typing import Optional
+from typing import Callable, List, Optional
 
 import numpy as np
 import torch
 
 from . import _lib
-from .engine import Engine, get_engine
+from .engine import Engine
+from .net import MODES
+
+
+class _Slot:
+    """Device-side staging of one in-flight batch."""
+
+    def __init__(self):
+        self.dev_in = None
+        self.dev_out = None
+        self.done = None      # event on the copy-out stream: the result is in the caller's pinned buffer
+        self.graph = None     # CUDA graph of the kernel sequence (small frames)
+        self.graph_key = None
 
 
 class Enhancer:
-    """Holds a model's packed weights and pinned staging buffers for repeated calls.
+    """A model's engine (packed weights) plus staging buffers and streams for repeated host-buffer calls.
 
     For small frames the ~15 kernel launches of one enhance call cost more host time than the GPU
     needs to run them; with ``cuda_graph=True`` (default for batches up to ``GRAPH_MAX_PIXELS``) the
@@ -25,26 +47,22 @@ class Enhancer:
 
     GRAPH_MAX_PIXELS = 1 << 20
 
-    def __init__(self, model, device=None, precision: Optional[str] = None, cuda_graph: bool = True):
-        self.engine: Engine = get_engine(device if device is not None else next(model.parameters()).device)
-        self.model = model.to(self.engine.device)
-        self.mode = model._mode() if precision is None else {
-            "default": _lib.MODE_DEFAULT, "fp32": _lib.MODE_FP32_SIMT, "bf16x3": _lib.MODE_BF16X3,
-                 "bf16_fp8": _lib.MODE_BF16_FP8}[precision]
+    def __init__(self, model, device=None, precision: Optional[str] = None, cuda_graph: bool = True, depth: int = 2):
+        if device is not None:
+            model = model.to(device)
+        self.model = model
+        self.engine: Engine = model.engine()  # raises without CUDA: there is no CPU path
+        self.mode = model._mode() if precision is None else MODES[precision]
+        self.cuda_graph = cuda_graph
+        self._slots: List[_Slot] = [_Slot() for _ in range(max(1, depth))]
+        self._next = 0
         self._pin_in = None
         self._pin_out = None
-        self._dev_in = None
-        self._dev_out = None
-        self.cuda_graph = cuda_graph
-        self._graph = None
-        self._graph_key = None
+        dev = self.engine.device
+        self._s_in = torch.cuda.Stream(dev)
+        self._s_out = torch.cuda.Stream(dev)
 
-    def _buffers(self, shape):
-        if self._dev_in is None or tuple(self._dev_in.shape) != tuple(shape):
-            self._graph = None
-            self._dev_in = torch.empty(shape, dtype=torch.uint8, device=self.engine.device)
-            self._dev_out = torch.empty(shape, dtype=torch.uint8, device=self.engine.device)
-
+    # ---- numpy convenience --------------------------------------------------------------------
     def __call__(self, rgb: np.ndarray) -> np.ndarray:
         """rgb: uint8 HWC or NHWC.  Returns the enhanced uint8 image(s), same layout."""
         arr = np.asarray(rgb)
@@ -53,9 +71,6 @@ class Enhancer:
             arr = arr[None]
         if arr.dtype != np.uint8 or arr.ndim != 4 or arr.shape[3] != 3:
             raise ValueError(f"expected uint8 (N)HWC RGB, got {arr.dtype} {arr.shape}")
-        eng = self.engine
-        params = self.model._ordered_params()
-        eng.pack_weights(params, key=tuple((p.data_ptr(), p._version) for p in params))
         if self._pin_in is None or tuple(self._pin_in.shape) != tuple(arr.shape):
             self._pin_in = torch.empty(arr.shape, dtype=torch.uint8).pin_memory()
             self._pin_out = torch.empty(arr.shape, dtype=torch.uint8).pin_memory()
@@ -64,37 +79,86 @@ class Enhancer:
         out = self._pin_out.numpy().copy()
         return out[0] if single else out
 
-    def _run_kernels(self) -> None:
-        """preprocess -> forward -> postprocess from ``_dev_in`` into ``_dev_out`` (graph replay when small)."""
-        eng = self.engine
-        shape = tuple(self._dev_in.shape)
-        if not self.cuda_graph or shape[0] * shape[1] * shape[2] > self.GRAPH_MAX_PIXELS:
-            eng.enhance(self._dev_in, mode=self.mode, out_u8=self._dev_out)
+    # ---- kernels of one pass --------------------------------------------------------------------
+    def _run_kernels(self, eng: Engine, slot: _Slot, a: int, b: int, whole: bool) -> None:
+        """preprocess -> forward -> ten2arr of images [a, b) of the slot (graph replay when small)."""
+        src, dst = slot.dev_in[a:b], slot.dev_out[a:b]
+        shape = tuple(slot.dev_in.shape)
+        if not (self.cuda_graph and whole and shape[0] * shape[1] * shape[2] <= self.GRAPH_MAX_PIXELS):
+            eng.enhance(src, mode=self.mode, out_u8=dst)
             return
+
         def key():  # everything a captured launch sequence has baked in
             ws = eng._ws.get("enhance")
-            return (shape, self.mode, self._dev_in.data_ptr(), self._dev_out.data_ptr(), eng._weights_key,
-                    None if ws is None else (ws.data_ptr(), ws.numel()))
+            return (shape, self.mode, eng.f8_overflowed(), slot.dev_in.data_ptr(), slot.dev_out.data_ptr(),
+                    eng._weights_key, None if ws is None else (ws.data_ptr(), ws.numel()))
 
-        if self._graph is None or self._graph_key != key():
-            eng.enhance(self._dev_in, mode=self.mode, out_u8=self._dev_out)  # warm-up: workspace, func attributes
+        if slot.graph is None or slot.graph_key != key():
+            eng.enhance(src, mode=self.mode, out_u8=dst)  # warm-up: workspace, func attributes
             torch.cuda.current_stream(eng.device).synchronize()
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                eng.enhance(self._dev_in, mode=self.mode, out_u8=self._dev_out)
-            self._graph, self._graph_key = graph, key()
+                eng.enhance(src, mode=self.mode, out_u8=dst)
+            slot.graph, slot.graph_key = graph, key()
             return  # the warm-up call already produced this frame's result
-        self._graph.replay()
+        slot.graph.replay()
 
-    def enhance_pinned(self, pin_in: torch.Tensor, pin_out: torch.Tensor, after_device=None) -> None:
-        """Pinned uint8 NHWC host tensor -> pinned uint8 NHWC host tensor (H2D, kernels, D2H, sync).
+    # ---- pipelined host-buffer path ---------------------------------------------------------------
+    def submit(self, pin_in: torch.Tensor, pin_out: torch.Tensor,
+               on_pass: Optional[Callable[[torch.Tensor, int, int], None]] = None) -> _Slot:
+        """Enqueue one batch: pinned uint8 NHWC host tensor -> pinned uint8 NHWC host tensor.
 
-        ``after_device(dev_out)`` runs on the device result before the copy back (e.g. an all-gather).
+        The batch is processed in passes of ``engine.chunk_images`` images; pass k's H2D copy runs on the
+        copy-in stream, its kernels on the current stream, and ``on_pass(dev_out[a:b], a, b)`` (e.g. the
+        all-gather of that pass's output) followed by its D2H copy on the copy-out stream.  Returns a ticket
+        for :meth:`wait`; neither ``pin_in`` nor ``pin_out`` may be touched before that.
         """
-        self._buffers(tuple(pin_in.shape))
-        self._dev_in.copy_(pin_in, non_blocking=True)
-        self._run_kernels()
-        if after_device is not None:
-            after_device(self._dev_out)
-        pin_out.copy_(self._dev_out, non_blocking=True)
-        torch.cuda.current_stream(self.engine.device).synchronize()
+        if pin_in.dtype != torch.uint8 or pin_in.dim() != 4 or pin_in.shape[3] != 3 or pin_in.shape != pin_out.shape:
+            raise ValueError(f"expected uint8 (N,H,W,3) pinned tensors of one shape, got {tuple(pin_in.shape)}")
+        eng = self.model.engine()  # re-packs if the parameters changed since the last call (no-op otherwise)
+        dev = eng.device
+        slot = self._slots[self._next % len(self._slots)]
+        self._next += 1
+        if slot.done is not None:
+            slot.done.synchronize()  # back-pressure: the previous user of these buffers has been delivered
+        shape = tuple(pin_in.shape)
+        if slot.dev_in is None or tuple(slot.dev_in.shape) != shape:
+            slot.graph = None
+            slot.dev_in = torch.empty(shape, dtype=torch.uint8, device=dev)
+            slot.dev_out = torch.empty(shape, dtype=torch.uint8, device=dev)
+        n, h, w, _ = shape
+        cur = torch.cuda.current_stream(dev)
+        if n * h * w == 0:
+            slot.done = torch.cuda.Event()
+            slot.done.record(cur)
+            return slot
+        nb = eng.chunk_images(n, h, w)
+        self._s_in.wait_stream(cur)   # whatever the caller enqueued before (e.g. filling pin_in on the device side)
+        self._s_out.wait_stream(cur)
+        for a in range(0, n, nb):
+            b = min(n, a + nb)
+            with torch.cuda.stream(self._s_in):
+                slot.dev_in[a:b].copy_(pin_in[a:b], non_blocking=True)
+                ev_in = torch.cuda.Event()
+                ev_in.record(self._s_in)
+            cur.wait_event(ev_in)
+            self._run_kernels(eng, slot, a, b, whole=(a == 0 and b == n))
+            ev_k = torch.cuda.Event()
+            ev_k.record(cur)
+            with torch.cuda.stream(self._s_out):
+                self._s_out.wait_event(ev_k)
+                if on_pass is not None:
+                    on_pass(slot.dev_out[a:b], a, b)
+                pin_out[a:b].copy_(slot.dev_out[a:b], non_blocking=True)
+        slot.done = torch.cuda.Event()
+        slot.done.record(self._s_out)
+        return slot
+
+    def wait(self, ticket: _Slot) -> None:
+        if ticket.done is not None:
+            ticket.done.synchronize()
+
+    def enhance_pinned(self, pin_in: torch.Tensor, pin_out: torch.Tensor, on_pass=None) -> None:
+        """Pinned uint8 NHWC host tensor -> pinned uint8 NHWC host tensor; returns when ``pin_out`` is complete."""
+        self.wait(self.submit(pin_in, pin_out, on_pass=on_pass))
+        torch.cuda.current_stream(self.engine.device).wait_stream(self._s_out)

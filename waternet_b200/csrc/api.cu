@@ -210,13 +210,29 @@ int wn_postprocess_u8(wn_handle* h, const float* out_nchw, uint8_t* out_nhwc, in
   return postprocess_u8(h, out_nchw, out_nhwc, n, height, width, (cudaStream_t)stream);
 }
 
+int wn_resize_u8(wn_handle* h, const uint8_t* const* src_dev, const int* src_h, const int* src_w, int n,
+                 uint8_t* dst_nhwc, int dst_h, int dst_w, int swap_rb, void* stream) {
+  if (!h || !src_dev || !src_h || !src_w || !dst_nhwc || n <= 0 || dst_h <= 0 || dst_w <= 0) {
+    set_error("wn_resize_u8: bad argument");
+    return WN_E_INVALID;
+  }
+  DeviceGuard guard(h->device);
+  return resize_u8(h, src_dev, src_h, src_w, n, dst_nhwc, dst_h, dst_w, swap_rb, (cudaStream_t)stream);
+}
+
 static size_t align256(size_t v) { return (v + 255) / 256 * 256; }
+
+// fp32 CUDA-core mode: the API tensors are materialised (preprocess -> 4 fp32 tensors -> forward -> fp32 -> ten2arr)
+static size_t enhance_simt_workspace_bytes(int n, int h, int w) {
+  size_t tens = align256((size_t)n * 3 * h * w * sizeof(float));
+  return 5 * tens + align256(preprocess_workspace_bytes(n, h, w)) +
+         align256(simt_forward_workspace_bytes(n, h, w)) + 256;
+}
 
 size_t wn_enhance_workspace_bytes(int n, int h, int w, int mode) {
   if (n <= 0 || h <= 0 || w <= 0) return 0;
-  size_t tens = align256((size_t)n * 3 * h * w * sizeof(float));
-  return 5 * tens + align256(preprocess_workspace_bytes(n, h, w)) +
-         align256(wn_forward_workspace_bytes(n, h, w, mode)) + 256;
+  if (resolve_mode(mode) == WN_MODE_FP32_SIMT) return enhance_simt_workspace_bytes(n, h, w);
+  return umma_enhance_workspace_bytes(n, h, w);
 }
 
 int wn_enhance_u8(wn_handle* h, const uint8_t* rgb, uint8_t* out_nhwc, float* out_f32_or_null,
@@ -226,10 +242,26 @@ int wn_enhance_u8(wn_handle* h, const uint8_t* rgb, uint8_t* out_nhwc, float* ou
     set_error("wn_enhance_u8: null argument");
     return WN_E_INVALID;
   }
+  if (n <= 0 || height <= 0 || width <= 0) {
+    set_error("wn_enhance_u8: bad shape n=%d h=%d w=%d", n, height, width);
+    return WN_E_INVALID;
+  }
+  if (!h->packed) {
+    set_error("wn_enhance_u8: wn_pack_weights has not been called");
+    return WN_E_STATE;
+  }
   if (workspace_bytes < wn_enhance_workspace_bytes(n, height, width, mode)) {
     set_error("wn_enhance_u8: workspace too small");
     return WN_E_WORKSPACE;
   }
+  if ((size_t)height * width > (size_t)0x7fffffff / 3 || n > 65535) {
+    set_error("image too large: n=%d h=%d w=%d", n, height, width);
+    return WN_E_UNSUPPORTED;
+  }
+  DeviceGuard guard(h->device);
+  if (resolve_mode(mode) != WN_MODE_FP32_SIMT)  // tensor-core modes: folded path, nothing fp32 is materialised
+    return umma_enhance_u8(h, rgb, out_nhwc, out_f32_or_null, n, height, width, workspace, workspace_bytes,
+                           (cudaStream_t)stream, resolve_mode(mode) == WN_MODE_BF16_FP8 ? 1 : 0);
   uint8_t* ws = (uint8_t*)(((uintptr_t)workspace + 255) / 256 * 256);
   const size_t tens = align256((size_t)n * 3 * height * width * sizeof(float));
   float* t[5];
@@ -241,7 +273,7 @@ int wn_enhance_u8(wn_handle* h, const uint8_t* rgb, uint8_t* out_nhwc, float* ou
   size_t pre_b = align256(preprocess_workspace_bytes(n, height, width));
   ws += pre_b;
   void* fwd_ws = ws;
-  size_t fwd_b = align256(wn_forward_workspace_bytes(n, height, width, mode));
+  size_t fwd_b = align256(simt_forward_workspace_bytes(n, height, width));
   int rc = wn_preprocess_u8(h, rgb, n, height, width, t[0], t[1], t[2], t[3], nullptr, nullptr,
                             nullptr, pre_ws, pre_b, stream);
   if (rc) return rc;
@@ -253,6 +285,101 @@ int wn_enhance_u8(wn_handle* h, const uint8_t* rgb, uint8_t* out_nhwc, float* ou
   if (rc) return rc;
   return wn_postprocess_u8(h, outf, out_nhwc, n, height, width, stream);
 }
+
+// ---- the reference's callable sub-modules (net.py:45-56 ConfidenceMapGenerator.forward, :75-80 Refiner.forward)
+size_t wn_submodule_workspace_bytes(int n, int h, int w, int mode) {
+  if (n <= 0 || h <= 0 || w <= 0) return 0;
+  if (resolve_mode(mode) == WN_MODE_FP32_SIMT) return simt_forward_workspace_bytes(n, h, w);
+  // + the three refined images side by side (the refiners run as one block-diagonal stack)
+  return align256(umma_forward_workspace_bytes(n, h, w)) + align256((size_t)n * 9 * h * w * sizeof(float)) + 256;
+}
+
+int wn_confidence_maps(wn_handle* h, const float* x, const float* wb, const float* he, const float* gc,
+                       const int64_t in_strides[4][4], float* out_maps, int n, int height, int width, int mode,
+                       void* workspace, size_t workspace_bytes, void* stream) {
+  if (!h || !x || !wb || !he || !gc || !in_strides || !out_maps || !workspace || n <= 0 || height <= 0 || width <= 0) {
+    set_error("wn_confidence_maps: bad argument");
+    return WN_E_INVALID;
+  }
+  if (!h->packed) {
+    set_error("wn_confidence_maps: wn_pack_weights has not been called");
+    return WN_E_STATE;
+  }
+  if (workspace_bytes < wn_submodule_workspace_bytes(n, height, width, mode)) {
+    set_error("wn_confidence_maps: workspace too small");
+    return WN_E_WORKSPACE;
+  }
+  DeviceGuard guard(h->device);
+  const float* in[4] = {x, wb, he, gc};
+  const int m = resolve_mode(mode);
+  if (m == WN_MODE_FP32_SIMT)
+    return simt_forward(h, in, in_strides, out_maps, n, height, width, workspace, workspace_bytes,
+                        (cudaStream_t)stream, kStackCmg, 0);
+  if (m != WN_MODE_BF16X3 && m != WN_MODE_BF16_FP8) {
+    set_error("wn_confidence_maps: unknown mode %d", mode);
+    return WN_E_INVALID;
+  }
+  return umma_forward(h, in, in_strides, out_maps, n, height, width, workspace, workspace_bytes,
+                      (cudaStream_t)stream, m == WN_MODE_BF16_FP8 ? 1 : 0, kStackCmg, nullptr);
+}
+
+int wn_refine(wn_handle* h, int which, const float* x, const float* xbar, const int64_t in_strides[2][4],
+              float* out, int n, int height, int width, int mode, void* workspace, size_t workspace_bytes,
+              void* stream) {
+  if (!h || !x || !xbar || !in_strides || !out || !workspace || n <= 0 || height <= 0 || width <= 0 || which < 0 ||
+      which > 2) {
+    set_error("wn_refine: bad argument");
+    return WN_E_INVALID;
+  }
+  if (!h->packed) {
+    set_error("wn_refine: wn_pack_weights has not been called");
+    return WN_E_STATE;
+  }
+  if (workspace_bytes < wn_submodule_workspace_bytes(n, height, width, mode)) {
+    set_error("wn_refine: workspace too small");
+    return WN_E_WORKSPACE;
+  }
+  DeviceGuard guard(h->device);
+  // refiner r sees cat[x, input r+1] (net.py:101-103): hand xbar to every slot, keep refiner `which`
+  const float* in[4] = {x, xbar, xbar, xbar};
+  int64_t st[4][4];
+  for (int t = 0; t < 4; t++)
+    for (int k = 0; k < 4; k++) st[t][k] = in_strides[t == 0 ? 0 : 1][k];
+  const int m = resolve_mode(mode);
+  if (m == WN_MODE_FP32_SIMT)
+    return simt_forward(h, in, st, out, n, height, width, workspace, workspace_bytes, (cudaStream_t)stream,
+                        kStackRefiners, which);
+  if (m != WN_MODE_BF16X3 && m != WN_MODE_BF16_FP8) {
+    set_error("wn_refine: unknown mode %d", mode);
+    return WN_E_INVALID;
+  }
+  uint8_t* ws = (uint8_t*)(((uintptr_t)workspace + 255) / 256 * 256);
+  const size_t fwd_b = align256(umma_forward_workspace_bytes(n, height, width));
+  float* refined = (float*)(ws + fwd_b);
+  int rc = umma_forward(h, in, st, nullptr, n, height, width, ws, fwd_b, (cudaStream_t)stream,
+                        m == WN_MODE_BF16_FP8 ? 1 : 0, kStackRefiners, refined);
+  if (rc) return rc;
+  const size_t img = (size_t)3 * height * width * sizeof(float);
+  WN_CUDA(cudaMemcpy2DAsync(out, img, refined + (size_t)which * 3 * height * width, 3 * img, img, n,
+                            cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return WN_OK;
+}
+
+int wn_set_chunk_pixels(wn_handle* h, long long max_pixels) {
+  if (!h || max_pixels < 0) {
+    set_error("wn_set_chunk_pixels: bad argument");
+    return WN_E_INVALID;
+  }
+  h->chunk_pixels = max_pixels;
+  return WN_OK;
+}
+
+int wn_forward_chunk_images(const wn_handle* h, int n, int height, int width) {
+  if (!h || n <= 0 || height <= 0 || width <= 0) return 0;
+  return umma_chunk_images(h, n, height, width);
+}
+
+int wn_f8_overflowed(const wn_handle* h) { return h ? umma_f8_overflowed(h) : 0; }
 
 uint64_t wn_launch_count(const wn_handle* h) { return h ? h->launches : 0; }
 

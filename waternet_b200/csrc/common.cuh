@@ -68,6 +68,8 @@ enum TimingSlot {
   kSlotPost = 22,
   kNumSlots = 23
 };
+// which part of WaterNet.forward a forward call evaluates (the reference's sub-modules are callable: net.py:45-56, :75-80)
+enum FwdStack { kStackAll = 0, kStackCmg = 1, kStackRefiners = 2 };
 struct Timing {
   static constexpr int kMax = 8192;
   bool on;
@@ -89,6 +91,7 @@ struct wn_handle {
   wn::Timing* timing;
   wn::UmmaBwd* bwd;
   int dbg_flags;  // bring-up switches for the conv kernel (wn_debug_set_flags); 0 in normal use
+  long long chunk_pixels;  // cap on pixels per pass of the tensor-core forward (0 = default, wn_set_chunk_pixels)
 };
 
 namespace wn {
@@ -124,14 +127,21 @@ int preprocess_u8(wn_handle* h, const uint8_t* rgb, int n, int height, int width
                   void* workspace, size_t workspace_bytes, cudaStream_t stream);
 int postprocess_u8(wn_handle* h, const float* out_nchw, uint8_t* out_nhwc, int n, int height,
                    int width, cudaStream_t stream);
+int resize_u8(wn_handle* h, const uint8_t* const* src, const int* src_h, const int* src_w, int n, uint8_t* dst,
+              int dst_h, int dst_w, int swap_rb, cudaStream_t stream);
+// transform + cat[x, wb, he, gc] straight into the first layer's operand planes: planes[n][2][H*W] of 16 B
+// (8 bf16 levels 0..255: plane 0 = x.rgb wb.rgb he.rg, plane 1 = he.b gc.rgb 0 0 0 0)
+int preprocess_u8_planes(wn_handle* h, const uint8_t* rgb, int n, int height, int width, uint4* planes,
+                         void* workspace, size_t workspace_bytes, cudaStream_t stream);
 
 // conv_simt.cu
 int simt_pack_weights(wn_handle* h, const float* const* params, cudaStream_t stream);
 void simt_free(wn_handle* h);
 size_t simt_forward_workspace_bytes(int n, int h, int w);
+// stack (FwdStack): kStackCmg -> out = the three confidence maps; kStackRefiners -> out = refiner `which`'s image
 int simt_forward(wn_handle* h, const float* const in[4], const int64_t in_strides[4][4], float* out,
                  int n, int height, int width, void* workspace, size_t workspace_bytes,
-                 cudaStream_t stream);
+                 cudaStream_t stream, int stack = 0, int which = 0);
 
 int simt_debug_layer(wn_handle* h, const float* const in[4], const int64_t in_strides[4][4], int n,
                      int height, int width, int layer, float* dst, void* workspace,
@@ -146,18 +156,35 @@ struct FwdBuffers {
   float* refined; // optional: refined images after ReLU, fp32 [n][9][H][W]
   int* exact_flag;
 };
+struct FwdOpts {
+  int scheme = 0;              // 1 = fp8 correction passes (WN_MODE_BF16_FP8)
+  int dbg_layer = -1;          // wn_debug_forward_layer: stop after this layer and decode it into dbg_dst
+  float* dbg_dst = nullptr;
+  bool packed = false;         // act0 already holds the 16-channel operand planes of this batch
+  bool hi_only = false;        // ... as exact 8-bit levels, hi planes only (written by the preprocess kernel)
+  const int* run_if = nullptr; // every launch is conditional on *run_if != 0 (ConvArgs::run_if)
+  uint8_t* out_u8 = nullptr;   // the last launch also writes ten2arr(out) as uint8 NHWC
+  int stack = kStackAll;       // kStackCmg: stop after the confidence maps; kStackRefiners: refiners only
+};
 int umma_forward_layers(wn_handle* h, const float* const in[4], const int64_t st[4][4], float* out, int n,
-                        int height, int width, const FwdBuffers& b, cudaStream_t stream, int dbg_layer = -1,
-                        float* dbg_dst = nullptr, int scheme = 0);  // scheme 1 = fp8 correction passes
+                        int height, int width, const FwdBuffers& b, cudaStream_t stream,
+                        const FwdOpts& opts = FwdOpts());
 int umma_debug_layer(wn_handle* h, const float* const in[4], const int64_t in_strides[4][4], int n,
                      int height, int width, int layer, float* dst, void* workspace,
                      size_t workspace_bytes, cudaStream_t stream, int scheme = 0);
 int umma_pack_weights(wn_handle* h, const float* const* params, cudaStream_t stream);
 void umma_free(wn_handle* h);
 size_t umma_forward_workspace_bytes(int n, int h, int w);
+int umma_chunk_images(const wn_handle* h, int n, int height, int width);
+// stack = kStackCmg: out receives the three confidence maps; kStackRefiners: `refined` receives the three
+// refined images as [n][9][H][W] and out is unused
 int umma_forward(wn_handle* h, const float* const in[4], const int64_t in_strides[4][4], float* out,
                  int n, int height, int width, void* workspace, size_t workspace_bytes,
-                 cudaStream_t stream, int scheme = 0);
+                 cudaStream_t stream, int scheme = 0, int stack = kStackAll, float* refined = nullptr);
+size_t umma_enhance_workspace_bytes(int n, int h, int w);
+int umma_enhance_u8(wn_handle* h, const uint8_t* rgb, uint8_t* out_u8, float* out_f32, int n, int height,
+                    int width, void* workspace, size_t workspace_bytes, cudaStream_t stream, int scheme);
+int umma_f8_overflowed(const wn_handle* h);
 
 // conv_bwd.cu
 int bwd_pack_weights(wn_handle* h, const float* const* params, cudaStream_t stream);

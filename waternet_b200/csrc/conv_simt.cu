@@ -262,10 +262,11 @@ __global__ void pair_kernel(const float* __restrict__ cat12, float* __restrict__
 static int simt_forward_chunk(wn_handle* h, const float* const in[4],
                               const int64_t in_strides[4][4], float* out, int n, int H, int W,
                               void* workspace, cudaStream_t stream, int dbg_layer = -1,
-                              float* dbg_dst = nullptr);
+                              float* dbg_dst = nullptr, int stack = kStackAll, int which = 0);
 
 int simt_forward(wn_handle* h, const float* const in[4], const int64_t in_strides[4][4], float* out,
-                 int n, int H, int W, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+                 int n, int H, int W, void* workspace, size_t workspace_bytes, cudaStream_t stream, int stack,
+                 int which) {
   if (workspace_bytes < simt_forward_workspace_bytes(n, H, W)) {
     set_error("forward workspace too small: %zu < %zu", workspace_bytes,
               simt_forward_workspace_bytes(n, H, W));
@@ -277,7 +278,7 @@ int simt_forward(wn_handle* h, const float* const in[4], const int64_t in_stride
     const float* sub[4];
     for (int t = 0; t < 4; t++) sub[t] = in[t] + (long long)n0 * in_strides[t][0];
     int rc = simt_forward_chunk(h, sub, in_strides, out + (size_t)n0 * 3 * H * W, cur, H, W,
-                                workspace, stream);
+                                workspace, stream, -1, nullptr, stack, which);
     if (rc) return rc;
   }
   return WN_OK;
@@ -295,7 +296,8 @@ int simt_debug_layer(wn_handle* h, const float* const in[4], const int64_t in_st
 
 static int simt_forward_chunk(wn_handle* h, const float* const in[4],
                               const int64_t in_strides[4][4], float* out, int n, int H, int W,
-                              void* workspace, cudaStream_t stream, int dbg_layer, float* dbg_dst) {
+                              void* workspace, cudaStream_t stream, int dbg_layer, float* dbg_dst, int stack,
+                              int which) {
   const size_t px = (size_t)n * H * W;
   const int plane = H * W;
   float* ws = (float*)(((uintptr_t)workspace + 255) / 256 * 256);
@@ -325,8 +327,8 @@ static int simt_forward_chunk(wn_handle* h, const float* const in[4],
   int rc;
   const float* cur = cat12;
   float* pp[2] = {bufA, bufB};
-  for (int i = 0; i < 8; i++) {
-    float* dst = i == 7 ? cm : pp[i & 1];
+  for (int i = 0; i < 8 && stack != kStackRefiners; i++) {
+    float* dst = i == 7 ? (stack == kStackCmg ? out : cm) : pp[i & 1];
     if ((rc = run_conv(h, i, cur, dst, n, H, W, i == 7 ? 2 : 1, stream))) return rc;
     cur = dst;
     if (dbg_layer == i) {
@@ -334,14 +336,16 @@ static int simt_forward_chunk(wn_handle* h, const float* const in[4],
       return WN_OK;
     }
   }
+  if (stack == kStackCmg) return WN_OK;  // ConfidenceMapGenerator.forward: the maps went straight to `out`
   // refiners: net.py:76-80, inputs cat[x, wb], cat[x, ce], cat[x, gc]
   for (int r = 0; r < 3; r++) {
+    if (stack == kStackRefiners && r != which) continue;  // Refiner.forward of one refiner
     {
       TimedScope ts(h, kSlotPack, stream);
       pair_kernel<<<dim3(gx, 6, n), 256, 0, stream>>>(cat12, pair, r + 1, plane);
       WN_LAUNCH_CHECK(h);
     }
-    float* refr = refined + (size_t)r * px * 3;
+    float* refr = stack == kStackRefiners ? out : refined + (size_t)r * px * 3;
     if ((rc = run_conv(h, 8 + 3 * r + 0, pair, r32a, n, H, W, 1, stream))) return rc;
     if ((rc = run_conv(h, 8 + 3 * r + 1, r32a, r32b, n, H, W, 1, stream))) return rc;
     if (dbg_layer == 8 || dbg_layer == 9) {  // (N,32,H,W) -> channels 32r.. of (N,96,H,W)
@@ -353,7 +357,7 @@ static int simt_forward_chunk(wn_handle* h, const float* const in[4],
     }
     if ((rc = run_conv(h, 8 + 3 * r + 2, r32b, refr, n, H, W, 1, stream))) return rc;
   }
-  if (dbg_layer >= 0) return WN_OK;
+  if (dbg_layer >= 0 || stack == kStackRefiners) return WN_OK;
   TimedScope ts(h, kSlotGate, stream);
   gate_sum_kernel<<<dim3((plane + 255) / 256, n), 256, 0, stream>>>(
       cm, refined, refined + px * 3, refined + 2 * px * 3, out, plane);

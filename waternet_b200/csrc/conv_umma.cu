@@ -136,6 +136,8 @@ static size_t stage8_bytes_total(const UmmaLayerSpec& s) {
 struct UmmaWeights {
   uint8_t* stages8[kNumUmmaLayers];  // fp8-correction weight images (has_f8_form layers)
   float* scale8[kNumUmmaLayers];     // {ws, 2^-9 / ws, max|w|, -}
+  int* overflow_dev;                 // sticky: an activation left the e4m3 range in the fp8-correction mode
+  int* overflow_host;                // pinned mirror, refreshed at the end of every forward of that mode
   uint8_t* stages[kNumUmmaLayers];
   float* bias[kNumUmmaLayers];
   float* dense;  // scratch for packing
@@ -158,7 +160,11 @@ int umma_pack_weights(wn_handle* h, const float* const* params, cudaStream_t str
     }
   }
   if (!h->umma->dense) WN_CUDA(cudaMalloc(&h->umma->dense, (size_t)224 * 128 * 49 * sizeof(float)));
+  if (!h->umma->overflow_dev) WN_CUDA(cudaMalloc(&h->umma->overflow_dev, sizeof(int)));
+  if (!h->umma->overflow_host) WN_CUDA(cudaHostAlloc(&h->umma->overflow_host, sizeof(int), cudaHostAllocDefault));
   UmmaWeights* u = h->umma;
+  *u->overflow_host = 0;  // new weights: the fp8-correction mode gets a fresh chance
+  WN_CUDA(cudaMemsetAsync(u->overflow_dev, 0, sizeof(int), stream));
   auto W = [&](int conv) { return params[2 * conv]; };
   auto B = [&](int conv) { return params[2 * conv + 1]; };
   for (int li = 0; li < kNumUmmaLayers; li++) {
@@ -221,6 +227,8 @@ void umma_free(wn_handle* h) {
     if (h->umma->scale8[i]) cudaFree(h->umma->scale8[i]);
   }
   if (h->umma->dense) cudaFree(h->umma->dense);
+  if (h->umma->overflow_dev) cudaFree(h->umma->overflow_dev);
+  if (h->umma->overflow_host) cudaFreeHost(h->umma->overflow_host);
   free(h->umma);
   h->umma = nullptr;
 }
@@ -228,15 +236,22 @@ void umma_free(wn_handle* h) {
 // bytes per pixel: act0 (16 ch) 64 | cmg ping/pong (128 ch) 512 each | ref ping/pong (96 ch) 384 each | cm 12
 static constexpr size_t kUmmaBytesPerPixel = 64 + 512 + 512 + 384 + 384 + 12;
 
-static int umma_chunk(int n, int h, int w) {
+// Images per pass: <= 8 Mi pixels (~15 GB of workspace) by default; wn_set_chunk_pixels lowers the cap
+// (tests force the multi-pass path on small batches with it; it never raises the workspace need).
+static constexpr long long kDefaultChunkPixels = 8ll << 20;
+static int umma_chunk(long long cap, int n, int h, int w) {
+  if (cap <= 0 || cap > kDefaultChunkPixels) cap = kDefaultChunkPixels;
   long long per = (long long)h * w;
-  long long nb = (8ll << 20) / (per > 0 ? per : 1);  // <= 8M pixels (~15 GB) per pass
+  long long nb = cap / (per > 0 ? per : 1);
   if (nb < 1) nb = 1;
   return nb < n ? (int)nb : n;
 }
+int umma_chunk_images(const wn_handle* h, int n, int height, int width) {
+  return umma_chunk(h ? h->chunk_pixels : 0, n, height, width);
+}
 
 size_t umma_forward_workspace_bytes(int n, int h, int w) {
-  return (size_t)umma_chunk(n, h, w) * h * w * kUmmaBytesPerPixel + 4096;
+  return (size_t)umma_chunk(0, n, h, w) * h * w * kUmmaBytesPerPixel + 4096;
 }
 
 // taps per weight stage of the layers where it is a tuning knob (A/B builds override with -D)
@@ -257,6 +272,7 @@ template <int KS, int CIN_PAD, int NPAD, int S, int AS, int EPI, int CONCAT = 0,
           int FMT = 0>
 static int launch_umma(wn_handle* h, int li, void* in_base, ConvArgs a, cudaStream_t stream) {
   const UmmaLayerSpec& spec = kSpecs[li];
+  if constexpr ((FMT & kFmtOut8) != 0) a.f8_overflow = h->umma->overflow_dev;
   if constexpr ((FMT & kFmtIn8) != 0) {  // fp8-correction form: its own weight images, [hi | fp8] layout, CTA pairs
     if (spec.ks != KS || spec.cinpad != CIN_PAD || spec.npad != NPAD || spec.nblk != NBLK || !has_f8_form(li)) {
       set_error("internal: fp8 launch configuration of layer %d does not match its packed weights", li);
@@ -310,13 +326,15 @@ __global__ void decode_planes_kernel(const uint4* __restrict__ src, float* __res
 // Where every layer's output lives.  Inference ping-pongs two buffers per stack; the training
 // forward (conv_bwd.cu) gives every activation its own buffer because the backward pass needs them.
 int umma_forward_layers(wn_handle* h, const float* const in[4], const int64_t st[4][4], float* out, int n, int H,
-                        int W, const FwdBuffers& b, cudaStream_t stream, int dbg_layer, float* dbg_dst, int scheme) {
-  PackInArgs pa;
-  for (int t = 0; t < 4; t++) {
-    pa.p[t] = in[t];
-    for (int k = 0; k < 4; k++) pa.s[t][k] = st[t][k];
-  }
-  {
+                        int W, const FwdBuffers& b, cudaStream_t stream, const FwdOpts& o) {
+  const int dbg_layer = o.dbg_layer;
+  float* const dbg_dst = o.dbg_dst;
+  if (!o.packed) {
+    PackInArgs pa;
+    for (int t = 0; t < 4; t++) {
+      pa.p[t] = in[t];
+      for (int k = 0; k < 4; k++) pa.s[t][k] = st[t][k];
+    }
     TimedScope ts(h, kSlotPack, stream);
     WN_CUDA(cudaMemsetAsync(b.exact_flag, 1, sizeof(int), stream));  // nonzero = "all inputs are 8-bit levels"
     pack_inputs_kernel<<<dim3((H * W + 255) / 256, n), 256, 0, stream>>>(pa, b.act0, H, W, b.exact_flag);
@@ -325,6 +343,7 @@ int umma_forward_layers(wn_handle* h, const float* const in[4], const int64_t st
   ConvArgs a;
   memset(&a, 0, sizeof(a));
   a.N = n; a.H = H; a.W = W;
+  a.run_if = o.run_if;
   int rc;
   auto dump = [&](int layer, const uint4* buf, int channels, int f8 = 0) -> bool {
     if (dbg_layer != layer) return false;
@@ -338,85 +357,99 @@ int umma_forward_layers(wn_handle* h, const float* const in[4], const int64_t st
     a.dst1.base = d1; a.dst1.planes_half = c1 / 8;
     a.split_c = c0; a.cout = c0 + c1;
   };
-  if (scheme == 1) {
+  // the last launch: refiner conv3 + ReLU, then (when the maps are given) the gated sum -> fp32 NCHW and/or
+  // ten2arr'd uint8 NHWC; refined_out optionally receives the three refined images
+  auto last = [&]() {
+    a.out_f32 = out;
+    a.out_u8 = o.out_u8;
+    a.cm = o.stack == kStackRefiners ? nullptr : b.cm;
+    a.refined_out = b.refined;
+  };
+  const bool want_cmg = o.stack != kStackRefiners, want_ref = o.stack != kStackCmg;
+  if (o.scheme == 1) {
     // fp8-correction scheme (inference): the tensor-bound layers replace the two bf16 correction passes by one
     // fp8 MMA (UmmaCfg FMT); a layer whose consumer is such a layer writes the hi + fp8-planes format
     constexpr int IN8 = kFmtIn8, OUT8 = kFmtOut8;
     act(b.a[1], 128, b.r[1], 96);
     a.skip_lo = b.exact_flag;
+    a.a_hi_only = o.hi_only ? 1 : 0;
     if ((rc = launch_umma<7, 16, 224, 1, 2, kEpiAct, 0, 1, 7, 2, OUT8>(h, kL1, b.act0, a, stream))) return rc;
     a.skip_lo = nullptr;
+    a.a_hi_only = 0;
     if (dump(0, b.a[1], 128, 1) || dump(8, b.r[1], 96, 1)) return WN_OK;
-    act(b.a[2], 128, nullptr, 0);
-    if ((rc = launch_umma<5, 128, 128, WN_F8_C23_S, WN_F8_C23_S == 1 ? 2 : 1, kEpiAct, 0, 1, 5, 2, IN8 | OUT8>(h, kC2, b.a[1], a, stream))) return rc;
-    if (dump(1, b.a[2], 128, 1)) return WN_OK;
-    act(b.a[3], 128, nullptr, 0);
-    if ((rc = launch_umma<3, 128, 128, WN_F8_C23_S, WN_F8_C23_S == 1 ? 2 : 1, kEpiAct, 0, 1, 9, 2, IN8>(h, kC3, b.a[2], a, stream))) return rc;
-    if (dump(2, b.a[3], 128)) return WN_OK;
-    act(b.a[4], 64, nullptr, 0);
-    if ((rc = launch_umma<1, 128, 64, 2, 2, kEpiAct, 1, 1, 1, 1, OUT8>(h, kC4, b.a[3], a, stream))) return rc;
-    if (dump(3, b.a[4], 64, 1)) return WN_OK;
-    act(b.a[5], 64, nullptr, 0);
-    if ((rc = launch_umma<7, 64, 64, 2, 2, kEpiAct, 0, 1, 7, 2, IN8 | OUT8>(h, kC5, b.a[4], a, stream))) return rc;
-    if (dump(4, b.a[5], 64, 1)) return WN_OK;
-    act(b.a[6], 64, nullptr, 0);
-    if ((rc = launch_umma<5, 64, 64, 2, 2, kEpiAct, 0, 1, 5, 2, IN8 | OUT8>(h, kC6, b.a[5], a, stream))) return rc;
-    if (dump(5, b.a[6], 64, 1)) return WN_OK;
-    act(b.a[7], 64, nullptr, 0);
-    if ((rc = launch_umma<3, 64, 64, 2, 2, kEpiAct, 0, 1, 9, 2, IN8>(h, kC7, b.a[6], a, stream))) return rc;
-    if (dump(6, b.a[7], 64)) return WN_OK;
-    a.out_f32 = dbg_layer == 7 ? dbg_dst : b.cm;
-    if ((rc = launch_umma<3, 64, 16, 4, 2, kEpiSigmoid, 1, 1, 9>(h, kC8, b.a[7], a, stream))) return rc;
-    if (dbg_layer == 7) return WN_OK;
+    if (want_cmg) {
+      act(b.a[2], 128, nullptr, 0);
+      if ((rc = launch_umma<5, 128, 128, WN_F8_C23_S, WN_F8_C23_S == 1 ? 2 : 1, kEpiAct, 0, 1, 5, 2, IN8 | OUT8>(h, kC2, b.a[1], a, stream))) return rc;
+      if (dump(1, b.a[2], 128, 1)) return WN_OK;
+      act(b.a[3], 128, nullptr, 0);
+      if ((rc = launch_umma<3, 128, 128, WN_F8_C23_S, WN_F8_C23_S == 1 ? 2 : 1, kEpiAct, 0, 1, 9, 2, IN8>(h, kC3, b.a[2], a, stream))) return rc;
+      if (dump(2, b.a[3], 128)) return WN_OK;
+      act(b.a[4], 64, nullptr, 0);
+      if ((rc = launch_umma<1, 128, 64, 2, 2, kEpiAct, 1, 1, 1, 1, OUT8>(h, kC4, b.a[3], a, stream))) return rc;
+      if (dump(3, b.a[4], 64, 1)) return WN_OK;
+      act(b.a[5], 64, nullptr, 0);
+      if ((rc = launch_umma<7, 64, 64, 2, 2, kEpiAct, 0, 1, 7, 2, IN8 | OUT8>(h, kC5, b.a[4], a, stream))) return rc;
+      if (dump(4, b.a[5], 64, 1)) return WN_OK;
+      act(b.a[6], 64, nullptr, 0);
+      if ((rc = launch_umma<5, 64, 64, 2, 2, kEpiAct, 0, 1, 5, 2, IN8 | OUT8>(h, kC6, b.a[5], a, stream))) return rc;
+      if (dump(5, b.a[6], 64, 1)) return WN_OK;
+      act(b.a[7], 64, nullptr, 0);
+      if ((rc = launch_umma<3, 64, 64, 2, 2, kEpiAct, 0, 1, 9, 2, IN8>(h, kC7, b.a[6], a, stream))) return rc;
+      if (dump(6, b.a[7], 64)) return WN_OK;
+      a.out_f32 = dbg_layer == 7 ? dbg_dst : b.cm;
+      if ((rc = launch_umma<3, 64, 16, 4, 2, kEpiSigmoid, 1, 1, 9>(h, kC8, b.a[7], a, stream))) return rc;
+      if (dbg_layer == 7) return WN_OK;
+    }
+    if (!want_ref) return WN_OK;
     act(b.r[2], 96, nullptr, 0);
     if ((rc = launch_umma<5, 96, 32, 2, 1, kEpiAct, 0, 3, 5, 2, IN8>(h, kR2, b.r[1], a, stream))) return rc;
     if (dump(9, b.r[2], 96)) return WN_OK;
-    a.out_f32 = out;
-    a.cm = b.cm;
-    a.refined_out = b.refined;
+    last();
     if ((rc = launch_umma<3, 96, 16, 4, 2, kEpiGate, 1, 1, 9>(h, kR3, b.r[2], a, stream))) return rc;
     return WN_OK;
   }
   // L1: 16 -> 128 (cmg) + 96 (refiners)
   act(b.a[1], 128, b.r[1], 96);
   a.skip_lo = b.exact_flag;
+  a.a_hi_only = o.hi_only ? 1 : 0;
   if ((rc = launch_umma<7, 16, 224, WN_L1_S, WN_L1_S == 1 ? 2 : 1, kEpiAct, 0, 1, WN_CG_L1R2 == 2 ? 7 : WN_L1_TPS, WN_CG_L1R2>(h, kL1, b.act0, a, stream))) return rc;
   a.skip_lo = nullptr;
+  a.a_hi_only = 0;
   if (dump(0, b.a[1], 128) || dump(8, b.r[1], 96)) return WN_OK;
-  act(b.a[2], 128, nullptr, 0);
-  if ((rc = launch_umma<5, 128, 128, 2, WN_C23_CONCAT ? 1 : 2, kEpiAct, WN_C23_CONCAT, 1, 5, WN_CG>(h, kC2, b.a[1], a, stream))) return rc;
-  if (dump(1, b.a[2], 128)) return WN_OK;
-  act(b.a[3], 128, nullptr, 0);
-  if ((rc = launch_umma<3, 128, 128, 2, WN_C23_CONCAT ? 1 : 2, kEpiAct, WN_C23_CONCAT, 1, WN_C3_TPS, WN_CG>(h, kC3, b.a[2], a, stream))) return rc;
-  if (dump(2, b.a[3], 128)) return WN_OK;
-  act(b.a[4], 64, nullptr, 0);
-  if ((rc = launch_umma<1, 128, 64, 2, 2, kEpiAct, 1>(h, kC4, b.a[3], a, stream))) return rc;
-  if (dump(3, b.a[4], 64)) return WN_OK;
-  act(b.a[5], 64, nullptr, 0);
-  if ((rc = launch_umma<7, 64, 64, 2, 2, kEpiAct, 1, 1, 7, WN_CG>(h, kC5, b.a[4], a, stream))) return rc;
-  if (dump(4, b.a[5], 64)) return WN_OK;
-  act(b.a[6], 64, nullptr, 0);
-  if ((rc = launch_umma<5, 64, 64, 2, 2, kEpiAct, 1, 1, 5, WN_CG>(h, kC6, b.a[5], a, stream))) return rc;
-  if (dump(5, b.a[6], 64)) return WN_OK;
-  act(b.a[7], 64, nullptr, 0);
-  if ((rc = launch_umma<3, 64, 64, 2, 2, kEpiAct, 1, 1, WN_C7_TPS, WN_CG>(h, kC7, b.a[6], a, stream))) return rc;
-  if (dump(6, b.a[7], 64)) return WN_OK;
-  a.out_f32 = dbg_layer == 7 ? dbg_dst : b.cm;
-  if ((rc = launch_umma<3, 64, 16, 4, 2, kEpiSigmoid, 1, 1, 9>(h, kC8, b.a[7], a, stream))) return rc;
-  if (dbg_layer == 7) return WN_OK;
+  if (want_cmg) {
+    act(b.a[2], 128, nullptr, 0);
+    if ((rc = launch_umma<5, 128, 128, 2, WN_C23_CONCAT ? 1 : 2, kEpiAct, WN_C23_CONCAT, 1, 5, WN_CG>(h, kC2, b.a[1], a, stream))) return rc;
+    if (dump(1, b.a[2], 128)) return WN_OK;
+    act(b.a[3], 128, nullptr, 0);
+    if ((rc = launch_umma<3, 128, 128, 2, WN_C23_CONCAT ? 1 : 2, kEpiAct, WN_C23_CONCAT, 1, WN_C3_TPS, WN_CG>(h, kC3, b.a[2], a, stream))) return rc;
+    if (dump(2, b.a[3], 128)) return WN_OK;
+    act(b.a[4], 64, nullptr, 0);
+    if ((rc = launch_umma<1, 128, 64, 2, 2, kEpiAct, 1>(h, kC4, b.a[3], a, stream))) return rc;
+    if (dump(3, b.a[4], 64)) return WN_OK;
+    act(b.a[5], 64, nullptr, 0);
+    if ((rc = launch_umma<7, 64, 64, 2, 2, kEpiAct, 1, 1, 7, WN_CG>(h, kC5, b.a[4], a, stream))) return rc;
+    if (dump(4, b.a[5], 64)) return WN_OK;
+    act(b.a[6], 64, nullptr, 0);
+    if ((rc = launch_umma<5, 64, 64, 2, 2, kEpiAct, 1, 1, 5, WN_CG>(h, kC6, b.a[5], a, stream))) return rc;
+    if (dump(5, b.a[6], 64)) return WN_OK;
+    act(b.a[7], 64, nullptr, 0);
+    if ((rc = launch_umma<3, 64, 64, 2, 2, kEpiAct, 1, 1, WN_C7_TPS, WN_CG>(h, kC7, b.a[6], a, stream))) return rc;
+    if (dump(6, b.a[7], 64)) return WN_OK;
+    a.out_f32 = dbg_layer == 7 ? dbg_dst : b.cm;
+    if ((rc = launch_umma<3, 64, 16, 4, 2, kEpiSigmoid, 1, 1, 9>(h, kC8, b.a[7], a, stream))) return rc;
+    if (dbg_layer == 7) return WN_OK;
+  }
+  if (!want_ref) return WN_OK;
   act(b.r[2], 96, nullptr, 0);
   if ((rc = launch_umma<5, 96, 32, WN_R2_S, WN_R2_S == 1 ? 2 : 1, kEpiAct, 1, 3, WN_R2_TPS, WN_CG_L1R2>(h, kR2, b.r[1], a, stream))) return rc;
   if (dump(9, b.r[2], 96)) return WN_OK;
-  a.out_f32 = out;
-  a.cm = b.cm;
-  a.refined_out = b.refined;
+  last();
   if ((rc = launch_umma<3, 96, 16, 4, 2, kEpiGate, 1, 1, 9>(h, kR3, b.r[2], a, stream))) return rc;
   return WN_OK;
 }
 
-static int umma_forward_chunk(wn_handle* h, const float* const in[4], const int64_t st[4][4], float* out, int n,
-                              int H, int W, void* workspace, cudaStream_t stream, int scheme, int dbg_layer = -1,
-                              float* dbg_dst = nullptr) {
+// Workspace carve-up of one pass (<= umma_chunk images).
+static FwdBuffers carve(void* workspace, int n, int H, int W) {
   const size_t px = (size_t)n * H * W;
   uint8_t* ws = (uint8_t*)(((uintptr_t)workspace + 1023) / 1024 * 1024);
   uint4* cmgAB[2];
@@ -433,22 +466,55 @@ static int umma_forward_chunk(wn_handle* h, const float* const in[4], const int6
   for (int l = 1; l <= 7; l++) b.a[l] = cmgAB[(l - 1) & 1];
   b.r[1] = refAB[0];
   b.r[2] = refAB[1];
-  return umma_forward_layers(h, in, st, out, n, H, W, b, stream, dbg_layer, dbg_dst, scheme);
+  return b;
+}
+
+// One pass in `scheme`; in the fp8-correction scheme the bf16x3 chain of the same batch is enqueued right behind
+// it, every launch conditional on the sticky e4m3 range flag (ConvArgs::run_if): a batch whose activations left
+// the e4m3 range is recomputed within the same call, nobody ever sees the degraded result.
+static int umma_pass(wn_handle* h, const float* const in[4], const int64_t st[4][4], float* out, int n, int H, int W,
+                     const FwdBuffers& b, cudaStream_t stream, FwdOpts o) {
+  int rc = umma_forward_layers(h, in, st, out, n, H, W, b, stream, o);
+  if (rc || o.scheme != 1 || o.dbg_layer >= 0) return rc;
+  o.scheme = 0;
+  o.packed = true;  // act0 (and the exact-levels flag) of this batch are still in place
+  o.run_if = h->umma->overflow_dev;
+  Timing* timing = h->timing;  // the conditional launches are not part of the per-kernel timing record
+  h->timing = nullptr;
+  rc = umma_forward_layers(h, in, st, out, n, H, W, b, stream, o);
+  h->timing = timing;
+  return rc;
 }
 
 int umma_debug_layer(wn_handle* h, const float* const in[4], const int64_t in_strides[4][4], int n, int H, int W,
                      int layer, float* dst, void* workspace, size_t workspace_bytes, cudaStream_t stream, int scheme) {
-  if (!h->umma || umma_chunk(n, H, W) != n || workspace_bytes < umma_forward_workspace_bytes(n, H, W)) {
+  if (!h->umma || umma_chunk(0, n, H, W) != n || workspace_bytes < umma_forward_workspace_bytes(n, H, W)) {
     set_error("debug layer dump: weights not packed, batch too large for one pass or workspace too small");
     return WN_E_WORKSPACE;
   }
   int rc = get_encoder();
   if (rc) return rc;
-  return umma_forward_chunk(h, in, in_strides, nullptr, n, H, W, workspace, stream, scheme, layer, dst);
+  FwdOpts o;
+  o.scheme = scheme;
+  o.dbg_layer = layer;
+  o.dbg_dst = dst;
+  return umma_forward_layers(h, in, in_strides, nullptr, n, H, W, carve(workspace, n, H, W), stream, o);
+}
+
+// fp8-correction mode: once an activation has left the e4m3 range (sticky flag, mirrored to the host at the end
+// of every call) this handle keeps to the bf16x3 kernels until new weights are packed.
+static int effective_scheme(wn_handle* h, int scheme) {
+  return (scheme == 1 && *h->umma->overflow_host) ? 0 : scheme;
+}
+static int mirror_overflow(wn_handle* h, int scheme, cudaStream_t stream) {
+  if (scheme == 1)
+    WN_CUDA(cudaMemcpyAsync(h->umma->overflow_host, h->umma->overflow_dev, sizeof(int), cudaMemcpyDeviceToHost, stream));
+  return WN_OK;
 }
 
 int umma_forward(wn_handle* h, const float* const in[4], const int64_t in_strides[4][4], float* out, int n, int H,
-                 int W, void* workspace, size_t workspace_bytes, cudaStream_t stream, int scheme) {
+                 int W, void* workspace, size_t workspace_bytes, cudaStream_t stream, int scheme, int stack,
+                 float* refined) {
   if (!h->umma) {
     set_error("tensor-core weights have not been packed");
     return WN_E_STATE;
@@ -459,15 +525,69 @@ int umma_forward(wn_handle* h, const float* const in[4], const int64_t in_stride
   }
   int rc = get_encoder();
   if (rc) return rc;
-  const int nb = umma_chunk(n, H, W);
+  scheme = effective_scheme(h, scheme);
+  const int nb = umma_chunk(h->chunk_pixels, n, H, W);
   for (int n0 = 0; n0 < n; n0 += nb) {
     const int cur = n - n0 < nb ? n - n0 : nb;
     const float* sub[4];
     for (int t = 0; t < 4; t++) sub[t] = in[t] + (long long)n0 * in_strides[t][0];
-    rc = umma_forward_chunk(h, sub, in_strides, out + (size_t)n0 * 3 * H * W, cur, H, W, workspace, stream, scheme);
+    FwdBuffers b = carve(workspace, cur, H, W);
+    FwdOpts o;
+    o.scheme = scheme;
+    o.stack = stack;
+    float* dst = out + (size_t)n0 * 3 * H * W;
+    if (stack == kStackCmg) b.cm = dst;                                   // the maps are the result
+    if (stack == kStackRefiners) { b.refined = refined + (size_t)n0 * 9 * H * W; dst = nullptr; }
+    rc = umma_pass(h, sub, in_strides, dst, cur, H, W, b, stream, o);
     if (rc) return rc;
   }
-  return WN_OK;
+  return mirror_overflow(h, scheme, stream);
 }
+
+// preprocess -> forward -> ten2arr without materialising the four fp32 input tensors or the fp32 output:
+// the per-pixel preprocess kernel writes the first layer's operand planes (8-bit levels are exact in bf16: hi
+// planes only), the last launch's epilogue writes uint8 NHWC (hubconf.py:8-34).
+size_t umma_enhance_workspace_bytes(int n, int h, int w) {
+  const int nb = umma_chunk(0, n, h, w);
+  return umma_forward_workspace_bytes(n, h, w) + (preprocess_workspace_bytes(nb, h, w) + 255) / 256 * 256 + 1024;
+}
+
+int umma_enhance_u8(wn_handle* h, const uint8_t* rgb, uint8_t* out_u8, float* out_f32, int n, int H, int W,
+                    void* workspace, size_t workspace_bytes, cudaStream_t stream, int scheme) {
+  if (!h->umma) {
+    set_error("tensor-core weights have not been packed");
+    return WN_E_STATE;
+  }
+  if (workspace_bytes < umma_enhance_workspace_bytes(n, H, W)) {
+    set_error("enhance workspace too small: %zu < %zu", workspace_bytes, umma_enhance_workspace_bytes(n, H, W));
+    return WN_E_WORKSPACE;
+  }
+  int rc = get_encoder();
+  if (rc) return rc;
+  scheme = effective_scheme(h, scheme);
+  const int nb = umma_chunk(h->chunk_pixels, n, H, W);
+  uint8_t* pre_ws = (uint8_t*)(((uintptr_t)workspace + 255) / 256 * 256);
+  const size_t pre_b = (preprocess_workspace_bytes(nb, H, W) + 255) / 256 * 256;
+  void* fwd_ws = pre_ws + pre_b;
+  const int64_t none[4][4] = {};
+  const float* no_in[4] = {nullptr, nullptr, nullptr, nullptr};
+  for (int n0 = 0; n0 < n; n0 += nb) {
+    const int cur = n - n0 < nb ? n - n0 : nb;
+    FwdBuffers b = carve(fwd_ws, cur, H, W);
+    WN_CUDA(cudaMemsetAsync(b.exact_flag, 1, sizeof(int), stream));
+    rc = preprocess_u8_planes(h, rgb + (size_t)n0 * H * W * 3, cur, H, W, b.act0, pre_ws, pre_b, stream);
+    if (rc) return rc;
+    FwdOpts o;
+    o.scheme = scheme;
+    o.packed = true;
+    o.hi_only = true;
+    o.out_u8 = out_u8 + (size_t)n0 * H * W * 3;
+    rc = umma_pass(h, no_in, none, out_f32 ? out_f32 + (size_t)n0 * 3 * H * W : nullptr, cur, H, W, b, stream, o);
+    if (rc) return rc;
+  }
+  return mirror_overflow(h, scheme, stream);
+}
+
+int umma_f8_overflowed(const wn_handle* h) { return h->umma && h->umma->overflow_host ? *h->umma->overflow_host : 0; }
 
 }  // namespace wn

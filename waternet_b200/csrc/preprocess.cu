@@ -11,10 +11,11 @@
 //                  white-balance LUT (float64 quantiles as numpy computes them)
 //   apply_kernel   one per-pixel pass: WB LUT, gamma LUT, RGB->Lab->CLAHE blend->
 //                  Lab->RGB in OpenCV's 8-bit fixed point, u/255, writes the four
-//                  fp32 NCHW tensors (and/or u8 NHWC images)
+//                  fp32 NCHW tensors and/or u8 NHWC images and/or -- the end-to-end path --
+//                  the first conv layer's operand planes (bf16 levels, 32 B/px)
 //
-// HBM-bound: 3 B/px read twice, 48 B/px written (fp32 tensors) -- see DESIGN.md.
-// Bit-exact with the reference's numpy/OpenCV output (tests/test_preprocess_gpu.py).
+// HBM-bound: 3 B/px read twice, 48 B/px (fp32 tensors) or 32 B/px (operand planes) written -- see DESIGN.md.
+// Bit-exact with the reference's numpy/OpenCV output (tests/test_gpu_parity.py::test_preprocess_bit_exact_*).
 #include <math.h>
 #include <string.h>
 
@@ -297,7 +298,19 @@ constexpr int kApplyIters = 16;
 struct ApplyOut {
   float* f32[4];    // x, wb, he, gc  -- NCHW planes, may be null
   uint8_t* u8[3];   // wb, he, gc     -- NHWC, may be null
+  uint4* planes;    // may be null: [n][2][H*W] x 16 B, the first conv layer's operand planes (8 bf16 levels each):
+                    // torch.cat([x, wb, he, gc], 1) (net.py:46) as plane 0 = x.rgb wb.rgb he.rg, plane 1 = he.b gc.rgb 0 0 0 0
 };
+// bf16 bit patterns of two integer levels 0..255 (exact: 8 significant bits), first level in the low half
+__device__ __forceinline__ uint32_t bf16_levels2(int a, int b) {
+  return (__float_as_uint((float)a) >> 16) | (__float_as_uint((float)b) & 0xffff0000u);
+}
+__device__ __forceinline__ void store_level_planes(uint4* planes, size_t n, size_t plane, size_t pix, const int* lv) {
+  uint4* p = planes + n * 2 * plane + pix;
+  p[0] = make_uint4(bf16_levels2(lv[0], lv[1]), bf16_levels2(lv[2], lv[3]), bf16_levels2(lv[4], lv[5]),
+                    bf16_levels2(lv[6], lv[7]));
+  p[plane] = make_uint4(bf16_levels2(lv[8], lv[9]), bf16_levels2(lv[10], lv[11]), 0u, 0u);
+}
 
 template <bool VEC4>
 __global__ void __launch_bounds__(256)
@@ -384,6 +397,10 @@ apply_kernel(const uint8_t* __restrict__ rgb, int H, int W, int th, int tw,
           *reinterpret_cast<float4*>(out.f32[t] + o + (size_t)c * plane) =
               make_float4(s_div[lv[0][t * 3 + c]], s_div[lv[1][t * 3 + c]], s_div[lv[2][t * 3 + c]], s_div[lv[3][t * 3 + c]]);
       }
+      if (out.planes) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) store_level_planes(out.planes, n, plane, pix + k, lv[k]);
+      }
       const size_t o8 = ((size_t)n * plane + pix) * 3;
 #pragma unroll
       for (int t = 0; t < 3; t++) {
@@ -410,6 +427,7 @@ apply_kernel(const uint8_t* __restrict__ rgb, int H, int W, int th, int tw,
         float* q = out.f32[t] + o;
         q[0] = s_div[lv[t * 3]]; q[plane] = s_div[lv[t * 3 + 1]]; q[2 * (size_t)plane] = s_div[lv[t * 3 + 2]];
       }
+      if (out.planes) store_level_planes(out.planes, n, plane, pix, lv);
       const size_t o8 = ((size_t)n * plane + pix) * 3;
 #pragma unroll
       for (int t = 0; t < 3; t++) {
@@ -476,9 +494,26 @@ size_t preprocess_workspace_bytes(int n, int, int) {
   return b;
 }
 
+static int preprocess_run(wn_handle* h, const uint8_t* rgb, int n, int H, int W, float* x, float* wb,
+                          float* he, float* gc, uint8_t* wb_u8, uint8_t* he_u8, uint8_t* gc_u8, uint4* planes,
+                          void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
 int preprocess_u8(wn_handle* h, const uint8_t* rgb, int n, int H, int W, float* x, float* wb,
                   float* he, float* gc, uint8_t* wb_u8, uint8_t* he_u8, uint8_t* gc_u8,
                   void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  return preprocess_run(h, rgb, n, H, W, x, wb, he, gc, wb_u8, he_u8, gc_u8, nullptr, workspace, workspace_bytes,
+                        stream);
+}
+
+int preprocess_u8_planes(wn_handle* h, const uint8_t* rgb, int n, int H, int W, uint4* planes, void* workspace,
+                         size_t workspace_bytes, cudaStream_t stream) {
+  return preprocess_run(h, rgb, n, H, W, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, planes,
+                        workspace, workspace_bytes, stream);
+}
+
+static int preprocess_run(wn_handle* h, const uint8_t* rgb, int n, int H, int W, float* x, float* wb,
+                          float* he, float* gc, uint8_t* wb_u8, uint8_t* he_u8, uint8_t* gc_u8, uint4* planes,
+                          void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   if (workspace_bytes < preprocess_workspace_bytes(n, H, W)) {
     set_error("preprocess workspace too small: %zu < %zu", workspace_bytes,
               preprocess_workspace_bytes(n, H, W));
@@ -522,6 +557,7 @@ int preprocess_u8(wn_handle* h, const uint8_t* rgb, int n, int H, int W, float* 
   ApplyOut ao;
   ao.f32[0] = x; ao.f32[1] = wb; ao.f32[2] = he; ao.f32[3] = gc;
   ao.u8[0] = wb_u8; ao.u8[1] = he_u8; ao.u8[2] = gc_u8;
+  ao.planes = planes;
   TimedScope ts(h, kSlotApply, stream);
   // vector path: 4 pixels per thread needs 4-pixel groups that do not straddle images (and aligned bases)
   const bool vec4 = (H * W) % 4 == 0 && ((uintptr_t)rgb % 4) == 0 && ((uintptr_t)x % 16) == 0 &&
@@ -537,6 +573,92 @@ int preprocess_u8(wn_handle* h, const uint8_t* rgb, int n, int H, int W, float* 
                                                                                     clahe_lut, wb_lut, ao);
   }
   WN_LAUNCH_CHECK(h);
+  return WN_OK;
+}
+
+// ---------------------------------------------------------------------------
+// cv2.resize(img, (w, h)) of 8-bit images, default INTER_LINEAR (training_utils.py:94-103), batched: every source
+// image has its own size, all land in one (N, dh, dw, 3) batch.  OpenCV imgproc/src/resize.cpp arithmetic, bit
+// exact (oracle/preprocess.py::resize_linear_u8 is the CPU restatement):
+//   fx = (float)((dx + 0.5) * scale - 0.5), scale = 1 / ((double)dsize / ssize); sx = floor(fx); fx -= sx;
+//   x: an index outside [0, ssize-1) is clamped with weights (1, 0); y: only the row index is clamped;
+//   weights = saturate_cast<short>(w * 2048) (round half to even); horizontal pass in int32,
+//   vertical pass (((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2;
+//   an exact 2x reduction in both directions is INTER_AREA ((a + b + c + d + 2) >> 2); equal sizes copy.
+// swap_rb folds the BGR -> RGB conversion that follows the resize in the reference (a per-channel permutation
+// commutes with a per-channel resize).
+// ---------------------------------------------------------------------------
+constexpr int kResizeGroup = 96;
+struct ResizeBatch {
+  const uint8_t* src[kResizeGroup];
+  int h[kResizeGroup], w[kResizeGroup];
+};
+__device__ __forceinline__ void resize_coeff(int d, int ssize, int dsize, bool clamp, int& idx, int& w0, int& w1) {
+  const double scale = __ddiv_rn(1.0, __ddiv_rn((double)dsize, (double)ssize));
+  float f = (float)__dsub_rn(__dmul_rn(__dadd_rn((double)d, 0.5), scale), 0.5);
+  int s = (int)floorf(f);
+  f = __fsub_rn(f, (float)s);
+  if (clamp) {
+    if (s < 0) { f = 0.f; s = 0; }
+    if (s >= ssize - 1) { f = 0.f; s = ssize - 1; }
+  }
+  idx = s;
+  w0 = (int)rintf(__fmul_rn(__fsub_rn(1.0f, f), 2048.0f));
+  w1 = (int)rintf(__fmul_rn(f, 2048.0f));
+}
+__global__ void __launch_bounds__(256)
+resize_linear_u8_kernel(const ResizeBatch batch, uint8_t* __restrict__ dst, int dh, int dw, int swap_rb, int n0) {
+  const int i = blockIdx.y;
+  const int pix = blockIdx.x * 256 + threadIdx.x;
+  if (pix >= dh * dw) return;
+  const int dy = pix / dw, dx = pix - dy * dw;
+  const uint8_t* __restrict__ src = batch.src[i];
+  const int sh = batch.h[i], sw = batch.w[i];
+  uint8_t* o = dst + ((size_t)(n0 + i) * dh * dw + pix) * 3;
+  int v[3];
+  if (sh == dh && sw == dw) {
+    const uint8_t* p = src + (size_t)pix * 3;
+    v[0] = p[0]; v[1] = p[1]; v[2] = p[2];
+  } else if (sh == 2 * dh && sw == 2 * dw) {
+    const uint8_t* p = src + ((size_t)(2 * dy) * sw + 2 * dx) * 3;
+    const uint8_t* q = p + (size_t)sw * 3;
+#pragma unroll
+    for (int c = 0; c < 3; c++) v[c] = ((int)p[c] + p[3 + c] + q[c] + q[3 + c] + 2) >> 2;
+  } else {
+    int xi, xa0, xa1, yi, yb0, yb1;
+    resize_coeff(dx, sw, dw, true, xi, xa0, xa1);
+    resize_coeff(dy, sh, dh, false, yi, yb0, yb1);
+    const int xi1 = min(xi + 1, sw - 1);
+    const int y0 = min(max(yi, 0), sh - 1), y1 = min(max(yi + 1, 0), sh - 1);
+    const uint8_t* r0 = src + (size_t)y0 * sw * 3;
+    const uint8_t* r1 = src + (size_t)y1 * sw * 3;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      const int s0 = (int)r0[xi * 3 + c] * xa0 + (int)r0[xi1 * 3 + c] * xa1;
+      const int s1 = (int)r1[xi * 3 + c] * xa0 + (int)r1[xi1 * 3 + c] * xa1;
+      const int t = (((yb0 * (s0 >> 4)) >> 16) + ((yb1 * (s1 >> 4)) >> 16) + 2) >> 2;
+      v[c] = min(max(t, 0), 255);
+    }
+  }
+  if (swap_rb) { const int t = v[0]; v[0] = v[2]; v[2] = t; }
+  o[0] = (uint8_t)v[0]; o[1] = (uint8_t)v[1]; o[2] = (uint8_t)v[2];
+}
+
+int resize_u8(wn_handle* h, const uint8_t* const* src, const int* src_h, const int* src_w, int n, uint8_t* dst,
+              int dh, int dw, int swap_rb, cudaStream_t stream) {
+  for (int n0 = 0; n0 < n; n0 += kResizeGroup) {
+    const int cur = n - n0 < kResizeGroup ? n - n0 : kResizeGroup;
+    ResizeBatch b;
+    for (int i = 0; i < cur; i++) {
+      if (!src[n0 + i] || src_h[n0 + i] <= 0 || src_w[n0 + i] <= 0) {
+        set_error("wn_resize_u8: image %d is null or empty", n0 + i);
+        return WN_E_INVALID;
+      }
+      b.src[i] = src[n0 + i]; b.h[i] = src_h[n0 + i]; b.w[i] = src_w[n0 + i];
+    }
+    resize_linear_u8_kernel<<<dim3((dh * dw + 255) / 256, cur), 256, 0, stream>>>(b, dst, dh, dw, swap_rb, n0);
+    WN_LAUNCH_CHECK(h);
+  }
   return WN_OK;
 }
 

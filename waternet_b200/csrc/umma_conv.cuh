@@ -330,11 +330,15 @@ struct ConvArgs {
   int split_c;          // channels [0, split_c) -> dst0, [split_c, cout) -> dst1
   int cout;             // valid output channels
   // kEpiSigmoid / kEpiGate
-  float* out_f32;       // [n][3][H][W]
-  const float* cm;      // [n][3][H][W] (gate)
+  float* out_f32;       // [n][3][H][W] (gate: optional)
+  const float* cm;      // [n][3][H][W] (gate; null = no gated sum, only refined_out is produced)
+  uint8_t* out_u8;      // gate, optional: ten2arr of the result (clip [0,1], *255, truncate), uint8 NHWC
   // optional: *skip_lo != 0 means every input value is exactly representable in the hi plane
   // (8-bit image levels), so the a_lo x w_hi pass contributes nothing and is not issued
   const int* skip_lo;
+  // the input planes hold exact 8-bit levels and only the hi planes exist (written by the preprocess kernel):
+  // the halo loads fetch two planes per chunk instead of four and the a_lo pass is never issued
+  int a_hi_only;
   // kEpiGate, training only: also store the three refined images (post-ReLU), fp32 [n][9][H][W]
   float* refined_out;
   // kEpiDgrad: saved forward activation (planes) whose zeros gate the gradient
@@ -342,6 +346,12 @@ struct ConvArgs {
   int mask_planes_half;
   // fp8 correction scheme (FMT bit 0): dequantisation factor 2^-9 / ws of the second accumulator
   const float* f8_scale;
+  // FMT bit 1: sticky device flag raised when an activation leaves the e4m3 range (its correction terms would
+  // saturate in the consumer's fp8 pass); the host side then re-runs the batch with the bf16x3 kernels
+  int* f8_overflow;
+  // conditional launch: when non-null and *run_if == 0 the kernel returns at once (the bf16x3 re-run of a
+  // batch is enqueued unconditionally behind the fp8-correction pass and only does work if the flag is up)
+  const int* run_if;
   // bring-up only (wn_debug_set_flags): bit 0 = epilogue skips its global stores (bit 6: also its arithmetic; bit 7: shared-memory stores instead), bit 1 = weight stages
   // are not re-fetched after the first ring fill, bit 2 = the a_lo / a_hi x w_lo passes are not issued,
   // bit 3 = no early probe of the next weight barrier.
@@ -368,6 +378,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
   using C = UmmaCfg<KS, CIN_PAD, NPAD, S, AS, CONCAT, NBLK, TPS, CG, FMT>;
   constexpr bool F8IN = C::F8IN, DUAL = C::DUAL, OUT8 = (FMT & kFmtOut8) != 0;
   static_assert(!OUT8 || EPI == kEpiAct, "fp8 planes are written by the activation epilogue only");
+  if (g.run_if != nullptr && *reinterpret_cast<const volatile int*>(g.run_if) == 0) return;  // whole grid alike
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* a_stages = smem;
@@ -433,10 +444,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
         for (int c = 0; c < C::NCHUNK; c++) {
           mbar_wait(&a_empty[stage], phase ^ 1);
           uint8_t* dst = a_stages + stage * C::A_STAGE;
-          mbar_expect_tx(&a_full[stage], 4 * C::PLANE_BYTES);
+          mbar_expect_tx(&a_full[stage], (g.a_hi_only ? 2 : 4) * C::PLANE_BYTES);
           tma_load_5d(dst, &tmap_in, &a_full[stage], 0, x0, y0, 2 * c, n);
-          tma_load_5d(dst + 2 * C::PLANE_BYTES, &tmap_in, &a_full[stage], 0, x0, y0,
-                      g.in_planes_half + 2 * c, n);
+          if (!g.a_hi_only)
+            tma_load_5d(dst + 2 * C::PLANE_BYTES, &tmap_in, &a_full[stage], 0, x0, y0,
+                        g.in_planes_half + 2 * c, n);
           if (++stage == C::NA) { stage = 0; phase ^= 1; }
         }
       }
@@ -519,7 +531,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
       constexpr uint32_t b_wlo_off = CG == 2 ? (uint32_t)NPAD : (uint32_t)(2 * NPAD * 16 >> 4);
       int astage = 0, bstage = 0, acc = 0;
       uint32_t aphase = 0, bphase = 0, tphase = 0;
-      const bool skip_lo = (g.skip_lo != nullptr && *g.skip_lo != 0) || (g.dbg & 4);
+      const bool skip_lo = (g.skip_lo != nullptr && *g.skip_lo != 0) || g.a_hi_only || (g.dbg & 4);
       bool b_ready = false;  // result of the early probe of the upcoming weight stage
       if constexpr (C::WRAP) {
         int slot = 0;  // position of the next tap inside its weight group
@@ -724,11 +736,15 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
                 for (int q = 0; q < GC; q += 16) {
                   const int ch = c0 + q;
                   uint32_t hi[8], l8[4], h8[4];
+                  float vmax = 0.f;
 #pragma unroll
                   for (int j = 0; j < 16; j += 4) {
                     float v[4], r[4];
 #pragma unroll
-                    for (int t = 0; t < 4; t++) v[t] = fmaxf(f[q + j + t] + s_bias[ch + j + t], 0.f);
+                    for (int t = 0; t < 4; t++) {
+                      v[t] = fmaxf(f[q + j + t] + s_bias[ch + j + t], 0.f);
+                      vmax = fmaxf(vmax, v[t]);
+                    }
 #pragma unroll
                     for (int t = 0; t < 4; t += 2) {
                       const __nv_bfloat162 h = __floats2bfloat162_rn(v[t], v[t + 1]);
@@ -740,6 +756,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
                     l8[j >> 2] = pack_e4m3x4(r[0], r[1], r[2], r[3]);
                     h8[j >> 2] = pack_e4m3x4(v[0], v[1], v[2], v[3]);
                   }
+                  // e4m3 range guard (|v| <= 448); written as !(<=) so that a NaN raises the flag too
+                  if (!(vmax <= 448.f) && g.f8_overflow) atomicOr(g.f8_overflow, 1);
                   const bool second = ch >= g.split_c;
                   const ActDst& d = second ? g.dst1 : g.dst0;
                   const int chl = second ? ch - g.split_c : ch;
@@ -823,11 +841,22 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
 #pragma unroll
                 for (int j = 0; j < 9; j++) g.refined_out[(size_t)n * 9 * hw + (size_t)gy * g.W + gx + j * hw] = r[j];
               }
-              const float c0 = g.cm[o], c1 = g.cm[o + hw], c2 = g.cm[o + 2 * hw];
+              if (g.cm) {
+                const float c0 = g.cm[o], c1 = g.cm[o + hw], c2 = g.cm[o + 2 * hw];
+                float v[3];
 #pragma unroll
-              for (int c = 0; c < 3; c++)
-                g.out_f32[o + c * hw] =
-                    __fadd_rn(__fadd_rn(__fmul_rn(r[c], c0), __fmul_rn(r[3 + c], c1)), __fmul_rn(r[6 + c], c2));
+                for (int c = 0; c < 3; c++)
+                  v[c] = __fadd_rn(__fadd_rn(__fmul_rn(r[c], c0), __fmul_rn(r[3 + c], c1)), __fmul_rn(r[6 + c], c2));
+                if (g.out_f32) {
+#pragma unroll
+                  for (int c = 0; c < 3; c++) g.out_f32[o + c * hw] = v[c];
+                }
+                if (g.out_u8) {  // ten2arr (hubconf.py:24-34): clip to [0,1], *255, truncate; NHWC
+                  uint8_t* q = g.out_u8 + ((size_t)n * hw + (size_t)gy * g.W + gx) * 3;
+#pragma unroll
+                  for (int c = 0; c < 3; c++) q[c] = (uint8_t)(int)__fmul_rn(fminf(fmaxf(v[c], 0.0f), 1.0f), 255.0f);
+                }
+              }
             }
           }
         }
@@ -1051,7 +1080,7 @@ static int launch_conv(wn_handle* h, int slot, const uint8_t* wpk, const float* 
   int rc = get_encoder();
   if (rc) return rc;
   CUtensorMap tm;
-  rc = make_tmap(&tm, in_base, 2 * (CIN_PAD / 8), a.N, a.H, a.W, C::HALO_W, C::HALO_H);
+  rc = make_tmap(&tm, in_base, (a.a_hi_only ? 1 : 2) * (CIN_PAD / 8), a.N, a.H, a.W, C::HALO_W, C::HALO_H);
   if (rc) return rc;
   a.wpk = wpk;
   a.bias = bias;

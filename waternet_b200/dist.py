@@ -49,6 +49,31 @@ def all_gather_batch(local: torch.Tensor, counts: List[int], group=None) -> torc
     return torch.cat([gathered[r * cap:r * cap + c] for r, c in enumerate(counts)], dim=0)
 
 
+class PassGather:
+    """All-gather of every rank's output batch, one pass of images at a time.
+
+    ``Enhancer.submit(..., on_pass=gather.on_pass)`` calls :meth:`on_pass` on the copy-out stream as soon as a
+    pass of the local batch is finished, so the collective of pass k runs under the kernels of pass k+1 (NCCL
+    over NVLink; the only exchange of the path).  Every rank contributes the same batch size
+    (weak scaling); ``gathered[r]`` is rank r's batch, ``result()`` the (world*B, ...) concatenation in rank order --
+    bitwise what one process computing all world*B images returns.
+    """
+
+    def __init__(self, local_shape, dtype, device, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.gathered = torch.empty((self.world,) + tuple(local_shape), dtype=dtype, device=device)
+        self.calls = 0
+
+    def on_pass(self, local_chunk: torch.Tensor, a: int, b: int) -> None:
+        outs = [self.gathered[r, a:b] for r in range(self.world)]  # each a contiguous block of rank r's batch
+        dist.all_gather(outs, local_chunk.contiguous(), group=self.group)
+        self.calls += 1
+
+    def result(self) -> torch.Tensor:
+        return self.gathered.view((-1,) + tuple(self.gathered.shape[2:]))
+
+
 def run_sharded(batch: torch.Tensor, fn: Callable[[torch.Tensor], torch.Tensor], gather: bool = True,
                 group=None) -> torch.Tensor:
     """Apply ``fn`` to this rank's contiguous shard of ``batch`` (dim 0) and all-gather the results.

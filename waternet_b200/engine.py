@@ -9,12 +9,15 @@ import ctypes
 import threading
 from typing import Dict, Optional, Sequence, Tuple
 
+import numpy as np
 import torch
 
 from . import _lib
 
 _engines: Dict[int, "Engine"] = {}
 _engines_lock = threading.Lock()
+# scratch buffers are shared by every engine of a device (all work is stream-ordered on the caller's stream)
+_ws_pool: Dict[int, Dict[str, torch.Tensor]] = {}
 
 
 def _require_cuda(device=None) -> torch.device:
@@ -30,6 +33,7 @@ def _require_cuda(device=None) -> torch.device:
 
 
 def get_engine(device=None) -> "Engine":
+    """The device's shared engine: preprocess / postprocess and callers that pack weights themselves."""
     dev = _require_cuda(device)
     with _engines_lock:
         eng = _engines.get(dev.index)
@@ -37,6 +41,15 @@ def get_engine(device=None) -> "Engine":
             eng = Engine(dev)
             _engines[dev.index] = eng
         return eng
+
+
+def new_engine(device=None) -> "Engine":
+    """A private engine (its own C-ABI handle, i.e. its own packed-weight slot) for one model on one device.
+
+    Every ``WaterNet`` / ``ConfidenceMapGenerator`` / ``Refiner`` instance owns one per device, so two models on
+    a device never evict -- or silently run with -- each other's packed weights.
+    """
+    return Engine(_require_cuda(device))
 
 
 def _stream_ptr(device: torch.device) -> ctypes.c_void_p:
@@ -50,7 +63,7 @@ class Engine:
         handle = ctypes.c_void_p()
         _lib.check(self.lib.wn_create(device.index, ctypes.byref(handle)), "wn_create")
         self.handle = handle
-        self._ws: Dict[str, torch.Tensor] = {}
+        self._ws = _ws_pool.setdefault(device.index, {})
         self._weights_key = None
         self._weights_keepalive = None
 
@@ -73,6 +86,20 @@ class Engine:
 
     def release_workspaces(self) -> None:
         self._ws.clear()
+
+    def chunk_images(self, n: int, h: int, w: int) -> int:
+        """Images per pass of the tensor-core forward for a batch of ``n`` (wn_forward_chunk_images)."""
+        return max(1, int(self.lib.wn_forward_chunk_images(self.handle, n, h, w)))
+
+    def set_chunk_pixels(self, max_pixels: int) -> None:
+        """Lower the per-pass pixel cap (0 = default 8 Mi); tests force the multi-pass path with it."""
+        _lib.check(self.lib.wn_set_chunk_pixels(self.handle, int(max_pixels)), "wn_set_chunk_pixels")
+
+    def f8_overflowed(self) -> bool:
+        """True once the fp8-correction mode saw an activation beyond the e4m3 range.  The batch that did was
+        recomputed by the bf16x3 kernels within the same call; from then on the handle uses those kernels
+        directly until new weights are packed (wn_f8_overflowed).  Valid after the stream has been synchronised."""
+        return bool(self.lib.wn_f8_overflowed(self.handle))
 
     @property
     def launch_count(self) -> int:
@@ -106,17 +133,8 @@ class Engine:
     # ---- forward -------------------------------------------------------------
     def forward(self, x, wb, he, gc, mode: int = _lib.MODE_DEFAULT, out: Optional[torch.Tensor] = None):
         """WaterNet.forward (net.py:99-108) on (N,3,H,W) fp32 CUDA tensors of any strides."""
-        ins = []
-        for t in (x, wb, he, gc):
-            if t.device != self.device:
-                raise ValueError(f"input on {t.device}, engine on {self.device}")
-            if t.dim() != 4 or t.shape[1] != 3:
-                raise ValueError(f"expected (N,3,H,W) inputs, got {tuple(t.shape)}")
-            ins.append(t.detach() if t.dtype == torch.float32 else t.detach().float())
+        ins = self._check_inputs((x, wb, he, gc))
         n, _, h, w = ins[0].shape
-        for t in ins[1:]:
-            if t.shape != ins[0].shape:
-                raise ValueError("the four inputs must have the same shape")
         if out is None:
             out = torch.empty((n, 3, h, w), dtype=torch.float32, device=self.device)
         if n == 0 or h == 0 or w == 0:  # empty batch: nothing to launch (torch's convs return empty too)
@@ -129,6 +147,51 @@ class Engine:
                                      ins[3].data_ptr(), strides, out.data_ptr(), n, h, w, mode,
                                      ws.data_ptr(), ws.numel(), _stream_ptr(self.device))
         _lib.check(rc, "wn_forward")
+        return out
+
+    def _check_inputs(self, tensors):
+        ins = []
+        for t in tensors:
+            if t.device != self.device:
+                raise ValueError(f"input on {t.device}, engine on {self.device}")
+            if t.dim() != 4 or t.shape[1] != 3:
+                raise ValueError(f"expected (N,3,H,W) inputs, got {tuple(t.shape)}")
+            ins.append(t.detach() if t.dtype == torch.float32 else t.detach().float())
+        for t in ins[1:]:
+            if t.shape != ins[0].shape:
+                raise ValueError("the inputs must have the same shape")
+        return ins
+
+    def confidence_maps(self, x, wb, he, gc, mode: int = _lib.MODE_DEFAULT) -> torch.Tensor:
+        """ConfidenceMapGenerator.forward (net.py:45-56): the three sigmoid maps as one (N,3,H,W) tensor."""
+        ins = self._check_inputs((x, wb, he, gc))
+        n, _, h, w = ins[0].shape
+        out = torch.empty((n, 3, h, w), dtype=torch.float32, device=self.device)
+        if out.numel() == 0:
+            return out
+        strides = (ctypes.c_int64 * 16)(*[s for t in ins for s in t.stride()])
+        ws = self._workspace("forward", self.lib.wn_submodule_workspace_bytes(n, h, w, mode))
+        with torch.cuda.device(self.device):
+            rc = self.lib.wn_confidence_maps(self.handle, ins[0].data_ptr(), ins[1].data_ptr(), ins[2].data_ptr(),
+                                             ins[3].data_ptr(), strides, out.data_ptr(), n, h, w, mode,
+                                             ws.data_ptr(), ws.numel(), _stream_ptr(self.device))
+        _lib.check(rc, "wn_confidence_maps")
+        return out
+
+    def refine(self, which: int, x, xbar, mode: int = _lib.MODE_DEFAULT) -> torch.Tensor:
+        """Refiner.forward (net.py:75-80) of refiner ``which`` (0 wb, 1 ce, 2 gc) of the packed state dict."""
+        ins = self._check_inputs((x, xbar))
+        n, _, h, w = ins[0].shape
+        out = torch.empty((n, 3, h, w), dtype=torch.float32, device=self.device)
+        if out.numel() == 0:
+            return out
+        strides = (ctypes.c_int64 * 8)(*[s for t in ins for s in t.stride()])
+        ws = self._workspace("forward", self.lib.wn_submodule_workspace_bytes(n, h, w, mode))
+        with torch.cuda.device(self.device):
+            rc = self.lib.wn_refine(self.handle, int(which), ins[0].data_ptr(), ins[1].data_ptr(), strides,
+                                    out.data_ptr(), n, h, w, mode, ws.data_ptr(), ws.numel(),
+                                    _stream_ptr(self.device))
+        _lib.check(rc, "wn_refine")
         return out
 
     LAYER_CHANNELS = (128, 128, 128, 64, 64, 64, 64, 3, 96, 96)
@@ -148,11 +211,20 @@ class Engine:
         return dst
 
     # ---- training step (wn_forward_train / wn_backward) ---------------------------------------
+    TRAIN_MAX_PIXELS = 8 << 20
+
     def forward_train(self, x, wb, he, gc):
         """Tensor-core forward that keeps every activation.  Returns (out, saved-workspace tensor)."""
-        ins = [t.detach() if t.dtype == torch.float32 else t.detach().float() for t in (x, wb, he, gc)]
+        ins = self._check_inputs((x, wb, he, gc))
         n, _, h, w = ins[0].shape
         out = torch.empty((n, 3, h, w), dtype=torch.float32, device=self.device)
+        if out.numel() == 0:
+            return out, None
+        if n * h * w > self.TRAIN_MAX_PIXELS:
+            raise _lib.WaterNetLibraryError(
+                f"a forward pass that keeps its activations for autograd holds ~5.6 KB per pixel: {n}x{h}x{w} exceeds "
+                f"the {self.TRAIN_MAX_PIXELS >> 20} Mi-pixel limit of wn_forward_train.  For inference wrap the call "
+                "in torch.no_grad() (the reference's autograd path would need the same memory)")
         strides = (ctypes.c_int64 * 16)(*[s for t in ins for s in t.stride()])
         ws = torch.empty(self.lib.wn_train_workspace_bytes(n, h, w), dtype=torch.uint8, device=self.device)
         with torch.cuda.device(self.device):
@@ -213,6 +285,31 @@ class Engine:
                                            ws.data_ptr(), ws.numel(), _stream_ptr(self.device))
         _lib.check(rc, "wn_preprocess_u8")
         return res
+
+    def resize_batch(self, images, dst_h: int, dst_w: int, swap_rb: bool = False) -> torch.Tensor:
+        """Batched ``cv2.resize(img, (dst_w, dst_h))`` (+ optional BGR<->RGB swap) of differently sized uint8 HWC
+        images (numpy arrays or CUDA tensors) into one uint8 (N, dst_h, dst_w, 3) CUDA tensor -- bit-exact
+        OpenCV INTER_LINEAR arithmetic on the device (wn_resize_u8; training_utils.py:94-107)."""
+        devs = []
+        for im in images:
+            t = torch.from_numpy(np.ascontiguousarray(im)) if isinstance(im, np.ndarray) else im
+            if t.dtype != torch.uint8 or t.dim() != 3 or t.shape[2] != 3:
+                raise ValueError(f"expected uint8 HWC images, got {t.dtype} {tuple(t.shape)}")
+            devs.append(t.to(self.device, non_blocking=True).contiguous())
+        n = len(devs)
+        out = torch.empty((n, dst_h, dst_w, 3), dtype=torch.uint8, device=self.device)
+        if n == 0 or out.numel() == 0:
+            return out
+        ptrs = (ctypes.c_void_p * n)(*[t.data_ptr() for t in devs])
+        hs = (ctypes.c_int * n)(*[t.shape[0] for t in devs])
+        ws = (ctypes.c_int * n)(*[t.shape[1] for t in devs])
+        with torch.cuda.device(self.device):
+            rc = self.lib.wn_resize_u8(self.handle, ptrs, hs, ws, n, out.data_ptr(), dst_h, dst_w, 1 if swap_rb else 0,
+                                       _stream_ptr(self.device))
+        _lib.check(rc, "wn_resize_u8")
+        for t in devs:  # the kernel reads them on the current stream after this call returns
+            t.record_stream(torch.cuda.current_stream(self.device))
+        return out
 
     def postprocess(self, out: torch.Tensor) -> torch.Tensor:
         """ten2arr on the device: fp32 (N,3,H,W) -> uint8 (N,H,W,3) CUDA tensor."""

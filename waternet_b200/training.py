@@ -1,8 +1,8 @@
 """Training / scoring loops of the reference (train.py:26-152, score.py) on the B200 forward.
 
-The model's forward values come from the CUDA library; gradients are obtained by
-re-evaluating the network with torch ops inside ``WaterNet``'s autograd function
-(native dgrad/wgrad kernels are the next widening step).  The
+The model's forward values and all of its gradients come from the CUDA library
+(``wn_forward_train`` / ``wn_backward``: tensor-core forward that keeps its activations, data-gradient and
+weight-gradient kernels; only ``precision="fp32"`` re-evaluates the torch graph for its backward).  The
 VGG19 perceptual model, Adam and the metrics stay PyTorch: they are not on the
 north-star path.
 """

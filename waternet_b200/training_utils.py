@@ -83,15 +83,23 @@ class UIEBDataset(torch.utils.data.Dataset):
     def __len__(self):
         return len(self.im_fns)
 
-    def pair(self, idx):
-        """Decoded, resized RGB uint8 (raw, ref) arrays of item ``idx`` -- no augmentation, no preprocess."""
-        import cv2  # file decode / resize only
+    def decoded(self, idx):
+        """The two files of item ``idx`` as decoded by ``cv2.imread`` (BGR uint8, native size) and the
+        ``(width, height)`` the reference resizes them to (training_utils.py:94-103)."""
+        import cv2  # file decode only
         raw_im = cv2.imread(os.fspath(self.raw_dir / self.im_fns[idx]))
         ref_im = cv2.imread(os.fspath(self.ref_dir / self.im_fns[idx]))
         if self.im_width is not None and self.im_height is not None:
             size = (self.im_width, self.im_height)
         else:  # multiple of 32 for VGG; the reference swaps the axis names here (training_utils.py:100-103)
             size = (int(raw_im.shape[0] / 32) * 32, int(raw_im.shape[1] / 32) * 32)
+        return raw_im, ref_im, size
+
+    def pair(self, idx):
+        """Decoded, resized RGB uint8 (raw, ref) arrays of item ``idx`` -- no augmentation, no preprocess
+        (the per-item CPU path; ``GpuBatchLoader`` resizes on the device instead)."""
+        import cv2
+        raw_im, ref_im, size = self.decoded(idx)
         raw_im = cv2.cvtColor(cv2.resize(raw_im, size), cv2.COLOR_BGR2RGB)
         ref_im = cv2.cvtColor(cv2.resize(ref_im, size), cv2.COLOR_BGR2RGB)
         return raw_im, ref_im
@@ -140,7 +148,8 @@ class GpuBatchLoader:
 
     The reference's loop is data-loading bound: every item runs ``transform`` and four ``arr2ten`` on
     the CPU in the main process (``training_utils.py:89-132``, ``train.py:234``).  Here a batch of
-    uint8 (raw, ref) pairs goes to the device once; the flip / rot90 augmentation (same p=0.5 choices
+    uint8 (raw, ref) pairs goes to the device once (file-backed datasets: at native size, resized there by ONE
+    batched ``wn_resize_u8`` with cv2's exact INTER_LINEAR arithmetic); the flip / rot90 augmentation (same p=0.5 choices
     as ``training_utils.py:72-78``, applied identically to raw and ref) and ONE batched
     ``wn_preprocess_u8`` produce the five fp32 tensors of the reference's item dictionary, already
     on the device.  ``dataset`` needs ``__len__`` and ``pair(idx) -> (raw_u8, ref_u8)`` (both
@@ -190,9 +199,20 @@ class GpuBatchLoader:
             idx = self.indices[start:start + self.batch_size]
             if self.drop_last and len(idx) < self.batch_size:
                 break
-            pairs = [self.dataset.pair(i) for i in idx]
-            raw = torch.from_numpy(np.stack([p[0] for p in pairs])).to(dev, non_blocking=True)
-            ref = torch.from_numpy(np.stack([p[1] for p in pairs])).to(dev, non_blocking=True)
+            if hasattr(self.dataset, "decoded"):
+                # file-backed dataset: cv2.imread on the host, then ONE batched bilinear resize + BGR->RGB on the
+                # device (wn_resize_u8, bit-exact cv2.resize arithmetic) instead of 2 x batch cv2.resize calls
+                items = [self.dataset.decoded(i) for i in idx]
+                sizes = {it[2] for it in items}
+                if len(sizes) != 1:
+                    raise ValueError("a batch needs one target size: give the dataset im_height / im_width")
+                (dw, dh), = sizes
+                raw = self.engine.resize_batch([it[0] for it in items], dh, dw, swap_rb=True)
+                ref = self.engine.resize_batch([it[1] for it in items], dh, dw, swap_rb=True)
+            else:
+                pairs = [self.dataset.pair(i) for i in idx]
+                raw = torch.from_numpy(np.stack([p[0] for p in pairs])).to(dev, non_blocking=True)
+                ref = torch.from_numpy(np.stack([p[1] for p in pairs])).to(dev, non_blocking=True)
             if self.augment:
                 raw, ref = self._augment(raw, ref)
             pre = self.engine.preprocess(raw, tensors=True, images=False)

@@ -182,8 +182,9 @@ int wn_debug_forward_layer(wn_handle* h, const float* x, const float* wb, const 
 
 /*
  * Bring-up aid: switch pieces of the tensor-core conv pipeline off to attribute time (bit 0: epilogue
- * stores, bit 1: weight-stage refetch, bit 2: the lo passes).  RESULTS ARE WRONG with any bit set;
- * 0 restores normal operation.  Used by tools/pipeline_attribution.py only.
+ * stores, bit 1: weight-stage refetch, bit 2: the lo passes).  RESULTS ARE WRONG with any of bits 0-7 set;
+ * 0 restores normal operation.  Used by tools/pipeline_attribution.py only.  Bit 8 (256) is an A/B switch with
+ * correct results: cmg.conv3 and conv4 run as two launches instead of conv3 with conv4 as its fused tail layer.
  */
 int wn_debug_set_flags(wn_handle* h, int flags);
 

@@ -771,7 +771,7 @@ def test_batched_resize_matches_cv2_bit_exact(eng):
 def test_gpu_batch_loader_resizes_files_on_the_device(tmp_path):
     """UIEBDataset (PNG pairs at native sizes) through GpuBatchLoader == the reference-style per-item CPU path."""
     cv2 = pytest.importorskip("cv2")
-    from waternet_b200.training_utils import GpuBatchLoader, UIEBDataset
+    from waternet_b200.training_utils import GpuBatchLoader, UIEBDataset, _item
     rng = np.random.default_rng(2)
     (tmp_path / "raw").mkdir()
     (tmp_path / "ref").mkdir()
@@ -783,7 +783,9 @@ def test_gpu_batch_loader_resizes_files_on_the_device(tmp_path):
     seen = 0
     for b, batch in enumerate(loader):
         for j in range(batch["raw"].shape[0]):
-            item = ds[b * 3 + j]   # per-item path: cv2.resize + cvtColor + transform + arr2ten
+            # per-item path of the reference (training_utils.py:89-123) without the random flips: cv2.imread,
+            # cv2.resize, cvtColor(BGR2RGB), transform, arr2ten
+            item = _item(*ds.pair(b * 3 + j))
             for key in ("raw", "wb", "gc", "he", "ref"):
                 assert torch.equal(batch[key][j].cpu(), item[key].cpu().reshape(batch[key][j].shape)), key
             seen += 1
@@ -882,3 +884,56 @@ def test_training_loss_curve_matches_the_reference_loop():
     assert curve_r[-1][0]["loss"] < curve_r[0][0]["loss"] and curve_o[-1][0]["loss"] < curve_o[0][0]["loss"]
     print("reference loop losses", [round(t["loss"], 3) for t, _ in curve_r])
     print("this repo's losses   ", [round(t["loss"], 3) for t, _ in curve_o])
+
+
+def test_fused_tail_layers_equal_separate_launches():
+    """Default mode: cmg.conv4 (1x1) runs as the tail GEMM of conv3's kernel (the activation tile goes back into tensor
+    memory as the A operand of a second tcgen05.mma, UmmaCfg TN), and cmg.conv8 (3x3, 64 -> 3) as the tap-stacked tail
+    of conv7 plus a gather kernel.  Same arithmetic as the separate launches up to the fp32 summation order."""
+    from waternet_b200 import _lib
+    sd = ofw.synthetic_state_dict(3, 3.0)
+    m = _model(3, 3.0, "default")
+    eng = m.engine()
+    # the last two shapes: many tiles per CTA (a fused launch must not write into the buffer it still reads halos from)
+    for n, h, w in [(1, 40, 56), (3, 37, 61), (2, 130, 70), (1, 16, 8), (1, 1, 1), (1, 300, 500), (2, 270, 480)]:
+        torch.manual_seed(h)
+        ins = [torch.rand(n, 3, h, w) for _ in range(4)]
+        cu = [t.cuda() for t in ins]
+        res = {}
+        with torch.no_grad():
+            for flags in (0, 256, 512, 768):   # 256: conv3 / conv4 as two launches; 512: conv7 / conv8 as two launches
+                eng.set_debug_flags(flags)
+                try:
+                    res[flags] = (m(*cu).cpu().numpy(),
+                                  eng.debug_layer(*cu, layer=3, mode=_lib.MODE_BF16_FP8).cpu().numpy(),
+                                  eng.debug_layer(*cu, layer=7, mode=_lib.MODE_BF16_FP8).cpu().numpy())
+                finally:
+                    eng.set_debug_flags(0)
+        torch.cuda.synchronize()
+        assert not eng.f8_overflowed(), "a garbage tile would trip the range guard and be silently recomputed"
+        # the fused and the separate forms add the same products in a different order (~1e-7); where that moves a
+        # value across a rounding boundary of the hi + fp8 activation format the fp8-correction scheme's own
+        # error (~1e-4) appears between the two -- so the bar between them is that error, the bar against the
+        # float64 oracle the parity bar
+        ref64 = ofw.waternet_forward(sd, *ins, dtype=torch.float64).numpy()
+        for flags in (0, 256, 512):
+            for got, want in zip(res[flags], res[768]):
+                _assert_close(got, want, tol=3e-4)
+            _assert_close(res[flags][0], ref64)
+
+
+def test_native_backward_is_bit_reproducible():
+    """The weight-gradient GEMM merges its per-CTA partial sums in a fixed order (no atomics): two backward passes
+    over the same batch give bit-identical gradients."""
+    torch.manual_seed(3)
+    m = _model(5, 3.0, "default").train()
+    ins = [t.cuda() for t in _inputs_from_rgb([ofw.synthetic_image(90 + i, 61, 83, "smooth") for i in range(3)])]
+    target = torch.rand(3, 3, 61, 83).cuda()
+    runs = []
+    for _ in range(3):
+        m.zero_grad(set_to_none=True)
+        torch.nn.functional.mse_loss(m(*ins), target).backward()
+        runs.append([p.grad.clone() for p in m.parameters()])
+    for other in runs[1:]:
+        for a, b in zip(runs[0], other):
+            assert torch.equal(a, b)

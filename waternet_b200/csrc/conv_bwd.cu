@@ -9,7 +9,8 @@
 //                        the activation-plane layout act[plane][y][x][8ch], which is exactly the
 //                        no-swizzle MN-major UMMA layout (8 channels contiguous, 16 consecutive
 //                        pixels of a row = one K=16 step); a tap is again only a start-address
-//                        shift of the B operand.  fp32 partial sums per CTA are merged with atomics.
+//                        shift of the B operand.  Every CTA stores its fp32 partial sums; a second kernel adds
+//                        them in a fixed order (bit-reproducible gradients, no atomics).
 //   bias_grad_kernel     db[co] = sum_px g[px][co]
 //
 // All three GEMM-shaped pieces use the same bf16x3 split as the forward (gradient error ~1e-5).
@@ -49,7 +50,7 @@ struct WgradCfg {
 };
 
 struct WgradArgs {
-  float* dense;  // [KS*KS][128][NCI] fp32, accumulated with atomics (zeroed by the caller)
+  float* partial;  // [CTA = split * NGROUPS + group][TPG][128][NCI] fp32 partial sums (reduced by reduce_wgrad_kernel)
   int N, H, W;
   int co_planes;    // 8-channel planes of the gradient to load (per hi/lo half)
   int planes_half;  // planes per half in the gradient buffer (lo parts start there)
@@ -163,17 +164,18 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
     tc_fence_after();
     const int co = warp * 32 + lane;  // TMEM lane == output channel
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    float* base = g.partial + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * (TPG * 128 * NCI);
     for (int tl = 0; tl < ntaps; tl++) {
-      float* dst = g.dense + ((size_t)(tap0 + tl) * 128 + co) * NCI;
+      float4* dst = reinterpret_cast<float4*>(base + ((size_t)tl * 128 + co) * NCI);
 #pragma unroll 1
       for (int c0 = 0; c0 < NCI; c0 += 16) {
         uint32_t v[16];
         tmem_ld16(tmem_base + lane_base + (uint32_t)(tl * NCI + c0), v);
         tmem_ld_wait();
-        if (co < g.co_valid) {
 #pragma unroll
-          for (int j = 0; j < 16; j++) atomicAdd(dst + c0 + j, __uint_as_float(v[j]));
-        }
+        for (int j = 0; j < 16; j += 4)
+          dst[(c0 + j) >> 2] = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                           __uint_as_float(v[j + 3]));
       }
     }
   }
@@ -187,7 +189,35 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
   }
 }
 
-// db[c] = sum over images and pixels of (hi + lo).  grid = (planes, splits), 256 threads.
+// dense[tap][co][c] = sum over the pixel splits, in split order, of the CTAs' partial sums (deterministic)
+__global__ void __launch_bounds__(256)
+reduce_wgrad_kernel(const float* __restrict__ partial, float* __restrict__ dense, int kk, int tpg, int ngroups,
+                    int splits, int nci, int co_valid) {
+  const int per_tap = 128 * nci;
+  const long long total = (long long)kk * per_tap;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int tap = (int)(i / per_tap);
+    const int rem = (int)(i - (long long)tap * per_tap);
+    const int grp = tap / tpg, tl = tap - grp * tpg;
+    float acc = 0.f;
+    if (rem / nci < co_valid) {
+      const float* p = partial + ((size_t)grp * tpg + tl) * per_tap + rem;
+      for (int s = 0; s < splits; s++) acc += p[(size_t)s * ngroups * tpg * per_tap];
+    }
+    dense[i] = acc;
+  }
+}
+// db[c] = sum of the per-block partial sums, in block order
+__global__ void reduce_bias_kernel(const float* __restrict__ part, float* __restrict__ db, int nsplit, int stride,
+                                   int co_valid) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= co_valid) return;
+  float acc = 0.f;
+  for (int s = 0; s < nsplit; s++) acc += part[(size_t)s * stride + c];
+  db[c] = acc;
+}
+
+// part[split][c] = sum over this block's images and pixels of (hi + lo).  grid = (planes, splits), 256 threads.
 __global__ void __launch_bounds__(256)
 bias_grad_kernel(const uint4* __restrict__ gplanes, float* __restrict__ db, int planes_half, int n_img, int hw,
                  int co_valid) {
@@ -216,7 +246,7 @@ bias_grad_kernel(const uint4* __restrict__ gplanes, float* __restrict__ db, int 
       for (int j = 0; j < 8; j++) s_part[j][threadIdx.x] += s_part[j][threadIdx.x + o];
     __syncthreads();
   }
-  if (threadIdx.x < 8 && plane * 8 + threadIdx.x < co_valid) atomicAdd(&db[plane * 8 + threadIdx.x], s_part[threadIdx.x][0]);
+  if (threadIdx.x < 8) db[(size_t)blockIdx.y * gridDim.x * 8 + plane * 8 + threadIdx.x] = s_part[threadIdx.x][0];
 }
 
 // dense [kk][128][nci] -> OIHW gradient tensor:  dst[o][c][t] = scale * dense[t][row_off + o][cd(c)]
@@ -421,8 +451,14 @@ struct TrainBuffers {
   FwdBuffers f;
   uint4 *ga, *gb, *gra, *grb, *g8, *gr3, *gin_a, *gin_b;
   float* dense;
+  float* partial;  // per-CTA partial sums of the weight-gradient GEMM / per-block partial bias sums
 };
 static constexpr size_t kDenseBytes = (size_t)49 * 128 * 128 * sizeof(float);
+// one slot per CTA of a weight-gradient launch (one wave: <= SM count), each TPG * NCI <= 512 accumulator columns
+// x 128 rows of fp32
+static constexpr size_t kPartialSlotBytes = (size_t)512 * 128 * sizeof(float);
+static constexpr int kPartialSlots = 192;
+static constexpr size_t kPartialBytes = kPartialSlots * kPartialSlotBytes;
 // bytes per pixel: act0 64 | a1..a3 512 each | a4..a7 256 each | r1, r2 384 each | cm 12 | refined 36 |
 //                  gradient ping-pong 512 + 512 + 384 + 384 | 16-channel gradients 64 + 64
 static constexpr size_t kTrainBytesPerPixel =
@@ -430,7 +466,7 @@ static constexpr size_t kTrainBytesPerPixel =
 static constexpr long long kTrainMaxPixels = 8ll << 20;
 
 size_t train_workspace_bytes(int n, int h, int w) {
-  return (size_t)n * h * w * kTrainBytesPerPixel + kDenseBytes + 8192;
+  return (size_t)n * h * w * kTrainBytesPerPixel + kDenseBytes + kPartialBytes + 8192;
 }
 
 static void carve(TrainBuffers* t, void* workspace, size_t px) {
@@ -458,6 +494,7 @@ static void carve(TrainBuffers* t, void* workspace, size_t px) {
   t->gin_a = (uint4*)take(px * 128);
   t->gin_b = (uint4*)take(px * 128);
   t->dense = (float*)take(kDenseBytes);
+  t->partial = (float*)take(kPartialBytes);
 }
 
 static int check_train_args(int n, int H, int W, size_t bytes) {
@@ -503,8 +540,8 @@ static int make_plane_tmap(CUtensorMap* tm, void* base, int planes_total, int N,
 
 // dense[tap][128][NCI] += sum_px g[px][co] * a[px + tap][ci]
 template <int KS, int NCI, int TPG>
-static int launch_wgrad(wn_handle* h, uint4* gplanes, int co_valid, uint4* aplanes, float* dense, int n, int H, int W,
-                        cudaStream_t stream) {
+static int launch_wgrad(wn_handle* h, uint4* gplanes, int co_valid, uint4* aplanes, float* dense, float* partial, int n,
+                        int H, int W, cudaStream_t stream) {
   using C = WgradCfg<KS, NCI, TPG>;
   const int co_planes = (co_valid + 7) / 8;
   const int planes_half = (co_valid + 15) / 16 * 2;  // gradient buffers hold a multiple of 16 channels
@@ -514,7 +551,7 @@ static int launch_wgrad(wn_handle* h, uint4* gplanes, int co_valid, uint4* aplan
   rc = make_plane_tmap(&ta, aplanes, 2 * C::A_PLANES, n, H, W, C::HALO_W, C::HALO_H, C::A_PLANES);
   if (rc) return rc;
   WgradArgs a;
-  a.dense = dense;
+  a.partial = partial;
   a.N = n; a.H = H; a.W = W;
   a.co_planes = co_planes;
   a.planes_half = planes_half;
@@ -525,10 +562,13 @@ static int launch_wgrad(wn_handle* h, uint4* gplanes, int co_valid, uint4* aplan
   long long splits = h->sm_count / C::NGROUPS;  // one wave: every CTA owns an SM (shared memory footprint)
   if (splits > tiles) splits = tiles;
   if (splits < 1) splits = 1;
-  WN_CUDA(cudaMemsetAsync(dense, 0, (size_t)KS * KS * 128 * NCI * sizeof(float), stream));
+  if (splits * C::NGROUPS > kPartialSlots) splits = kPartialSlots / C::NGROUPS;
+  static_assert((size_t)TPG * 128 * NCI * sizeof(float) <= kPartialSlotBytes, "partial-sum slot");
   auto kern = wgrad_umma_kernel<KS, NCI, TPG>;
   WN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
   kern<<<dim3(C::NGROUPS, (unsigned)splits), kWgradThreads, C::SMEM_BYTES, stream>>>(tg, ta, a);
+  WN_LAUNCH_CHECK(h);
+  reduce_wgrad_kernel<<<256, 256, 0, stream>>>(partial, dense, KS * KS, TPG, C::NGROUPS, (int)splits, NCI, co_valid);
   WN_LAUNCH_CHECK(h);
   return WN_OK;
 }
@@ -540,10 +580,12 @@ static int extract(wn_handle* h, const float* dense, float* dst, int co, int ci,
   return WN_OK;
 }
 
-static int bias_grad(wn_handle* h, const uint4* gplanes, int planes_half, int co_valid, float* db, int n, int hw,
-                     cudaStream_t stream) {
-  WN_CUDA(cudaMemsetAsync(db, 0, co_valid * sizeof(float), stream));
-  bias_grad_kernel<<<dim3((co_valid + 7) / 8, 64), 256, 0, stream>>>(gplanes, db, planes_half, n, hw, co_valid);
+static int bias_grad(wn_handle* h, const uint4* gplanes, int planes_half, int co_valid, float* db, float* partial, int n,
+                     int hw, cudaStream_t stream) {
+  const int planes = (co_valid + 7) / 8;
+  bias_grad_kernel<<<dim3(planes, 64), 256, 0, stream>>>(gplanes, partial, planes_half, n, hw, co_valid);
+  WN_LAUNCH_CHECK(h);
+  reduce_bias_kernel<<<(co_valid + 127) / 128, 128, 0, stream>>>(partial, db, 64, planes * 8, co_valid);
   WN_LAUNCH_CHECK(h);
   return WN_OK;
 }
@@ -589,75 +631,75 @@ int backward(wn_handle* h, const float* grad_out, float* const* grads, float* co
 
   // ---- confidence-map stack: conv8 ... conv1 ---------------------------------------------
   // conv8 (64 -> 3, 3x3): g = g8 (16-channel planes, 3 valid), a = a7
-  if ((rc = launch_wgrad<3, 64, 8>(h, t.g8, 3, t.f.a[7], t.dense, n, H, W, stream))) return rc;
+  if ((rc = launch_wgrad<3, 64, 8>(h, t.g8, 3, t.f.a[7], t.dense, t.partial, n, H, W, stream))) return rc;
   if ((rc = extract(h, t.dense, gw(7), 3, 64, 3, 64, 0, 64, 0, 0, 1.f, stream))) return rc;
-  if ((rc = bias_grad(h, t.g8, 2, 3, gb(7), n, hw, stream))) return rc;
+  if ((rc = bias_grad(h, t.g8, 2, 3, gb(7), t.partial, n, hw, stream))) return rc;
   if ((rc = launch_dgrad<3, 16, 64, 2, 2, 1, 1, 9, WN_CG_BWD>(h, kD8, t.g8, t.ga, 64, t.f.a[7], n, H, W, stream))) return rc;
   // conv7 (64 -> 64, 3x3): g = ga
-  if ((rc = launch_wgrad<3, 64, 8>(h, t.ga, 64, t.f.a[6], t.dense, n, H, W, stream))) return rc;
+  if ((rc = launch_wgrad<3, 64, 8>(h, t.ga, 64, t.f.a[6], t.dense, t.partial, n, H, W, stream))) return rc;
   if ((rc = extract(h, t.dense, gw(6), 64, 64, 3, 64, 0, 64, 0, 0, 1.f, stream))) return rc;
-  if ((rc = bias_grad(h, t.ga, 8, 64, gb(6), n, hw, stream))) return rc;
+  if ((rc = bias_grad(h, t.ga, 8, 64, gb(6), t.partial, n, hw, stream))) return rc;
   if ((rc = launch_dgrad<3, 64, 64, 2, 2, 1, 1, 9, WN_CG_BWD>(h, kD7, t.ga, t.gb, 64, t.f.a[6], n, H, W, stream))) return rc;
   // conv6 (5x5): g = gb
-  if ((rc = launch_wgrad<5, 64, 8>(h, t.gb, 64, t.f.a[5], t.dense, n, H, W, stream))) return rc;
+  if ((rc = launch_wgrad<5, 64, 8>(h, t.gb, 64, t.f.a[5], t.dense, t.partial, n, H, W, stream))) return rc;
   if ((rc = extract(h, t.dense, gw(5), 64, 64, 5, 64, 0, 64, 0, 0, 1.f, stream))) return rc;
-  if ((rc = bias_grad(h, t.gb, 8, 64, gb(5), n, hw, stream))) return rc;
+  if ((rc = bias_grad(h, t.gb, 8, 64, gb(5), t.partial, n, hw, stream))) return rc;
   if ((rc = launch_dgrad<5, 64, 64, 2, 2, 1, 1, 5, WN_CG_BWD>(h, kD6, t.gb, t.ga, 64, t.f.a[5], n, H, W, stream))) return rc;
   // conv5 (7x7): g = ga
-  if ((rc = launch_wgrad<7, 64, 8>(h, t.ga, 64, t.f.a[4], t.dense, n, H, W, stream))) return rc;
+  if ((rc = launch_wgrad<7, 64, 8>(h, t.ga, 64, t.f.a[4], t.dense, t.partial, n, H, W, stream))) return rc;
   if ((rc = extract(h, t.dense, gw(4), 64, 64, 7, 64, 0, 64, 0, 0, 1.f, stream))) return rc;
-  if ((rc = bias_grad(h, t.ga, 8, 64, gb(4), n, hw, stream))) return rc;
+  if ((rc = bias_grad(h, t.ga, 8, 64, gb(4), t.partial, n, hw, stream))) return rc;
   if ((rc = launch_dgrad<7, 64, 64, 2, 2, 1, 1, 7, WN_CG_BWD>(h, kD5, t.ga, t.gb, 64, t.f.a[4], n, H, W, stream))) return rc;
   // conv4 (128 -> 64, 1x1): g = gb (64), a = a3 (128)
-  if ((rc = launch_wgrad<1, 128, 1>(h, t.gb, 64, t.f.a[3], t.dense, n, H, W, stream))) return rc;
+  if ((rc = launch_wgrad<1, 128, 1>(h, t.gb, 64, t.f.a[3], t.dense, t.partial, n, H, W, stream))) return rc;
   if ((rc = extract(h, t.dense, gw(3), 64, 128, 1, 128, 0, 128, 0, 0, 1.f, stream))) return rc;
-  if ((rc = bias_grad(h, t.gb, 8, 64, gb(3), n, hw, stream))) return rc;
+  if ((rc = bias_grad(h, t.gb, 8, 64, gb(3), t.partial, n, hw, stream))) return rc;
   if ((rc = launch_dgrad<1, 64, 128, 2, 2, 0, 1, 1>(h, kD4, t.gb, t.ga, 128, t.f.a[3], n, H, W, stream))) return rc;
   // conv3 (128 -> 128, 3x3): g = ga
-  if ((rc = launch_wgrad<3, 128, 4>(h, t.ga, 128, t.f.a[2], t.dense, n, H, W, stream))) return rc;
+  if ((rc = launch_wgrad<3, 128, 4>(h, t.ga, 128, t.f.a[2], t.dense, t.partial, n, H, W, stream))) return rc;
   if ((rc = extract(h, t.dense, gw(2), 128, 128, 3, 128, 0, 128, 0, 0, 1.f, stream))) return rc;
-  if ((rc = bias_grad(h, t.ga, 16, 128, gb(2), n, hw, stream))) return rc;
+  if ((rc = bias_grad(h, t.ga, 16, 128, gb(2), t.partial, n, hw, stream))) return rc;
   if ((rc = launch_dgrad<3, 128, 128, 2, 2, 0, 1, 3, WN_CG_BWD>(h, kD3, t.ga, t.gb, 128, t.f.a[2], n, H, W, stream))) return rc;
   // conv2 (5x5): g = gb
-  if ((rc = launch_wgrad<5, 128, 4>(h, t.gb, 128, t.f.a[1], t.dense, n, H, W, stream))) return rc;
+  if ((rc = launch_wgrad<5, 128, 4>(h, t.gb, 128, t.f.a[1], t.dense, t.partial, n, H, W, stream))) return rc;
   if ((rc = extract(h, t.dense, gw(1), 128, 128, 5, 128, 0, 128, 0, 0, 1.f, stream))) return rc;
-  if ((rc = bias_grad(h, t.gb, 16, 128, gb(1), n, hw, stream))) return rc;
+  if ((rc = bias_grad(h, t.gb, 16, 128, gb(1), t.partial, n, hw, stream))) return rc;
   if ((rc = launch_dgrad<5, 128, 128, 2, 2, 0, 1, 5, WN_CG_BWD>(h, kD2, t.gb, t.ga, 128, t.f.a[1], n, H, W, stream))) return rc;
   // conv1 (12 -> 128, 7x7): g = ga, a = act0 (holds v*255 -> scale the gradient back)
-  if ((rc = launch_wgrad<7, 16, 32>(h, t.ga, 128, t.f.act0, t.dense, n, H, W, stream))) return rc;
+  if ((rc = launch_wgrad<7, 16, 32>(h, t.ga, 128, t.f.act0, t.dense, t.partial, n, H, W, stream))) return rc;
   if ((rc = extract(h, t.dense, gw(0), 128, 12, 7, 16, 0, 12, 0, 0, 1.f / 255.f, stream))) return rc;
-  if ((rc = bias_grad(h, t.ga, 16, 128, gb(0), n, hw, stream))) return rc;
+  if ((rc = bias_grad(h, t.ga, 16, 128, gb(0), t.partial, n, hw, stream))) return rc;
   if (input_grads) {  // d/d(packed input) from cmg.conv1: ga (128) -> g8 region reused as a 32-channel buffer
     if ((rc = launch_dgrad<7, 128, 32, 2, 2, 1, 1, 7, WN_CG_BWD>(h, kD1, t.ga, t.gin_a, 32, nullptr, n, H, W, stream))) return rc;
   }
 
   // ---- refiners: conv3, conv2, conv1 (three side by side) ---------------------------------
-  if ((rc = launch_wgrad<3, 96, 5>(h, t.gr3, 9, t.f.r[2], t.dense, n, H, W, stream))) return rc;
+  if ((rc = launch_wgrad<3, 96, 5>(h, t.gr3, 9, t.f.r[2], t.dense, t.partial, n, H, W, stream))) return rc;
   for (int r = 0; r < 3; r++) {
     if ((rc = extract(h, t.dense, gw(8 + 3 * r + 2), 3, 32, 3, 96, 3 * r, 32, 32 * r, 0, 1.f, stream))) return rc;
   }
   {
     // the nine bias gradients sit in one 16-channel buffer: reduce once, then split per refiner
     float* tmp = t.dense + (size_t)9 * 128 * 96;
-    if ((rc = bias_grad(h, t.gr3, 2, 9, tmp, n, hw, stream))) return rc;
+    if ((rc = bias_grad(h, t.gr3, 2, 9, tmp, t.partial, n, hw, stream))) return rc;
     for (int r = 0; r < 3; r++)
       WN_CUDA(cudaMemcpyAsync(gb(8 + 3 * r + 2), tmp + 3 * r, 3 * sizeof(float), cudaMemcpyDeviceToDevice, stream));
   }
   if ((rc = launch_dgrad<3, 16, 96, 2, 2, 0, 1, 9, WN_CG_BWD>(h, kDR3, t.gr3, t.gra, 96, t.f.r[2], n, H, W, stream))) return rc;
-  if ((rc = launch_wgrad<5, 96, 5>(h, t.gra, 96, t.f.r[1], t.dense, n, H, W, stream))) return rc;
+  if ((rc = launch_wgrad<5, 96, 5>(h, t.gra, 96, t.f.r[1], t.dense, t.partial, n, H, W, stream))) return rc;
   {
     float* tmp = t.dense + (size_t)25 * 128 * 96;
-    if ((rc = bias_grad(h, t.gra, 12, 96, tmp, n, hw, stream))) return rc;
+    if ((rc = bias_grad(h, t.gra, 12, 96, tmp, t.partial, n, hw, stream))) return rc;
     for (int r = 0; r < 3; r++) {
       if ((rc = extract(h, t.dense, gw(8 + 3 * r + 1), 32, 32, 5, 96, 32 * r, 32, 32 * r, 0, 1.f, stream))) return rc;
       WN_CUDA(cudaMemcpyAsync(gb(8 + 3 * r + 1), tmp + 32 * r, 32 * sizeof(float), cudaMemcpyDeviceToDevice, stream));
     }
   }
   if ((rc = launch_dgrad<5, 96, 32, 2, 1, 1, 3, 5, WN_CG_BWD>(h, kDR2, t.gra, t.grb, 96, t.f.r[1], n, H, W, stream))) return rc;
-  if ((rc = launch_wgrad<7, 16, 32>(h, t.grb, 96, t.f.act0, t.dense, n, H, W, stream))) return rc;
+  if ((rc = launch_wgrad<7, 16, 32>(h, t.grb, 96, t.f.act0, t.dense, t.partial, n, H, W, stream))) return rc;
   {
     float* tmp = t.dense + (size_t)49 * 128 * 16;
-    if ((rc = bias_grad(h, t.grb, 12, 96, tmp, n, hw, stream))) return rc;
+    if ((rc = bias_grad(h, t.grb, 12, 96, tmp, t.partial, n, hw, stream))) return rc;
     for (int r = 0; r < 3; r++) {
       // refiner r reads cat[x, input r+1]: channels 0..2 and 3(r+1)..3(r+1)+2 of the packed input
       if ((rc = extract(h, t.dense, gw(8 + 3 * r), 32, 6, 7, 16, 32 * r, 3, 0, 3 * (r + 1), 1.f / 255.f, stream))) return rc;

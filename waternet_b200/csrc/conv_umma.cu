@@ -107,10 +107,11 @@ enum UmmaLayer {
 #ifndef WN_R2_S
 #define WN_R2_S 2
 #endif
-// fp8-correction scheme: sub-tiles per CTA tile of conv2/conv3 (two accumulator halves of 128 columns each:
-// S=1 double-buffers them, S=2 fills TMEM)
+// fp8-correction scheme: sub-tiles per CTA tile of conv2/conv3.  One shared accumulator of 128 columns per
+// sub-tile (round 1 kept the correction product in a second one): S=2 double-buffered fills TMEM exactly and
+// halves the weight-stage fill traffic per MMA, which competes with the operand reads for the 128 B/clk port
 #ifndef WN_F8_C23_S
-#define WN_F8_C23_S 1
+#define WN_F8_C23_S 2
 #endif
 struct UmmaLayerSpec {
   int ks, cinpad, npad, cout, slot, concat, nblk;  // npad = output columns per diagonal block
@@ -128,6 +129,44 @@ static const UmmaLayerSpec kSpecs[kNumUmmaLayers] = {
     {5, 96, 32, 96, 9, 1, 3, WN_CG_L1R2},
     {3, 96, 16, 9, 10, 1, 1, 1}};
 
+static int spec_slot(int li) { return kSpecs[li].slot; }
+
+// OIHW [co][ci][kk] -> dense [kk * co rows][ci]: row 3 * tap + c holds tap's filter of output channel c
+static __global__ void scatter_tapstack_kernel(const float* __restrict__ src, float* __restrict__ dense, int co, int ci, int kk) {
+  const int total = co * ci * kk;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int t = i % kk, c = (i / kk) % ci, o = i / (kk * ci);
+    dense[(size_t)(t * co + o) * ci + c] = src[i];
+  }
+}
+// cm[n][c][y][x] = sigmoid(bias[c] + sum over the 3x3 taps of taps[n][3 * tap + c][y + ky - 1][x + kx - 1]), zero outside
+// the image ("same" padding): the second half of the tap-stacked cmg.conv8 (net.py:40-43, 54).  HBM-bound: 108 B/px
+// read (every partial sum exactly once), 12 B/px written.
+static __global__ void __launch_bounds__(256)
+gather_sigmoid_kernel(const float* __restrict__ taps, const float* __restrict__ bias, float* __restrict__ cm, int H, int W) {
+  const int x = blockIdx.x * 64 + threadIdx.x, y = blockIdx.y * 4 + threadIdx.y, n = blockIdx.z;
+  if (x >= W || y >= H) return;
+  const size_t hw = (size_t)H * W;
+  const float* t = taps + (size_t)n * 27 * hw;
+  float acc[3] = {bias[0], bias[1], bias[2]};
+#pragma unroll
+  for (int ky = 0; ky < 3; ky++) {
+    const int yy = y + ky - 1;
+    if (yy < 0 || yy >= H) continue;
+#pragma unroll
+    for (int kx = 0; kx < 3; kx++) {
+      const int xx = x + kx - 1;
+      if (xx < 0 || xx >= W) continue;
+      const float* p = t + (size_t)((ky * 3 + kx) * 3) * hw + (size_t)yy * W + xx;
+#pragma unroll
+      for (int c = 0; c < 3; c++) acc[c] += p[(size_t)c * hw];
+    }
+  }
+  float* o = cm + (size_t)n * 3 * hw + (size_t)y * W + x;
+#pragma unroll
+  for (int c = 0; c < 3; c++) o[(size_t)c * hw] = 1.0f / (1.0f + expf(-acc[c]));
+}
+
 // layers that have an fp8-correction form (UmmaCfg FMT bit 0): the tensor-bound CTA-pair layers
 static bool has_f8_form(int li) { return li == kC2 || li == kC3 || li == kC5 || li == kC6 || li == kC7 || li == kR2; }
 static size_t stage8_bytes_total(const UmmaLayerSpec& s) {
@@ -136,6 +175,8 @@ static size_t stage8_bytes_total(const UmmaLayerSpec& s) {
 struct UmmaWeights {
   uint8_t* stages8[kNumUmmaLayers];  // fp8-correction weight images (has_f8_form layers)
   float* scale8[kNumUmmaLayers];     // {ws, 2^-9 / ws, max|w|, -}
+  uint8_t* tail8;                    // cmg.conv8 tap-stacked (27 = 9 taps x 3 channels columns) as the tail layer of conv7
+  uint8_t* tail4;                    // cmg.conv4 as the tail layer of conv3: two per-rank images, CG=2 CONCAT layout
   int* overflow_dev;                 // sticky: an activation left the e4m3 range in the fp8-correction mode
   int* overflow_host;                // pinned mirror, refreshed at the end of every forward of that mode
   uint8_t* stages[kNumUmmaLayers];
@@ -160,6 +201,8 @@ int umma_pack_weights(wn_handle* h, const float* const* params, cudaStream_t str
     }
   }
   if (!h->umma->dense) WN_CUDA(cudaMalloc(&h->umma->dense, (size_t)224 * 128 * 49 * sizeof(float)));
+  if (!h->umma->tail4) WN_CUDA(cudaMalloc(&h->umma->tail4, (size_t)2 * 8 * 64 * 48));
+  if (!h->umma->tail8) WN_CUDA(cudaMalloc(&h->umma->tail8, (size_t)2 * 4 * 32 * 48));
   if (!h->umma->overflow_dev) WN_CUDA(cudaMalloc(&h->umma->overflow_dev, sizeof(int)));
   if (!h->umma->overflow_host) WN_CUDA(cudaHostAlloc(&h->umma->overflow_host, sizeof(int), cudaHostAllocDefault));
   UmmaWeights* u = h->umma;
@@ -204,6 +247,18 @@ int umma_pack_weights(wn_handle* h, const float* const* params, cudaStream_t str
       pack_stages_kernel<<<256, 256, 0, stream>>>(u->dense, (__nv_bfloat16*)u->stages[li], s.npad, s.cinpad, kk,
                                                   s.concat, s.nblk);
     WN_LAUNCH_CHECK(h);
+    if (li == kC4) {  // the same weights as conv3's fused tail layer (UmmaCfg TN): per rank [chunk][k8][64 | 32 rows][8]
+      pack_stages_cg2_kernel<<<256, 256, 0, stream>>>(u->dense, (__nv_bfloat16*)u->tail4, s.npad, s.cinpad, kk, 1, 1);
+      WN_LAUNCH_CHECK(h);
+    }
+    if (li == kC8) {  // tap-stacked form: dense [32 rows = 3 * tap + channel (27 used)][64 input channels], a 1x1 layer
+      float* stacked = u->dense + (size_t)16 * 64 * 9;  // behind conv8's own [16][64][9] matrix
+      WN_CUDA(cudaMemsetAsync(stacked, 0, (size_t)32 * 64 * sizeof(float), stream));
+      scatter_tapstack_kernel<<<8, 256, 0, stream>>>(W(7), stacked, 3, 64, 9);
+      WN_LAUNCH_CHECK(h);
+      pack_stages_cg2_kernel<<<64, 256, 0, stream>>>(stacked, (__nv_bfloat16*)u->tail8, 32, 64, 1, 1, 1);
+      WN_LAUNCH_CHECK(h);
+    }
     if (has_f8_form(li)) {
       WN_CUDA(cudaMemsetAsync(u->scale8[li], 0, 4 * sizeof(float), stream));
       f8_absmax_kernel<<<64, 256, 0, stream>>>(u->dense, (size_t)rows * s.cinpad * kk, u->scale8[li]);
@@ -227,6 +282,8 @@ void umma_free(wn_handle* h) {
     if (h->umma->scale8[i]) cudaFree(h->umma->scale8[i]);
   }
   if (h->umma->dense) cudaFree(h->umma->dense);
+  if (h->umma->tail4) cudaFree(h->umma->tail4);
+  if (h->umma->tail8) cudaFree(h->umma->tail8);
   if (h->umma->overflow_dev) cudaFree(h->umma->overflow_dev);
   if (h->umma->overflow_host) cudaFreeHost(h->umma->overflow_host);
   free(h->umma);
@@ -261,6 +318,24 @@ size_t umma_forward_workspace_bytes(int n, int h, int w) {
 #ifndef WN_C3_TPS
 #define WN_C3_TPS 3
 #endif
+#ifndef WN_F8_C3_TPS
+#define WN_F8_C3_TPS 9
+#endif
+#ifndef WN_F8_R2_AS
+#define WN_F8_R2_AS 2   // the refiners' conv2: 96 accumulator columns per sub-tile, S=2 double-buffered = 384
+#endif
+#ifndef WN_C34_TPS
+#define WN_C34_TPS 9   // conv3 with the fused conv4 tail (24 KB of shared memory hold the tail's weights)
+#endif
+// ... and its accumulator stages: one sub-tile = 128 columns and the bf16 copy of the tile (the tail GEMM's A
+// operand) another 128, so three stages fill tensor memory; the tile's second epilogue pass (after the tail GEMM)
+// then has two tiles of slack before its accumulator stage is needed again
+#ifndef WN_C34_AS
+#define WN_C34_AS 3
+#endif
+#ifndef WN_C78_AS
+#define WN_C78_AS 3   // conv7 with the tap-stacked conv8 tail: 2 x 64 accumulator columns per stage + 2 x 64 for the bf16 tiles
+#endif
 #ifndef WN_C7_TPS
 #define WN_C7_TPS 9
 #endif
@@ -269,7 +344,7 @@ size_t umma_forward_workspace_bytes(int n, int h, int w) {
 #endif
 
 template <int KS, int CIN_PAD, int NPAD, int S, int AS, int EPI, int CONCAT = 0, int NBLK = 1, int TPS = 1, int CG = 1,
-          int FMT = 0>
+          int FMT = 0, int TN = 0, int TEPI = 0>
 static int launch_umma(wn_handle* h, int li, void* in_base, ConvArgs a, cudaStream_t stream) {
   const UmmaLayerSpec& spec = kSpecs[li];
   if constexpr ((FMT & kFmtOut8) != 0) a.f8_overflow = h->umma->overflow_dev;
@@ -279,14 +354,15 @@ static int launch_umma(wn_handle* h, int li, void* in_base, ConvArgs a, cudaStre
       return WN_E_STATE;
     }
     a.f8_scale = h->umma->scale8[li] + 1;
-    return launch_conv<KS, CIN_PAD, NPAD, S, AS, EPI, 0, NBLK, TPS, 2, FMT>(h, spec.slot, h->umma->stages8[li],
-                                                                           h->umma->bias[li], in_base, a, stream);
+    return launch_conv<KS, CIN_PAD, NPAD, S, AS, EPI, 0, NBLK, TPS, 2, FMT, TN, TEPI>(h, spec.slot, h->umma->stages8[li],
+                                                                                     h->umma->bias[li], in_base, a, stream);
   }
   if (spec.ks != KS || spec.cinpad != CIN_PAD || spec.npad != NPAD || spec.concat != CONCAT || spec.nblk != NBLK ||
       spec.cg != CG) {
     set_error("internal: launch configuration of layer %d does not match its packed weights", li);
     return WN_E_STATE;
   }
+  static_assert(TN == 0 || (FMT & kFmtIn8) != 0, "the fused tail layer exists for the fp8-correction form only");
   return launch_conv<KS, CIN_PAD, NPAD, S, AS, EPI, CONCAT, NBLK, TPS, CG, FMT>(h, spec.slot, h->umma->stages[li],
                                                                        h->umma->bias[li], in_base, a, stream);
 }
@@ -379,30 +455,70 @@ int umma_forward_layers(wn_handle* h, const float* const in[4], const int64_t st
     if (dump(0, b.a[1], 128, 1) || dump(8, b.r[1], 96, 1)) return WN_OK;
     if (want_cmg) {
       act(b.a[2], 128, nullptr, 0);
-      if ((rc = launch_umma<5, 128, 128, WN_F8_C23_S, WN_F8_C23_S == 1 ? 2 : 1, kEpiAct, 0, 1, 5, 2, IN8 | OUT8>(h, kC2, b.a[1], a, stream))) return rc;
+      if ((rc = launch_umma<5, 128, 128, WN_F8_C23_S, 2, kEpiAct, 0, 1, 5, 2, IN8 | OUT8>(h, kC2, b.a[1], a, stream))) return rc;
       if (dump(1, b.a[2], 128, 1)) return WN_OK;
-      act(b.a[3], 128, nullptr, 0);
-      if ((rc = launch_umma<3, 128, 128, WN_F8_C23_S, WN_F8_C23_S == 1 ? 2 : 1, kEpiAct, 0, 1, 9, 2, IN8>(h, kC3, b.a[2], a, stream))) return rc;
-      if (dump(2, b.a[3], 128)) return WN_OK;
-      act(b.a[4], 64, nullptr, 0);
-      if ((rc = launch_umma<1, 128, 64, 2, 2, kEpiAct, 1, 1, 1, 1, OUT8>(h, kC4, b.a[3], a, stream))) return rc;
-      if (dump(3, b.a[4], 64, 1)) return WN_OK;
-      act(b.a[5], 64, nullptr, 0);
-      if ((rc = launch_umma<7, 64, 64, 2, 2, kEpiAct, 0, 1, 7, 2, IN8 | OUT8>(h, kC5, b.a[4], a, stream))) return rc;
-      if (dump(4, b.a[5], 64, 1)) return WN_OK;
-      act(b.a[6], 64, nullptr, 0);
-      if ((rc = launch_umma<5, 64, 64, 2, 2, kEpiAct, 0, 1, 5, 2, IN8 | OUT8>(h, kC6, b.a[5], a, stream))) return rc;
-      if (dump(5, b.a[6], 64, 1)) return WN_OK;
-      act(b.a[7], 64, nullptr, 0);
-      if ((rc = launch_umma<3, 64, 64, 2, 2, kEpiAct, 0, 1, 9, 2, IN8>(h, kC7, b.a[6], a, stream))) return rc;
-      if (dump(6, b.a[7], 64)) return WN_OK;
-      a.out_f32 = dbg_layer == 7 ? dbg_dst : b.cm;
-      if ((rc = launch_umma<3, 64, 16, 4, 2, kEpiSigmoid, 1, 1, 9>(h, kC8, b.a[7], a, stream))) return rc;
+      // where conv4..conv7 write: the ping-pong assignment of carve() has conv4's output in conv2's buffer, which
+      // the fused conv3+conv4 launch is still reading (halos of tiles to come) -- with conv4 fused, conv4..7 take
+      // the buffers of conv3..6 instead
+      const bool fuse34 = dbg_layer != 2 && !(h->dbg_flags & 256);
+      uint4* const a4 = fuse34 ? b.a[3] : b.a[4];
+      uint4* const a5 = fuse34 ? b.a[4] : b.a[5];
+      uint4* const a6 = fuse34 ? b.a[5] : b.a[6];
+      uint4* const a7 = fuse34 ? b.a[6] : b.a[7];
+      if (fuse34) {
+        // conv3 with conv4 (1x1) as its fused tail layer: conv3's output tile goes back into tensor memory as the
+        // A operand of a second GEMM; only conv4's 64 channels reach HBM (net.py:20-27)
+        act(a4, 64, nullptr, 0);
+        a.wtail = h->umma->tail4;
+        a.bias2 = h->umma->bias[kC4];
+        if ((rc = launch_umma<3, 128, 128, 1, WN_C34_AS, kEpiAct, 0, 1, WN_C34_TPS, 2, IN8 | OUT8, 64>(h, kC3, b.a[2], a, stream))) return rc;
+        a.wtail = nullptr;
+        a.bias2 = nullptr;
+      } else {
+        act(b.a[3], 128, nullptr, 0);
+        if ((rc = launch_umma<3, 128, 128, WN_F8_C23_S, 2, kEpiAct, 0, 1, WN_F8_C3_TPS, 2, IN8>(h, kC3, b.a[2], a, stream))) return rc;
+        if (dump(2, b.a[3], 128)) return WN_OK;
+        act(a4, 64, nullptr, 0);
+        if ((rc = launch_umma<1, 128, 64, 2, 2, kEpiAct, 1, 1, 1, 1, OUT8>(h, kC4, b.a[3], a, stream))) return rc;
+      }
+      if (dump(3, a4, 64, 1)) return WN_OK;
+      act(a5, 64, nullptr, 0);
+      if ((rc = launch_umma<7, 64, 64, 2, 2, kEpiAct, 0, 1, 7, 2, IN8 | OUT8>(h, kC5, a4, a, stream))) return rc;
+      if (dump(4, a5, 64, 1)) return WN_OK;
+      act(a6, 64, nullptr, 0);
+      if ((rc = launch_umma<5, 64, 64, 2, 2, kEpiAct, 0, 1, 5, 2, IN8 | OUT8>(h, kC6, a5, a, stream))) return rc;
+      if (dump(5, a6, 64, 1)) return WN_OK;
+      float* const cm_dst = dbg_layer == 7 ? dbg_dst : b.cm;
+      if (dbg_layer != 6 && !(h->dbg_flags & 512)) {
+        // conv7 with conv8 (3x3, 64 -> 3) tap-stacked as its fused tail layer: the 27 per-tap partial sums of every
+        // pixel (fp32 planes, 108 B/px, in the buffer conv7's activations would have taken) instead of conv7's 64
+        // channels (256 B/px); gather_sigmoid_kernel then adds the nine shifted planes, the bias, and applies the
+        // sigmoid (net.py:36-43, 54)
+        float* taps = reinterpret_cast<float*>(a7);
+        a.out_f32 = taps;
+        a.cout = 27;
+        a.wtail = h->umma->tail8;
+        a.bias2 = h->umma->bias[kC8];  // unused by the tap-stacked epilogue (the gather adds the bias)
+        if ((rc = launch_umma<3, 64, 64, 2, WN_C78_AS, kEpiAct, 0, 1, 9, 2, IN8, 32, kTailTaps>(h, kC7, a6, a, stream))) return rc;
+        a.wtail = nullptr;
+        a.bias2 = nullptr;
+        {
+          TimedScope ts(h, spec_slot(kC8), stream);
+          gather_sigmoid_kernel<<<dim3((W + 63) / 64, (H + 3) / 4, n), dim3(64, 4), 0, stream>>>(taps, h->umma->bias[kC8], cm_dst, H, W);
+          WN_LAUNCH_CHECK(h);
+        }
+      } else {
+        act(a7, 64, nullptr, 0);
+        if ((rc = launch_umma<3, 64, 64, 2, 2, kEpiAct, 0, 1, 9, 2, IN8>(h, kC7, a6, a, stream))) return rc;
+        if (dump(6, a7, 64)) return WN_OK;
+        a.out_f32 = cm_dst;
+        if ((rc = launch_umma<3, 64, 16, 4, 2, kEpiSigmoid, 1, 1, 9>(h, kC8, a7, a, stream))) return rc;
+      }
       if (dbg_layer == 7) return WN_OK;
     }
     if (!want_ref) return WN_OK;
     act(b.r[2], 96, nullptr, 0);
-    if ((rc = launch_umma<5, 96, 32, 2, 1, kEpiAct, 0, 3, 5, 2, IN8>(h, kR2, b.r[1], a, stream))) return rc;
+    if ((rc = launch_umma<5, 96, 32, 2, WN_F8_R2_AS, kEpiAct, 0, 3, 5, 2, IN8>(h, kR2, b.r[1], a, stream))) return rc;
     if (dump(9, b.r[2], 96)) return WN_OK;
     last();
     if ((rc = launch_umma<3, 96, 16, 4, 2, kEpiGate, 1, 1, 9>(h, kR3, b.r[2], a, stream))) return rc;

@@ -57,6 +57,13 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank)
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(rank));
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
+// ... with cluster-scope release: what was written before (shared-memory data another SM's issuer hands to the
+// tensor cores) is ordered before the arrival
+__device__ __forceinline__ void mbar_arrive_remote_release(uint64_t* bar, uint32_t rank) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(rank));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -153,6 +160,37 @@ __device__ __forceinline__ void umma_issue(uint32_t d_tmem, uint32_t a_lo, uint3
   if constexpr (CG == 2) umma2_bf16_split(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, accumulate);
   else umma_bf16_split(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, accumulate);
 }
+// A operand from tensor memory (lane = M row, one 32-bit column = two consecutive bf16 K elements), B from shared
+// memory: the fused tail layer's GEMM reads the activation tile the epilogue wrote back with tcgen05.st.
+template <int CG>
+__device__ __forceinline__ void umma_issue_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi,
+                                              uint32_t idesc, uint32_t accumulate) {
+  if constexpr (CG == 2)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], db, %4, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // kind::f8f6f4 (K = 32 fp8 values per instruction): the fp8 correction pass.  Same descriptors as the bf16
 // form -- a core-matrix row is 16 bytes either way (8 bf16 or 16 fp8 values).
 template <int CG>
@@ -258,15 +296,32 @@ constexpr int kWarpA = 8, kWarpB = 9, kWarpTmem = 10, kWarpMma = 11;
 // FMT    bit 0 (kFmtIn8): fp8 correction scheme on the input side.  v = hi (bf16) + lo; instead of the two
 //        bf16 correction passes (a_lo x w_hi, a_hi x w_lo) ONE kind::f8f6f4 MMA of K = 32 multiplies
 //        [e4m3(lo * 2^9) | e4m3(v)] (the two fp8 planes the producing layer wrote where the bf16 lo planes
-//        used to be) by [e4m3(w * ws) ; e4m3(w_lo * ws * 2^9)] into a second accumulator that the epilogue
-//        scales by 2^-9 / ws: 2 pass-equivalents instead of 3 at half the operand bytes.
+//        used to be) by [e4m3(w * ws) ; e4m3(w_lo * ws * 2^9)]: 2 pass-equivalents instead of 3 at half the
+//        operand bytes.  Both MMAs accumulate into the SAME fp32 accumulator: the bf16 weights of such a layer
+//        are packed pre-scaled by the power of two ws * 2^9 (exact), so the two products carry the same scale
+//        and the epilogue multiplies the sum by 2^-9 / ws once.  (A separate correction accumulator, as in
+//        round 1, doubles the TMEM columns and forces single-buffered or single-sub-tile configurations.)
 //        bit 1 (kFmtOut8): the epilogue writes that hi + fp8-planes format (its consumer has bit 0 set).
 constexpr int kFmtIn8 = 1, kFmtOut8 = 2;
+// TN     fused "tail" layer (0 = none): a 1x1 convolution of TN output channels applied to this layer's output tile
+//        before it ever leaves the SM.  The epilogue writes the tile's activations (bias, ReLU, bf16 hi/lo split) back
+//        into TENSOR MEMORY as packed bf16 pairs (tcgen05.st: lane = pixel row, one 32-bit column = two channels --
+//        exactly the K-major A operand of a tcgen05.mma that takes A from TMEM), the issuer runs a second, small
+//        GEMM (K = this layer's output channels, bf16x3 in the CONCAT form, weights resident in shared memory) into
+//        the accumulator columns the epilogue has just drained, and a second epilogue pass stores the tail layer's
+//        output.  cmg.conv3 -> conv4 (net.py:20-27): conv3's 512 B/px write, conv4's 512 B/px read and its launch
+//        disappear; no shared memory is spent on the intermediate tile.
 template <int KS, int CIN_PAD, int NPAD, int S, int AS, int CONCAT = 0, int NBLK = 1, int TPS = 1, int CG = 1,
-          int FMT = 0>
+          int FMT = 0, int TN = 0>
 struct UmmaCfg {
+  static constexpr int K2 = NPAD * NBLK;                                 // tail GEMM K = this layer's output channels
+  static constexpr int A2_COLS = TN ? K2 : 0;                            // TMEM columns per sub-tile: K2/2 hi pairs | K2/2 lo pairs
+  static constexpr int WT_TAP = TN * 48;                                 // per K=16 step and rank: [k8][TN | TN/2 rows][16 B]
+  static constexpr int WT_BYTES = TN ? (K2 / 16) * WT_TAP : 0;
+  static constexpr int TAIL_BYTES = (WT_BYTES + 1023) / 1024 * 1024;
+
   static constexpr bool F8IN = (FMT & kFmtIn8) != 0;
-  static constexpr bool DUAL = CONCAT || F8IN;  // two accumulator halves per block
+  static constexpr bool DUAL = CONCAT != 0;  // two accumulator halves per block: [a x w_hi | a_hi x w_lo]
   static constexpr int TILE_W = kSubW * S, TILE_H = kSubH;
   static constexpr int HALO_W = TILE_W + KS - 1, HALO_H = TILE_H + KS - 1;
   static constexpr int NCHUNK = CIN_PAD / 16;
@@ -281,7 +336,7 @@ struct UmmaCfg {
   // consecutive taps of the endless tap stream (tile after tile), so a group may straddle two tiles
   static constexpr bool WRAP = (KS * KS) % TPS != 0;
   static constexpr int NSTAGE_PER_CHUNK = KS * KS / TPS;
-  static constexpr int BUDGET = 225 * 1024 - 2048;
+  static constexpr int BUDGET = 225 * 1024 - 2048 - TAIL_BYTES;
   // halo ring: enough stages to prefetch the next chunk (or the next tile when there is one chunk)
   // (a 1x1 layer is HBM-bound and its stages are small: keep more loads in flight)
   static constexpr int NA_WANT = NCHUNK == 1 ? 2 : KS == 1 ? 6 : 3;
@@ -303,15 +358,18 @@ struct UmmaCfg {
   static constexpr int N1 = CONCAT ? 2 * NPAD : NPAD;      // UMMA N of the a_hi pass
   static constexpr int BLK_COLS = DUAL ? 2 * NPAD : NPAD;   // accumulator columns per block
   static constexpr int SUB_COLS = NBLK * BLK_COLS;         // accumulator columns per sub-tile
-  static constexpr int TMEM_COLS_USED = AS * S * SUB_COLS;
+  static constexpr int A2_COL0 = AS * S * SUB_COLS;        // tail: first TMEM column of the activation tile(s)
+  static constexpr int TMEM_COLS_USED = AS * S * SUB_COLS + S * A2_COLS;
   static_assert(NCHUNK % NBLK == 0, "chunks must split evenly over the diagonal blocks");
   static_assert(N1 % 16 == 0 && N1 <= 256, "invalid UMMA N for the a_hi pass");
   static constexpr int TMEM_COLS = TMEM_COLS_USED <= 32 ? 32 : TMEM_COLS_USED <= 64 ? 64
                                    : TMEM_COLS_USED <= 128 ? 128 : TMEM_COLS_USED <= 256 ? 256 : 512;
-  static constexpr int SMEM_BYTES = NA * A_STAGE + NB * B_STAGE + 2048 + 1024;  // + barriers/bias + align slack
+  static constexpr int SMEM_BYTES = NA * A_STAGE + NB * B_STAGE + TAIL_BYTES + 2048 + 1024;  // + barriers/bias + align slack
   static_assert(NA >= 1, "halo tile does not fit in shared memory");
   static_assert(TMEM_COLS_USED <= 512, "accumulators do not fit in TMEM");
   static_assert(NPAD % 16 == 0 && NPAD >= 16 && NPAD <= 256, "invalid UMMA N");
+  static_assert(TN == 0 || (CG == 2 && AS >= 2 && !WRAP && TN % 32 == 0 && 2 * TN <= SUB_COLS),
+                "tail layer: CTA pairs, multi-buffered accumulators, and its accumulators fit the drained columns");
 };
 
 struct ActDst {
@@ -349,6 +407,10 @@ struct ConvArgs {
   // FMT bit 1: sticky device flag raised when an activation leaves the e4m3 range (its correction terms would
   // saturate in the consumer's fp8 pass); the host side then re-runs the batch with the bf16x3 kernels
   int* f8_overflow;
+  // fused tail layer (UmmaCfg TN): packed weights (two per-rank images, CG=2 CONCAT layout) and bias; dst0 / dst1 /
+  // split_c / cout then describe the TAIL layer's output
+  const uint8_t* wtail;
+  const float* bias2;
   // conditional launch: when non-null and *run_if == 0 the kernel returns at once (the bf16x3 re-run of a
   // batch is enqueued unconditionally behind the fp8-correction pass and only does work if the flag is up)
   const int* run_if;
@@ -372,10 +434,18 @@ __device__ __forceinline__ void split_bf16x2(float f0, float f1, uint32_t& hi, u
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
-template <int KS, int CIN_PAD, int NPAD, int S, int AS, int EPI, int CONCAT, int NBLK, int TPS, int CG = 1, int FMT = 0>
+// TEPI   what the tail layer's epilogue stores: kTailAct = bias, ReLU, activation planes (conv4 behind conv3);
+//        kTailTaps = the raw fp32 sums as planes [n][cout][H][W].  The latter serves a 3x3 layer with very few
+//        output channels (cmg.conv8: 64 -> 3) in "tap-stacked" form: its 9 x 3 = 27 (tap, channel) filters are 27
+//        output columns of a 1x1 tail GEMM on the UNSHIFTED tile -- column 3*tap + c of pixel q is tap's
+//        contribution to output pixel q - shift(tap) -- and a small gather kernel adds the nine shifted planes.
+enum TailEpilogue { kTailAct = 0, kTailTaps = 1 };
+template <int KS, int CIN_PAD, int NPAD, int S, int AS, int EPI, int CONCAT, int NBLK, int TPS, int CG = 1, int FMT = 0,
+          int TN = 0, int TEPI = kTailAct>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) {
-  using C = UmmaCfg<KS, CIN_PAD, NPAD, S, AS, CONCAT, NBLK, TPS, CG, FMT>;
+  using C = UmmaCfg<KS, CIN_PAD, NPAD, S, AS, CONCAT, NBLK, TPS, CG, FMT, TN>;
+  static_assert(TN == 0 || EPI == kEpiAct, "a tail layer follows an activation layer");
   constexpr bool F8IN = C::F8IN, DUAL = C::DUAL, OUT8 = (FMT & kFmtOut8) != 0;
   static_assert(!OUT8 || EPI == kEpiAct, "fp8 planes are written by the activation epilogue only");
   if (g.run_if != nullptr && *reinterpret_cast<const volatile int*>(g.run_if) == 0) return;  // whole grid alike
@@ -383,7 +453,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* a_stages = smem;
   uint8_t* b_stages = smem + C::NA * C::A_STAGE;
-  uint8_t* tail = b_stages + C::NB * C::B_STAGE;
+  uint8_t* wt_smem = b_stages + C::NB * C::B_STAGE;     // tail layer: its weights, resident for the whole launch
+  uint8_t* tail = wt_smem + C::TAIL_BYTES;
   uint64_t* a_full = reinterpret_cast<uint64_t*>(tail);
   uint64_t* a_empty = a_full + C::NA;
   uint64_t* b_full = a_empty + C::NA;
@@ -392,8 +463,15 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
   uint64_t* t_empty = t_full + AS;
   uint64_t* a_full_peer = t_empty + AS;        // CG=2, leader: "the peer CTA's stage is full too"
   uint64_t* b_full_peer = a_full_peer + C::NA;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_full_peer + C::NB);
+  uint64_t* a2_full = b_full_peer + C::NB;     // [S] tail: "sub-tile s is back in TMEM as bf16 operand" (leader's barrier counts both CTAs)
+  uint64_t* t2_full = a2_full + S;             // [AS] tail: "the tail GEMM of this accumulator stage has completed"
+  uint64_t* wt_full = t2_full + AS;            // tail weights landed (own CTA) / (leader) in the peer CTA
+  uint64_t* wt_full_peer = wt_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wt_full_peer + 1);
   float* s_bias = reinterpret_cast<float*>(tail + 512);
+  float* s_bias2 = s_bias + NBLK * NPAD;
+  static_assert(AS <= 4 && S <= 4 && (3 * 6 + 3 * 8 + 2 * AS + S + AS + 2) * 8 + 4 <= 512, "barrier area");
+  static_assert((NBLK * NPAD + TN) * 4 <= 2048 - 512, "bias area");
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int num_tiles = g.tiles_x * g.tiles_y * g.N;
@@ -407,9 +485,17 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
     for (int i = 0; i < C::NA; i++) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); mbar_init(&a_full_peer[i], 1); }
     for (int i = 0; i < C::NB; i++) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); mbar_init(&b_full_peer[i], 1); }
     for (int i = 0; i < AS; i++) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 8 * CG); }
+    if constexpr (TN > 0) {
+      for (int i = 0; i < S; i++) mbar_init(&a2_full[i], (S == 1 ? 8 : 4) * CG);
+      for (int i = 0; i < AS; i++) mbar_init(&t2_full[i], 1);
+      mbar_init(wt_full, 1);
+      mbar_init(wt_full_peer, 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int i = tid; i < NBLK * NPAD; i += kThreads) s_bias[i] = g.bias[i];
+  if constexpr (TN > 0 && TEPI == kTailAct)
+    for (int i = tid; i < TN; i += kThreads) s_bias2[i] = g.bias2[i];
   if (warp == kWarpTmem) {
     if constexpr (CG == 2) {
       asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
@@ -475,6 +561,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
     } else if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      if constexpr (TN > 0) {  // the tail layer's weights: this rank's image, once
+        mbar_expect_tx(wt_full, C::WT_BYTES);
+        bulk_load(wt_smem, g.wtail + (size_t)rank * C::WT_BYTES, C::WT_BYTES, wt_full);
+      }
       // CG=2: this rank's half of the weight rows (second image right after the first)
       const uint8_t* wpk = g.wpk + (size_t)rank * ((size_t)C::NCHUNK * C::NSTAGE_PER_CHUNK * C::B_STAGE);
       for (int pt = cid; pt < num_ptiles; pt += ncl) {
@@ -497,6 +587,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
     if (lane == 0) {
       int astage = 0, bstage = 0;
       uint32_t aphase = 0, bphase = 0;
+      if constexpr (TN > 0) {
+        mbar_wait(wt_full, 0);
+        mbar_arrive_remote(wt_full_peer, 0);
+      }
       for (int pt = cid; pt < num_ptiles; pt += ncl) {
         for (int c = 0; c < C::NCHUNK; c++) {
           mbar_wait(&a_full[astage], aphase);
@@ -594,7 +688,51 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
           if (++astage == C::NA) { astage = 0; aphase ^= 1; }
           if (++acc == AS) { acc = 0; tphase ^= 1; }
         }
-      } else
+      } else {
+      // ---- fused tail layer (UmmaCfg TN): the second GEMM of a tile is issued while the NEXT tile's main loop
+      // runs -- as soon as the epilogue has put the tile's activations into shared memory (a2_full), at the
+      // latest before the next tile's last chunk, so that the epilogue's second pass (which releases the
+      // accumulator stage the tile after next needs) never waits for the issuer.
+      int pend_acc = -1;            // accumulator stage whose tail GEMM is still to be issued
+      uint32_t pend_mask = 0;       // ... sub-tiles not yet issued
+      uint32_t a2phase = 0;
+      auto tail_step = [&](bool force) {
+        if constexpr (TN > 0) {
+          if (pend_acc < 0) return;
+#pragma unroll
+          for (int sb = 0; sb < S; sb++) {
+            if (!(pend_mask & (1u << sb))) continue;
+            // a warp-uniform decision (lane 0 probes): the lanes must stay converged for the election below
+            if (!force && __shfl_sync(0xffffffffu, (int)mbar_try(&a2_full[sb], a2phase), 0) == 0) continue;
+            mbar_wait(&a2_full[sb], a2phase);
+            tc_fence_after();
+            if (elect_one_sync()) {
+              constexpr uint32_t idesc_t1 = make_idesc(128 * CG, 2 * TN);   // a_hi x [w_hi | w_lo]
+              constexpr uint32_t idesc_t2 = make_idesc(128 * CG, TN);       // a_lo x w_hi
+              constexpr uint32_t wt_hi32 = (128u >> 4) | (1u << 14);
+              const uint32_t d2 = (uint32_t)((pend_acc * S + sb) * C::SUB_COLS);
+              const uint32_t a2 = (uint32_t)(C::A2_COL0 + sb * C::A2_COLS);  // K = 16 bf16 = 8 columns per step
+              const uint32_t wt_lo32 = (smem_u32(wt_smem) >> 4) | ((uint32_t)(TN * 24 >> 4) << 16);
+#pragma unroll
+              for (int j = 0; j < C::K2 / 16; j++)
+                umma_issue_ts<CG>(d2, a2 + (uint32_t)(8 * j), wt_lo32 + (uint32_t)(j * (C::WT_TAP >> 4)), wt_hi32, idesc_t1,
+                                  j == 0 ? 0u : 1u);
+#pragma unroll
+              for (int j = 0; j < C::K2 / 16; j++)
+                umma_issue_ts<CG>(d2, a2 + (uint32_t)(C::K2 / 2 + 8 * j), wt_lo32 + (uint32_t)(j * (C::WT_TAP >> 4)) + (uint32_t)TN,
+                                  wt_hi32, idesc_t2, 1u);
+              if (pend_mask == (1u << sb)) umma_done<CG>(&t2_full[pend_acc]);  // the last sub-tile of the tile
+            }
+            __syncwarp();
+            pend_mask &= ~(1u << sb);
+          }
+          if (pend_mask == 0) { pend_acc = -1; a2phase ^= 1; }
+        }
+      };
+      if constexpr (TN > 0) {  // the tail weights of both CTAs are in place
+        mbar_wait(wt_full, 0);
+        mbar_wait(wt_full_peer, 0);
+      }
       for (int pt = cid; pt < num_ptiles; pt += ncl) {
         if constexpr (CG == 2) mbar_wait(&t_empty[acc], tphase ^ 1);  // both CTAs' epilogues arrive here
         else mbar_wait(&t_empty[acc], tphase ^ 1);
@@ -610,6 +748,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
           const int blk = NBLK > 1 ? c / C::CPB : 0;
           const uint32_t d_base = d_tile + (uint32_t)(blk * C::BLK_COLS);
           for (int tg = 0; tg < C::NSTAGE_PER_CHUNK; tg++) {
+            tail_step(c == C::NCHUNK - 1 && tg == C::NSTAGE_PER_CHUNK - 1);
             if (!b_ready) mbar_wait(&b_full[bstage], bphase);
             if constexpr (CG == 2) mbar_wait(&b_full_peer[bstage], bphase);
             tc_fence_after();
@@ -635,8 +774,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
                 if constexpr (F8IN) {
 #pragma unroll
                   for (int s = 0; s < S; s++)  // [e4m3(lo*2^9) | e4m3(v)] x [e4m3(w*ws) ; e4m3(w_lo*ws*2^9)], K = 32
-                    umma_issue_f8<CG>(d_base + (uint32_t)(s * C::SUB_COLS + NPAD), a_tap + (uint32_t)(s * kSubW) + a_lo_off,
-                                      a_hi32, b_lo32 + b_wlo_off, b_hi32, idesc8, first);
+                    umma_issue_f8<CG>(d_base + (uint32_t)(s * C::SUB_COLS), a_tap + (uint32_t)(s * kSubW) + a_lo_off,
+                                      a_hi32, b_lo32 + b_wlo_off, b_hi32, idesc8, 1u);
                 } else if (!skip_lo) {
 #pragma unroll
                   for (int s = 0; s < S; s++)  // a_lo x w_hi
@@ -661,7 +800,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
           }
           if (++astage == C::NA) { astage = 0; aphase ^= 1; }
         }
+        if constexpr (TN > 0) { pend_acc = acc; pend_mask = (1u << S) - 1; }
         if (++acc == AS) { acc = 0; tphase ^= 1; }
+      }
+      tail_step(true);  // the last tile's tail GEMM
       }
     }
   } else if (warp < 8) {
@@ -686,6 +828,134 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
       // the two epilogue groups take alternate sub-tiles; a single sub-tile (S == 1) is split by channel
       // groups instead (a warp may read any columns of its own 32 TMEM lanes)
       static_assert(S > 1 || EPI == kEpiAct || EPI == kEpiDgrad, "S == 1 needs the channel-group split");
+      if constexpr (TN > 0) {
+        // ===== fused tail layer =====
+        // pass 1: this layer's activations (bias, ReLU, bf16 hi/lo) -> tensor memory as packed bf16 pairs
+        //         (K2/2 columns of hi parts, K2/2 of lo parts); then "sub-tile ready" to the issuer
+        constexpr int GC = 32, NG = NBLK * NPAD / GC, STEP = S == 1 ? 2 : 1;
+        static_assert(S <= 2 && NBLK == 1 && (NBLK * NPAD) % GC == 0 && NG % STEP == 0, "tail layer: tile shape");
+#pragma unroll 1
+        for (int s = (S == 1 ? 0 : egroup); s < S; s += 2) {
+          const uint32_t t_addr = tmem_base + lane_base + (uint32_t)((acc * S + s) * C::SUB_COLS);
+          const uint32_t a2_addr = tmem_base + lane_base + (uint32_t)(C::A2_COL0 + s * C::A2_COLS);
+          uint32_t vb[2][GC], wb[2][DUAL ? GC : 1];
+          auto issue1 = [&](int ch0, uint32_t* v, uint32_t* w) {
+#pragma unroll
+            for (int q = 0; q < GC; q += 16) tmem_ld16(t_addr + (uint32_t)(ch0 + q), v + q);
+            if constexpr (DUAL) {
+#pragma unroll
+              for (int q = 0; q < GC; q += 16) tmem_ld16(t_addr + (uint32_t)(ch0 + NPAD + q), w + q);
+            }
+          };
+          const int first = S == 1 ? egroup : 0;
+          issue1(first * GC, vb[0], wb[0]);
+#pragma unroll
+          for (int k = 0; k < NG / STEP; k++) {
+            const int c0 = (first + k * STEP) * GC;
+            tmem_ld_wait();
+            if (k + 1 < NG / STEP) issue1(c0 + STEP * GC, vb[(k + 1) & 1], wb[(k + 1) & 1]);
+            uint32_t hi[GC / 2], lo[GC / 2];   // bf16 pairs (channel c in the low half, c + 1 in the high half)
+#pragma unroll
+            for (int j = 0; j < GC; j += 2) {
+              const float a0 = F8IN ? __uint_as_float(vb[k & 1][j]) * dscale
+                                    : __uint_as_float(vb[k & 1][j]) + (DUAL ? __uint_as_float(wb[k & 1][DUAL ? j : 0]) : 0.f);
+              const float a1 = F8IN ? __uint_as_float(vb[k & 1][j + 1]) * dscale
+                                    : __uint_as_float(vb[k & 1][j + 1]) + (DUAL ? __uint_as_float(wb[k & 1][DUAL ? j + 1 : 0]) : 0.f);
+              split_bf16x2(fmaxf(a0 + s_bias[c0 + j], 0.f), fmaxf(a1 + s_bias[c0 + j + 1], 0.f), hi[j >> 1], lo[j >> 1]);
+            }
+            tmem_st16(a2_addr + (uint32_t)(c0 >> 1), hi);
+            tmem_st16(a2_addr + (uint32_t)(C::K2 / 2 + (c0 >> 1)), lo);
+          }
+          tmem_st_wait();
+          // the tail GEMM reads the columns just written and overwrites the accumulator columns just read
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if constexpr (CG == 2) mbar_arrive_remote_release(&a2_full[s], 0);
+            else mbar_arrive(&a2_full[s]);
+          }
+        }
+        // pass 2: the tail layer's accumulators (CONCAT: [a x w_hi | a_hi x w_lo]) -> bias, ReLU -> planes in HBM
+        mbar_wait(&t2_full[acc], tphase);
+        tc_fence_after();
+        constexpr int NG2 = TN / GC;
+        static_assert(S == 2 || NG2 % 2 == 0, "S == 1 splits the tail's channel groups over the two epilogue groups");
+        static_assert(TEPI == kTailAct || !OUT8, "the tap-stacked tail stores raw sums");
+#pragma unroll 1
+        for (int s = (S == 1 ? 0 : egroup); s < S; s += 2) {
+          const int gx = tx * C::TILE_W + s * kSubW + px;
+          const bool inside = gx < g.W && gy < g.H && tile_valid;
+          const uint32_t t_addr = tmem_base + lane_base + (uint32_t)((acc * S + s) * C::SUB_COLS);
+          const size_t pix = (size_t)gy * g.W + gx;
+          const size_t hw = (size_t)g.H * g.W;
+#pragma unroll
+          for (int k = (S == 1 ? egroup : 0); k < NG2; k += STEP) {
+            const int c0 = k * GC;
+            uint32_t v[GC], w[GC];
+#pragma unroll
+            for (int q = 0; q < GC; q += 16) tmem_ld16(t_addr + (uint32_t)(c0 + q), v + q);
+#pragma unroll
+            for (int q = 0; q < GC; q += 16) tmem_ld16(t_addr + (uint32_t)(TN + c0 + q), w + q);
+            tmem_ld_wait();
+            if (!inside || c0 >= g.cout) continue;
+            if constexpr (TEPI == kTailTaps) {
+              float* o = g.out_f32 + ((size_t)n * g.cout + c0) * hw + pix;
+#pragma unroll
+              for (int j = 0; j < GC; j++)
+                if (c0 + j < g.cout) o[(size_t)j * hw] = __uint_as_float(v[j]) + __uint_as_float(w[j]);
+            } else if constexpr (OUT8) {
+#pragma unroll
+              for (int q = 0; q < GC; q += 16) {
+                const int ch = c0 + q;
+                uint32_t hi[8], l8[4], h8[4];
+                float vmax = 0.f;
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                  float x[4], r[4];
+#pragma unroll
+                  for (int t = 0; t < 4; t++) {
+                    x[t] = fmaxf(__uint_as_float(v[q + j + t]) + __uint_as_float(w[q + j + t]) + s_bias2[ch + j + t], 0.f);
+                    vmax = fmaxf(vmax, x[t]);
+                  }
+#pragma unroll
+                  for (int t = 0; t < 4; t += 2) {
+                    const __nv_bfloat162 hh = __floats2bfloat162_rn(x[t], x[t + 1]);
+                    const uint32_t hb = *reinterpret_cast<const uint32_t*>(&hh);
+                    hi[(j + t) >> 1] = hb;
+                    r[t] = (x[t] - __uint_as_float(hb << 16)) * 512.f;
+                    r[t + 1] = (x[t + 1] - __uint_as_float(hb & 0xffff0000u)) * 512.f;
+                  }
+                  l8[j >> 2] = pack_e4m3x4(r[0], r[1], r[2], r[3]);
+                  h8[j >> 2] = pack_e4m3x4(x[0], x[1], x[2], x[3]);
+                }
+                if (!(vmax <= 448.f) && g.f8_overflow) atomicOr(g.f8_overflow, 1);
+                const ActDst& d = g.dst0;
+                uint4* p_hi = d.base + ((size_t)n * 2 * d.planes_half + (ch >> 3)) * hw + pix;
+                uint4* p_f8 = d.base + ((size_t)n * 2 * d.planes_half + d.planes_half + 2 * (ch >> 4)) * hw + pix;
+                p_hi[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                p_hi[hw] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+                p_f8[0] = make_uint4(l8[0], l8[1], l8[2], l8[3]);
+                p_f8[hw] = make_uint4(h8[0], h8[1], h8[2], h8[3]);
+              }
+            } else {
+#pragma unroll
+              for (int q = 0; q < GC; q += 8) {
+                const int ch = c0 + q;
+                uint32_t hi[4], lo[4];
+#pragma unroll
+                for (int j = 0; j < 8; j += 2)
+                  split_bf16x2(fmaxf(__uint_as_float(v[q + j]) + __uint_as_float(w[q + j]) + s_bias2[ch + j], 0.f),
+                               fmaxf(__uint_as_float(v[q + j + 1]) + __uint_as_float(w[q + j + 1]) + s_bias2[ch + j + 1], 0.f),
+                               hi[j >> 1], lo[j >> 1]);
+                const ActDst& d = g.dst0;
+                uint4* p_hi = d.base + ((size_t)n * 2 * d.planes_half + (ch >> 3)) * hw + pix;
+                p_hi[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                p_hi[(size_t)d.planes_half * hw] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+              }
+            }
+          }
+        }
+      } else {
 #pragma unroll 1
       for (int s = (S == 1 ? 0 : egroup); s < S; s += 2) {
         const int gx = tx * C::TILE_W + s * kSubW + px;
@@ -724,7 +994,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
             float f[GC];
 #pragma unroll
             for (int j = 0; j < GC; j++)
-              f[j] = F8IN ? fmaf(__uint_as_float(wb[k & 1][DUAL ? j : 0]), dscale, __uint_as_float(vb[k & 1][j]))
+              f[j] = F8IN ? __uint_as_float(vb[k & 1][j]) * dscale
                           : __uint_as_float(vb[k & 1][j]) + (DUAL ? __uint_as_float(wb[k & 1][DUAL ? j : 0]) : 0.f);
             if (c0 < g.cout && inside && !(g.dbg & 64)) {
               const size_t pix = (size_t)gy * g.W + gx;
@@ -825,7 +1095,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
           float f[16];
 #pragma unroll
           for (int j = 0; j < 16; j++)
-            f[j] = F8IN ? fmaf(__uint_as_float(w16[DUAL ? j : 0]), dscale, __uint_as_float(v16[j]))
+            f[j] = F8IN ? __uint_as_float(v16[j]) * dscale
                         : __uint_as_float(v16[j]) + (DUAL ? __uint_as_float(w16[DUAL ? j : 0]) : 0.f);
           if (inside) {
             const size_t hw = (size_t)g.H * g.W;
@@ -861,6 +1131,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
           }
         }
       }
+      }  // TN == 0
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -970,7 +1241,7 @@ static __global__ void pack_stages_cg2_kernel(const float* __restrict__ dense, _
 }
 
 // fp8 correction scheme (UmmaCfg FMT bit 0), CTA pairs: per rank, per (chunk, tap):
-//   part 0  [k8 0|1][rows][8 bf16]            w_hi                         (K = 16 bf16 MMA)
+//   part 0  [k8 0|1][rows][8 bf16]            w_hi * ws * 2^9              (K = 16 bf16 MMA)
 //   part 1  [k16 0|1][rows][16 fp8 (e4m3)]    w * ws  |  w_lo * ws * 2^9   (K = 32 fp8 MMA)
 // with rows = npad/2 of this rank.  scale[0] = ws (a power of two placing max|w| in [112, 224]),
 // scale[1] = 2^-9 / ws (what the epilogue multiplies the second accumulator with); scale[2] = max|w|.
@@ -1022,8 +1293,12 @@ static __global__ void pack_stages_f8_cg2_kernel(const float* __restrict__ dense
       wl[t] = w[t] - __bfloat162float(h);
     }
     uint8_t* base = out + (size_t)rank * per_rank + ((size_t)chunk * kk + tap) * tap_bytes;
-    // part 0: channel c = 2cp+t -> k8 = c / 8, element c % 8
+    // part 0: channel c = 2cp+t -> k8 = c / 8, element c % 8.  bf16(w) * (ws * 2^9): an exact power-of-two scaling
+    // that puts the bf16 product on the scale of the fp8 correction product (one shared accumulator)
     const int c = 2 * cp;
+#pragma unroll
+    for (int t = 0; t < 2; t++)
+      hb[t] = __bfloat16_as_ushort(__float2bfloat16_rn(__bfloat162float(__ushort_as_bfloat16(hb[t])) * ws * 512.f));
     *reinterpret_cast<uint32_t*>(base + ((size_t)(c / 8) * rows + row) * 16 + (c % 8) * 2) =
         (uint32_t)hb[0] | ((uint32_t)hb[1] << 16);
     // part 1: K half 0 = e4m3(w * ws), K half 1 = e4m3(w_lo * ws * 512), 16 channels per row
@@ -1073,10 +1348,10 @@ static int make_tmap(CUtensorMap* tm, void* base, int planes_total, int N, int H
 
 // Launch one convolution.  `slot` is the timing slot (common.cuh).
 template <int KS, int CIN_PAD, int NPAD, int S, int AS, int EPI, int CONCAT = 0, int NBLK = 1, int TPS = 1, int CG = 1,
-          int FMT = 0>
+          int FMT = 0, int TN = 0, int TEPI = 0>
 static int launch_conv(wn_handle* h, int slot, const uint8_t* wpk, const float* bias, void* in_base, ConvArgs a,
                        cudaStream_t stream) {
-  using C = UmmaCfg<KS, CIN_PAD, NPAD, S, AS, CONCAT, NBLK, TPS, CG, FMT>;
+  using C = UmmaCfg<KS, CIN_PAD, NPAD, S, AS, CONCAT, NBLK, TPS, CG, FMT, TN>;
   int rc = get_encoder();
   if (rc) return rc;
   CUtensorMap tm;
@@ -1089,7 +1364,7 @@ static int launch_conv(wn_handle* h, int slot, const uint8_t* wpk, const float* 
   a.tiles_x = (a.W + C::TILE_W - 1) / C::TILE_W;
   a.tiles_y = (a.H + C::TILE_H - 1) / C::TILE_H;
   const long long tiles = (long long)a.tiles_x * a.tiles_y * a.N;
-  auto kern = conv_umma_kernel<KS, CIN_PAD, NPAD, S, AS, EPI, CONCAT, NBLK, TPS, CG, FMT>;
+  auto kern = conv_umma_kernel<KS, CIN_PAD, NPAD, S, AS, EPI, CONCAT, NBLK, TPS, CG, FMT, TN, TEPI>;
   WN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
   TimedScope ts(h, slot, stream);
   if constexpr (CG == 2) {  // clusters of two CTAs (one TPC each); every pair takes two adjacent tiles at a time

@@ -419,6 +419,16 @@ def main():
             names_by_slot[0] = "cmg.conv1+refiner.conv1x3"
             names_by_slot[9] = "refiner.conv2x3"
             names_by_slot[10] = "refiner.conv3x3+gate"
+            flags = int(os.environ.get("WATERNET_B200_DEBUG_FLAGS", "0"), 0)
+            if mode != _lib.MODE_BF16X3 and not flags & 256:   # conv4 runs as the tail GEMM of conv3's launch
+                macs_by_slot[2] += macs_by_slot[3]
+                macs_by_slot[3] = 0
+                names_by_slot[2] = "cmg.conv3+conv4"
+            if mode != _lib.MODE_BF16X3 and not flags & 512:   # conv8 tap-stacked behind conv7 + a gather kernel
+                macs_by_slot[6] += macs_by_slot[7]
+                macs_by_slot[7] = 0
+                names_by_slot[6] = "cmg.conv7+conv8(taps)"
+                names_by_slot[7] = "cmg.conv8.gather+sigmoid"
         top = int(np.argmax(conv_ms))
         n_launch = max(slot_cnt[top], 1)
         avg_ms = conv_ms[top] / n_launch
@@ -497,7 +507,7 @@ def main():
             "kernel_ms_per_step": {name: round(slot_ms[i] / args.steps, 4) for i, name in enumerate(
                 names_by_slot + ["pack", "gate", "pre_stats", "pre_luts", "pre_apply", "post"]) if slot_cnt[i]},
             "kernel_tflops": {name: round(2.0 * macs_by_slot[i] * H * W * B * args.steps / (slot_ms[i] * 1e-3) / 1e12, 1)
-                              for i, name in enumerate(names_by_slot) if slot_cnt[i] and slot_ms[i] > 0},
+                              for i, name in enumerate(names_by_slot) if slot_cnt[i] and slot_ms[i] > 0 and macs_by_slot[i]},
             "cpu_baseline": cpu_baseline,
         }
         if world > 1:

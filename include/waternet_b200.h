@@ -102,6 +102,14 @@ int wn_preprocess_u8(wn_handle* h, const uint8_t* rgb, int n, int height, int wi
                      uint8_t* gc_u8, void* workspace, size_t workspace_bytes, void* stream);
 
 /*
+ * The grayscale branch of white_balance_transform (waternet/data.py:30-36: saturation levels 0.001 / 0.005):
+ * gray / out are uint8 (N,H,W).  No caller in the reference uses it; provided for completeness of data.py.
+ */
+size_t wn_white_balance_gray_workspace_bytes(int n, int h, int w);
+int wn_white_balance_gray_u8(wn_handle* h, const uint8_t* gray, uint8_t* out, int n, int height, int width,
+                             void* workspace, size_t workspace_bytes, void* stream);
+
+/*
  * Batched cv2.resize(img, (dst_w, dst_h)) of 8-bit 3-channel images, default INTER_LINEAR, as the training
  * dataset applies it per item (waternet/training_utils.py:94-103) -- bit-exact OpenCV arithmetic.  src_dev,
  * src_h, src_w are HOST arrays of n entries: device pointers to HWC uint8 images and their sizes.  dst_nhwc:
@@ -183,8 +191,10 @@ int wn_debug_forward_layer(wn_handle* h, const float* x, const float* wb, const 
 /*
  * Bring-up aid: switch pieces of the tensor-core conv pipeline off to attribute time (bit 0: epilogue
  * stores, bit 1: weight-stage refetch, bit 2: the lo passes).  RESULTS ARE WRONG with any of bits 0-7 set;
- * 0 restores normal operation.  Used by tools/pipeline_attribution.py only.  Bit 8 (256) is an A/B switch with
- * correct results: cmg.conv3 and conv4 run as two launches instead of conv3 with conv4 as its fused tail layer.
+ * 0 restores normal operation.  Used by tools/pipeline_attribution.py only.  Bits 8-10 are A/B switches with
+ * correct results: 256 = cmg.conv3 and conv4 as two launches (instead of conv4 as conv3's fused tail layer),
+ * 512 = cmg.conv7 and conv8 as two launches (instead of conv8 tap-stacked behind conv7 + gather), 1024 = (an
+ * experiment that measured slower, hence opt-in) the refiners' conv3 + gate tap-stacked behind their conv2.
  */
 int wn_debug_set_flags(wn_handle* h, int flags);
 

@@ -30,8 +30,19 @@ def white_balance_transform(im_rgb: np.ndarray) -> np.ndarray:
     ``(v - min) * 255 / (max - min)`` (``:46-48``) and a truncating uint8 cast
     (``:58``).
     """
+    if im_rgb.ndim == 2:
+        # grayscale branch, data.py:30-36: fixed saturation levels, one channel.  Unlike the RGB branch the flat
+        # array stays uint8 (`np.reshape`, :36), so the clipping assignments `temp[temp < q] = q` (:43-44) store the
+        # TRUNCATED quantiles: the stretch runs between floor(lo) and floor(hi)
+        flat = im_rgb.reshape(-1)
+        lo, hi = np.quantile(flat, [0.001, 1 - 0.005])
+        chan = flat.astype(np.float64)
+        chan[flat < lo] = np.floor(lo)
+        chan[flat > hi] = np.floor(hi)
+        bottom, top = chan.min(), chan.max()
+        return ((chan - bottom) * 255 / (top - bottom)).reshape(im_rgb.shape).astype(np.uint8)
     if im_rgb.ndim != 3 or im_rgb.shape[2] != 3:
-        raise ValueError("white_balance_transform expects an HWC RGB uint8 image")
+        raise ValueError("white_balance_transform expects an HWC RGB (or HW grayscale) uint8 image")
     h, w, _ = im_rgb.shape
     sums = [np.sum(im_rgb[:, :, c], axis=None) for c in range(3)]
     biggest = max(sums)

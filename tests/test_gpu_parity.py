@@ -889,7 +889,8 @@ def test_training_loss_curve_matches_the_reference_loop():
 def test_fused_tail_layers_equal_separate_launches():
     """Default mode: cmg.conv4 (1x1) runs as the tail GEMM of conv3's kernel (the activation tile goes back into tensor
     memory as the A operand of a second tcgen05.mma, UmmaCfg TN), and cmg.conv8 (3x3, 64 -> 3) as the tap-stacked tail
-    of conv7 plus a gather kernel.  Same arithmetic as the separate launches up to the fp32 summation order."""
+    of conv7 plus a gather kernel, the refiners' conv3 + gate likewise behind their conv2.  Same arithmetic as the
+    separate launches up to the fp32 summation order."""
     from waternet_b200 import _lib
     sd = ofw.synthetic_state_dict(3, 3.0)
     m = _model(3, 3.0, "default")
@@ -901,7 +902,9 @@ def test_fused_tail_layers_equal_separate_launches():
         cu = [t.cuda() for t in ins]
         res = {}
         with torch.no_grad():
-            for flags in (0, 256, 512, 768):   # 256: conv3 / conv4 as two launches; 512: conv7 / conv8 as two launches
+            # 256: conv3 / conv4 as two launches; 512: conv7 / conv8 as two launches; 1024: (opt-in experiment) the
+            # refiners' conv3 + gate tap-stacked behind their conv2; 768: nothing fused
+            for flags in (0, 256, 512, 1024, 768):
                 eng.set_debug_flags(flags)
                 try:
                     res[flags] = (m(*cu).cpu().numpy(),
@@ -916,7 +919,7 @@ def test_fused_tail_layers_equal_separate_launches():
         # error (~1e-4) appears between the two -- so the bar between them is that error, the bar against the
         # float64 oracle the parity bar
         ref64 = ofw.waternet_forward(sd, *ins, dtype=torch.float64).numpy()
-        for flags in (0, 256, 512):
+        for flags in (0, 256, 512, 1024):
             for got, want in zip(res[flags], res[768]):
                 _assert_close(got, want, tol=3e-4)
             _assert_close(res[flags][0], ref64)
@@ -937,3 +940,16 @@ def test_native_backward_is_bit_reproducible():
     for other in runs[1:]:
         for a, b in zip(runs[0], other):
             assert torch.equal(a, b)
+
+
+def test_white_balance_grayscale_branch(eng):
+    """data.py:30-36: the 2-D branch of white_balance_transform (no reference caller uses it; provided for completeness)."""
+    from waternet_b200 import data
+    rng = np.random.default_rng(4)
+    for shape, kind in [((40, 56), 0), ((112, 112), 0), ((7, 9), 0), ((33, 17), 1), ((200, 300), 1)]:
+        g = rng.integers(0, 256, shape, dtype=np.uint8) if kind == 0 else (rng.random(shape) * 90 + 40).astype(np.uint8)
+        assert np.array_equal(data.white_balance_transform(g), opre.white_balance_transform(g)), shape
+    batch = rng.integers(0, 256, (3, 24, 40), dtype=np.uint8)
+    got = eng.white_balance_gray(torch.from_numpy(batch).cuda()).cpu().numpy()
+    for i in range(3):
+        assert np.array_equal(got[i], opre.white_balance_transform(batch[i]))

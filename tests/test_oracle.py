@@ -110,3 +110,16 @@ def test_resize_restatement_matches_cv2():
     for sh, sw, dh, dw in cases:
         src = rng.integers(0, 256, (sh, sw, 3), dtype=np.uint8)
         assert np.array_equal(opre.resize_linear_u8(src, (dw, dh)), cv2.resize(src, (dw, dh))), (sh, sw, dh, dw)
+
+
+def test_grayscale_white_balance_matches_live_reference(reference_dir):
+    """The 2-D branch of white_balance_transform (data.py:30-36), including its uint8 truncation of the quantiles."""
+    spec = importlib.util.spec_from_file_location("_ref_data_gray", os.path.join(reference_dir, "waternet", "data.py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.dont_write_bytecode = True
+    spec.loader.exec_module(mod)
+    rng = np.random.default_rng(0)
+    for shape in [(40, 56), (7, 9), (33, 17), (112, 112)]:
+        for k in range(2):
+            g = rng.integers(0, 256, shape, dtype=np.uint8) if k == 0 else (rng.random(shape) * 90 + 40).astype(np.uint8)
+            assert np.array_equal(mod.white_balance_transform(g.copy()), opre.white_balance_transform(g)), (shape, k)

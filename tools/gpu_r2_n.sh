@@ -1,0 +1,15 @@
+#!/bin/bash
+# N-GPU pass (gpurun --gpus N): the NCCL sharded == single-GPU test (2 ranks) and the bench line at N ranks.
+# usage: gpu_r2_n.sh N
+cd "${GRAFT_REPO_ROOT:-/root/repo}"
+N="${1:-2}"
+mkdir -p gpurun_out
+nvidia-smi -L > gpurun_out/gpus_n$N.txt
+timeout 600 python -m pytest tests -m gpu -q -x -k "nccl" > gpurun_out/pytest_nccl.log 2>&1; echo "pytest nccl exit $?"; tail -3 gpurun_out/pytest_nccl.log
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 \
+  bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err; echo "bench n$N exit $?"
+python - <<PY
+import json
+d = json.loads([l for l in open("gpurun_out/bench_n$N.json") if l.startswith("{")][-1])
+print("value", d["value"], "e2e", d["e2e"]["value"], "ms", d["ms_per_step"]); print(d.get("multi_gpu"))
+PY

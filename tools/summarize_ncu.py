@@ -80,23 +80,51 @@ def launch_list(path, out):
     print(open(out).read())
 
 
-# the ten tensor-core launches of one forward pass, in launch order (conv_umma.cu: umma_forward_layers)
-FORWARD_LAUNCHES = ["cmg.conv1+refiner.conv1x3", "cmg.conv2", "cmg.conv3", "cmg.conv4", "cmg.conv5", "cmg.conv6",
-                    "cmg.conv7", "cmg.conv8", "refiner.conv2x3", "refiner.conv3x3+gate"]
+# kernel (template signature prefix) -> layer name of bench.py's kernel_ms_per_step
+LAYER_OF_KERNEL = [
+    ("conv_umma_kernel<7, 16, 224", "cmg.conv1+refiner.conv1x3"),
+    ("conv_umma_kernel<5, 128, 128", "cmg.conv2"),
+    ("conv_umma_kernel<3, 128, 128", "cmg.conv3"),       # "+conv4" when the template's tail width (12th argument) is 64
+    ("conv_umma_kernel<1, 128, 64", "cmg.conv4"),
+    ("conv_umma_kernel<7, 64, 64", "cmg.conv5"),
+    ("conv_umma_kernel<5, 64, 64", "cmg.conv6"),
+    ("conv_umma_kernel<3, 64, 64", "cmg.conv7"),         # "+conv8(taps)" with a tail of 32 columns
+    ("conv_umma_kernel<3, 64, 16", "cmg.conv8"),
+    ("gather_sigmoid_kernel", "cmg.conv8.gather+sigmoid"),
+    ("conv_umma_kernel<5, 96, 32", "refiner.conv2x3"),
+    ("conv_umma_kernel<3, 96, 16", "refiner.conv3x3+gate"),
+]
+
+
+def layer_name(kernel):
+    k = kernel.replace("wn::", "")
+    for prefix, name in LAYER_OF_KERNEL:
+        if k.startswith(prefix):
+            args = [a.strip() for a in k[k.index("<") + 1:k.rindex(">")].split(",")] if "<" in k else []
+            if name == "cmg.conv3" and len(args) >= 12 and args[11] == "64":
+                return "cmg.conv3+conv4"
+            if name == "cmg.conv7" and len(args) >= 12 and args[11] == "32":
+                return "cmg.conv7+conv8(taps)"
+            return name
+    return None
 
 
 def traffic(kernels_csv, out):
-    """DRAM bytes per launch of each forward kernel (one 1080p image per launch) -> the JSON bench.py reads
-    for roofline.traffic.  Input: the CSV written by `full` from a capture of exactly one forward pass."""
+    """DRAM bytes per launch of each forward kernel (one 1080p image per launch) -> the JSON bench.py reads for
+    roofline.traffic.  Input: the CSV written by `full` from a capture of one forward pass; the conditional
+    launches of the range guard's bf16x3 re-run (they return at once: < 20 us) are dropped."""
     import json
-    rows = list(csv.DictReader(open(kernels_csv)))
-    assert len(rows) == len(FORWARD_LAUNCHES), f"expected one forward pass ({len(FORWARD_LAUNCHES)} launches), got {len(rows)}"
+    rows = [r for r in csv.DictReader(open(kernels_csv)) if float(r["time_ms"]) > 0.02]
     doc = {"source": f"ncu --set full, one 1920x1080 image per launch ({kernels_csv}): "
                      "dram__bytes_read.sum + dram__bytes_write.sum",
            "height": 1080, "width": 1920, "kernels": {}}
-    for name, r in zip(FORWARD_LAUNCHES, rows):
+    for r in rows:
+        name = layer_name(r["kernel"])
+        assert name is not None and name not in doc["kernels"], f"unexpected or repeated kernel {r['kernel']}"
         doc["kernels"][name] = {"dram_bytes_per_image": (float(r["dram_read_GB"]) + float(r["dram_write_GB"])) * 1e9,
+                                "time_ms": float(r["time_ms"]), "tensor_pipe_pct": float(r["tensor_pipe_pct"] or 0),
                                 "kernel": r["kernel"]}
+    doc["total_dram_bytes_per_image"] = sum(k["dram_bytes_per_image"] for k in doc["kernels"].values())
     with open(out, "w") as f:
         json.dump(doc, f, indent=1)
     print(json.dumps(doc, indent=1))

@@ -36,6 +36,8 @@ _SIGNATURES = {
     "wn_preprocess_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "wn_preprocess_u8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "wn_white_balance_gray_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "wn_white_balance_gray_u8": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "wn_resize_u8": (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_int), POINTER(c_int), c_int, c_void_p, c_int, c_int,
                              c_int, c_void_p]),
     "wn_postprocess_u8": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),

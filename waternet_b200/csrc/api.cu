@@ -210,6 +210,25 @@ int wn_postprocess_u8(wn_handle* h, const float* out_nchw, uint8_t* out_nhwc, in
   return postprocess_u8(h, out_nchw, out_nhwc, n, height, width, (cudaStream_t)stream);
 }
 
+size_t wn_white_balance_gray_workspace_bytes(int n, int h, int w) {
+  if (n <= 0 || h <= 0 || w <= 0) return 0;
+  return white_balance_gray_workspace_bytes(n, h, w);
+}
+
+int wn_white_balance_gray_u8(wn_handle* h, const uint8_t* gray, uint8_t* out, int n, int height, int width,
+                             void* workspace, size_t workspace_bytes, void* stream) {
+  if (!h || !gray || !out || !workspace || n <= 0 || height <= 0 || width <= 0) {
+    set_error("wn_white_balance_gray_u8: bad argument");
+    return WN_E_INVALID;
+  }
+  if ((size_t)height * width > (size_t)0x7fffffff / 3 || n > 65535) {
+    set_error("image too large: n=%d h=%d w=%d", n, height, width);
+    return WN_E_UNSUPPORTED;
+  }
+  DeviceGuard guard(h->device);
+  return white_balance_gray_u8(h, gray, out, n, height, width, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
 int wn_resize_u8(wn_handle* h, const uint8_t* const* src_dev, const int* src_h, const int* src_w, int n,
                  uint8_t* dst_nhwc, int dst_h, int dst_w, int swap_rb, void* stream) {
   if (!h || !src_dev || !src_h || !src_w || !dst_nhwc || n <= 0 || dst_h <= 0 || dst_w <= 0) {

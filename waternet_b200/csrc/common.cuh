@@ -127,6 +127,9 @@ int preprocess_u8(wn_handle* h, const uint8_t* rgb, int n, int height, int width
                   void* workspace, size_t workspace_bytes, cudaStream_t stream);
 int postprocess_u8(wn_handle* h, const float* out_nchw, uint8_t* out_nhwc, int n, int height,
                    int width, cudaStream_t stream);
+size_t white_balance_gray_workspace_bytes(int n, int h, int w);
+int white_balance_gray_u8(wn_handle* h, const uint8_t* gray, uint8_t* out, int n, int height, int width,
+                          void* workspace, size_t workspace_bytes, cudaStream_t stream);
 int resize_u8(wn_handle* h, const uint8_t* const* src, const int* src_h, const int* src_w, int n, uint8_t* dst,
               int dst_h, int dst_w, int swap_rb, cudaStream_t stream);
 // transform + cat[x, wb, he, gc] straight into the first layer's operand planes: planes[n][2][H*W] of 16 B

@@ -131,12 +131,67 @@ static const UmmaLayerSpec kSpecs[kNumUmmaLayers] = {
 
 static int spec_slot(int li) { return kSpecs[li].slot; }
 
-// OIHW [co][ci][kk] -> dense [kk * co rows][ci]: row 3 * tap + c holds tap's filter of output channel c
-static __global__ void scatter_tapstack_kernel(const float* __restrict__ src, float* __restrict__ dense, int co, int ci, int kk) {
+// OIHW [co][ci][kk] -> dense [kk * co rows][ld]: row co * tap + c holds tap's filter of output channel c
+static __global__ void scatter_tapstack_kernel(const float* __restrict__ src, float* __restrict__ dense, int co, int ci, int kk,
+                                               int ld) {
   const int total = co * ci * kk;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int t = i % kk, c = (i / kk) % ci, o = i / (kk * ci);
-    dense[(size_t)(t * co + o) * ci + c] = src[i];
+    dense[(size_t)(t * co + o) * ld + c] = src[i];
+  }
+}
+// The second half of the three refiners' tap-stacked conv3 + the gated sum (net.py:68-70, 79, 104-108):
+//   refined[r][c] = relu(bias[3r + c] + sum over the 3x3 taps of taps[n][27 r + 3 tap + c][y + ky - 1][x + kx - 1])
+//   out[c]        = refined[0][c] * cm[0] + refined[1][c] * cm[1] + refined[2][c] * cm[2]
+// written as fp32 NCHW and/or ten2arr'd uint8 NHWC; refined_out optionally receives the nine refined planes.
+// HBM-bound: 324 B/px of partial sums read exactly once, 12 B/px of maps, 3..48 B/px written.
+static __global__ void __launch_bounds__(256)
+gather_gate_kernel(const float* __restrict__ taps, const float* __restrict__ bias, const float* __restrict__ cm,
+                   float* __restrict__ out_f32, uint8_t* __restrict__ out_u8, float* __restrict__ refined_out, int H, int W) {
+  const int x = blockIdx.x * 64 + threadIdx.x, y = blockIdx.y * 4 + threadIdx.y, n = blockIdx.z;
+  if (x >= W || y >= H) return;
+  const size_t hw = (size_t)H * W, pix = (size_t)y * W + x;
+  const float* t = taps + (size_t)n * 81 * hw;
+  float r[9];
+#pragma unroll
+  for (int j = 0; j < 9; j++) r[j] = bias[j];
+#pragma unroll
+  for (int ky = 0; ky < 3; ky++) {
+    const int yy = y + ky - 1;
+    if (yy < 0 || yy >= H) continue;
+#pragma unroll
+    for (int kx = 0; kx < 3; kx++) {
+      const int xx = x + kx - 1;
+      if (xx < 0 || xx >= W) continue;
+      const float* p = t + (size_t)((ky * 3 + kx) * 3) * hw + (size_t)yy * W + xx;
+#pragma unroll
+      for (int rr = 0; rr < 3; rr++)
+#pragma unroll
+        for (int c = 0; c < 3; c++) r[3 * rr + c] += p[(size_t)(27 * rr + c) * hw];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 9; j++) r[j] = fmaxf(r[j], 0.f);
+  if (refined_out) {
+#pragma unroll
+    for (int j = 0; j < 9; j++) refined_out[((size_t)n * 9 + j) * hw + pix] = r[j];
+  }
+  if (cm) {
+    const size_t o = (size_t)n * 3 * hw + pix;
+    const float c0 = cm[o], c1 = cm[o + hw], c2 = cm[o + 2 * hw];
+    float v[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+      v[c] = __fadd_rn(__fadd_rn(__fmul_rn(r[c], c0), __fmul_rn(r[3 + c], c1)), __fmul_rn(r[6 + c], c2));
+    if (out_f32) {
+#pragma unroll
+      for (int c = 0; c < 3; c++) out_f32[o + c * hw] = v[c];
+    }
+    if (out_u8) {  // ten2arr (hubconf.py:24-34)
+      uint8_t* q = out_u8 + ((size_t)n * hw + pix) * 3;
+#pragma unroll
+      for (int c = 0; c < 3; c++) q[c] = (uint8_t)(int)__fmul_rn(fminf(fmaxf(v[c], 0.0f), 1.0f), 255.0f);
+    }
   }
 }
 // cm[n][c][y][x] = sigmoid(bias[c] + sum over the 3x3 taps of taps[n][3 * tap + c][y + ky - 1][x + kx - 1]), zero outside
@@ -175,6 +230,7 @@ static size_t stage8_bytes_total(const UmmaLayerSpec& s) {
 struct UmmaWeights {
   uint8_t* stages8[kNumUmmaLayers];  // fp8-correction weight images (has_f8_form layers)
   float* scale8[kNumUmmaLayers];     // {ws, 2^-9 / ws, max|w|, -}
+  uint8_t* tailr3;                   // the three refiners' conv3 tap-stacked (block-diagonal, 3 x 27 columns) as the tail of their conv2
   uint8_t* tail8;                    // cmg.conv8 tap-stacked (27 = 9 taps x 3 channels columns) as the tail layer of conv7
   uint8_t* tail4;                    // cmg.conv4 as the tail layer of conv3: two per-rank images, CG=2 CONCAT layout
   int* overflow_dev;                 // sticky: an activation left the e4m3 range in the fp8-correction mode
@@ -203,6 +259,7 @@ int umma_pack_weights(wn_handle* h, const float* const* params, cudaStream_t str
   if (!h->umma->dense) WN_CUDA(cudaMalloc(&h->umma->dense, (size_t)224 * 128 * 49 * sizeof(float)));
   if (!h->umma->tail4) WN_CUDA(cudaMalloc(&h->umma->tail4, (size_t)2 * 8 * 64 * 48));
   if (!h->umma->tail8) WN_CUDA(cudaMalloc(&h->umma->tail8, (size_t)2 * 4 * 32 * 48));
+  if (!h->umma->tailr3) WN_CUDA(cudaMalloc(&h->umma->tailr3, (size_t)2 * 6 * 32 * 32));
   if (!h->umma->overflow_dev) WN_CUDA(cudaMalloc(&h->umma->overflow_dev, sizeof(int)));
   if (!h->umma->overflow_host) WN_CUDA(cudaHostAlloc(&h->umma->overflow_host, sizeof(int), cudaHostAllocDefault));
   UmmaWeights* u = h->umma;
@@ -254,9 +311,19 @@ int umma_pack_weights(wn_handle* h, const float* const* params, cudaStream_t str
     if (li == kC8) {  // tap-stacked form: dense [32 rows = 3 * tap + channel (27 used)][64 input channels], a 1x1 layer
       float* stacked = u->dense + (size_t)16 * 64 * 9;  // behind conv8's own [16][64][9] matrix
       WN_CUDA(cudaMemsetAsync(stacked, 0, (size_t)32 * 64 * sizeof(float), stream));
-      scatter_tapstack_kernel<<<8, 256, 0, stream>>>(W(7), stacked, 3, 64, 9);
+      scatter_tapstack_kernel<<<8, 256, 0, stream>>>(W(7), stacked, 3, 64, 9, 64);
       WN_LAUNCH_CHECK(h);
       pack_stages_cg2_kernel<<<64, 256, 0, stream>>>(stacked, (__nv_bfloat16*)u->tail8, 32, 64, 1, 1, 1);
+      WN_LAUNCH_CHECK(h);
+    }
+    if (li == kR3) {  // tap-stacked, block-diagonal: dense [96 rows: 32 r + 3 tap + c][96 channels: 32 r + ci], a 1x1 layer
+      float* stacked = u->dense + (size_t)16 * 96 * 9;  // behind the refiners' own [16][96][9] matrix
+      WN_CUDA(cudaMemsetAsync(stacked, 0, (size_t)96 * 96 * sizeof(float), stream));
+      for (int r = 0; r < 3; r++) {
+        scatter_tapstack_kernel<<<8, 256, 0, stream>>>(W(8 + 3 * r + 2), stacked + ((size_t)32 * r * 96 + 32 * r), 3, 32, 9, 96);
+        WN_LAUNCH_CHECK(h);
+      }
+      pack_stages_cg2_kernel<<<64, 256, 0, stream>>>(stacked, (__nv_bfloat16*)u->tailr3, 32, 96, 1, 0, 3);
       WN_LAUNCH_CHECK(h);
     }
     if (has_f8_form(li)) {
@@ -284,6 +351,7 @@ void umma_free(wn_handle* h) {
   if (h->umma->dense) cudaFree(h->umma->dense);
   if (h->umma->tail4) cudaFree(h->umma->tail4);
   if (h->umma->tail8) cudaFree(h->umma->tail8);
+  if (h->umma->tailr3) cudaFree(h->umma->tailr3);
   if (h->umma->overflow_dev) cudaFree(h->umma->overflow_dev);
   if (h->umma->overflow_host) cudaFreeHost(h->umma->overflow_host);
   free(h->umma);
@@ -332,6 +400,14 @@ size_t umma_forward_workspace_bytes(int n, int h, int w) {
 // then has two tiles of slack before its accumulator stage is needed again
 #ifndef WN_C34_AS
 #define WN_C34_AS 3
+#endif
+// conv5 / conv6 (64 -> 64): sub-tiles per CTA tile.  One accumulator of 64 columns per sub-tile: S=4 double-buffered fills
+// TMEM; more sub-tiles per weight stage = less weight-stage fill traffic on the shared-memory port these layers are bound by
+#ifndef WN_F8_C56_S
+#define WN_F8_C56_S 2
+#endif
+#ifndef WN_R23_AS
+#define WN_R23_AS 3   // refiner conv2 with the tap-stacked conv3 tail: one sub-tile = 96 accumulator columns per stage + 96 for its bf16 copy
 #endif
 #ifndef WN_C78_AS
 #define WN_C78_AS 3   // conv7 with the tap-stacked conv8 tail: 2 x 64 accumulator columns per stage + 2 x 64 for the bf16 tiles
@@ -483,10 +559,10 @@ int umma_forward_layers(wn_handle* h, const float* const in[4], const int64_t st
       }
       if (dump(3, a4, 64, 1)) return WN_OK;
       act(a5, 64, nullptr, 0);
-      if ((rc = launch_umma<7, 64, 64, 2, 2, kEpiAct, 0, 1, 7, 2, IN8 | OUT8>(h, kC5, a4, a, stream))) return rc;
+      if ((rc = launch_umma<7, 64, 64, WN_F8_C56_S, 2, kEpiAct, 0, 1, 7, 2, IN8 | OUT8>(h, kC5, a4, a, stream))) return rc;
       if (dump(4, a5, 64, 1)) return WN_OK;
       act(a6, 64, nullptr, 0);
-      if ((rc = launch_umma<5, 64, 64, 2, 2, kEpiAct, 0, 1, 5, 2, IN8 | OUT8>(h, kC6, a5, a, stream))) return rc;
+      if ((rc = launch_umma<5, 64, 64, WN_F8_C56_S, 2, kEpiAct, 0, 1, 5, 2, IN8 | OUT8>(h, kC6, a5, a, stream))) return rc;
       if (dump(5, a6, 64, 1)) return WN_OK;
       float* const cm_dst = dbg_layer == 7 ? dbg_dst : b.cm;
       if (dbg_layer != 6 && !(h->dbg_flags & 512)) {
@@ -517,6 +593,26 @@ int umma_forward_layers(wn_handle* h, const float* const in[4], const int64_t st
       if (dbg_layer == 7) return WN_OK;
     }
     if (!want_ref) return WN_OK;
+    if (dbg_layer != 9 && (h->dbg_flags & 1024)) {
+      // EXPERIMENT, off by default (flag bit 10): the refiners' conv2 with their conv3 (3x3, 32 -> 3 each) tap-stacked
+      // as a block-diagonal fused tail layer: 81 partial-sum planes (324 B/px) instead of 96 channels (384 B/px);
+      // gather_gate_kernel adds the nine shifted planes per output, bias, ReLU and the gated sum (net.py:65-70,
+      // 104-108).  Correct (tests), but measured SLOWER than the two launches: 22.4 + gather vs 15.7 + 6.2 ms per
+      // batch -- the one-sub-tile tile this needs (TMEM: 96 accumulator + 96 operand columns per sub-tile) pays the
+      // tensor-memory-operand drain once per 128 pixels, and the refiners' conv2 is already bound by its operand
+      // reads (profiles/r2_ab_fused_tails.log).
+      float* taps = reinterpret_cast<float*>(b.r[2]);
+      a.out_f32 = taps;
+      a.wtail = h->umma->tailr3;
+      a.bias2 = nullptr;
+      if ((rc = launch_umma<5, 96, 32, 1, WN_R23_AS, kEpiAct, 0, 3, 25, 2, IN8, 96, kTailTaps>(h, kR2, b.r[1], a, stream))) return rc;
+      a.wtail = nullptr;
+      TimedScope ts(h, spec_slot(kR3), stream);
+      gather_gate_kernel<<<dim3((W + 63) / 64, (H + 3) / 4, n), dim3(64, 4), 0, stream>>>(
+          taps, h->umma->bias[kR3], o.stack == kStackRefiners ? nullptr : b.cm, out, o.out_u8, b.refined, H, W);
+      WN_LAUNCH_CHECK(h);
+      return WN_OK;
+    }
     act(b.r[2], 96, nullptr, 0);
     if ((rc = launch_umma<5, 96, 32, 2, WN_F8_R2_AS, kEpiAct, 0, 3, 5, 2, IN8>(h, kR2, b.r[1], a, stream))) return rc;
     if (dump(9, b.r[2], 96)) return WN_OK;

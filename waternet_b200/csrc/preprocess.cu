@@ -220,7 +220,7 @@ __device__ double np_quantile_from_cum(const uint32_t* cum, int n, double q) {
 __global__ void __launch_bounds__(256)
 luts_kernel(const uint32_t* __restrict__ tile_hist, const uint32_t* __restrict__ rgb_hist,
             int npix, int clip, float lut_scale, uint8_t* __restrict__ clahe_lut,
-            uint8_t* __restrict__ wb_lut) {
+            uint8_t* __restrict__ wb_lut, int gray) {
   __shared__ uint32_t s_warp[8];
   __shared__ uint32_t s_cum[3][256];
   __shared__ unsigned long long s_sum[3];
@@ -265,7 +265,12 @@ luts_kernel(const uint32_t* __restrict__ tile_hist, const uint32_t* __restrict__
     const int c = tid;
     unsigned long long mx = max(s_sum[0], max(s_sum[1], s_sum[2]));
     double lo = 0.0, hi = 255.0;
-    if (s_sum[c] != 0ull) {
+    if (gray) {
+      // grayscale branch (data.py:30-36): fixed saturation levels 0.001 / 0.005, no channel ratios; its flat array
+      // stays uint8, so the clipping assignments (data.py:43-44) store the TRUNCATED quantiles
+      lo = floor(np_quantile_from_cum(s_cum[c], npix, 0.001));
+      hi = floor(np_quantile_from_cum(s_cum[c], npix, __dsub_rn(1.0, 0.005)));
+    } else if (s_sum[c] != 0ull) {
       double ratio = __ddiv_rn((double)mx, (double)s_sum[c]);
       double sat = __dmul_rn(0.005, ratio);
       double qlo = sat, qhi = __dsub_rn(1.0, sat);
@@ -496,7 +501,41 @@ size_t preprocess_workspace_bytes(int n, int, int) {
 
 static int preprocess_run(wn_handle* h, const uint8_t* rgb, int n, int H, int W, float* x, float* wb,
                           float* he, float* gc, uint8_t* wb_u8, uint8_t* he_u8, uint8_t* gc_u8, uint4* planes,
-                          void* workspace, size_t workspace_bytes, cudaStream_t stream);
+                          void* workspace, size_t workspace_bytes, cudaStream_t stream, int gray = 0);
+
+// grayscale branch of white_balance_transform (data.py:30-36, 38-58 with p = 1): the 2-D image runs through the RGB
+// machinery as r = g = b with the branch's fixed saturation levels; channel 0 of the result is the answer
+__global__ void gray_expand_kernel(const uint8_t* __restrict__ g, uint8_t* __restrict__ rgb, size_t npix) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (size_t)gridDim.x * blockDim.x) {
+    const uint8_t v = g[i];
+    rgb[3 * i] = v; rgb[3 * i + 1] = v; rgb[3 * i + 2] = v;
+  }
+}
+__global__ void gray_extract_kernel(const uint8_t* __restrict__ rgb, uint8_t* __restrict__ g, size_t npix) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (size_t)gridDim.x * blockDim.x) g[i] = rgb[3 * i];
+}
+size_t white_balance_gray_workspace_bytes(int n, int h, int w) {
+  return align_up(preprocess_workspace_bytes(n, h, w), 256) + 2 * align_up((size_t)n * h * w * 3, 256);
+}
+int white_balance_gray_u8(wn_handle* h, const uint8_t* gray, uint8_t* out, int n, int H, int W, void* workspace,
+                          size_t workspace_bytes, cudaStream_t stream) {
+  if (workspace_bytes < white_balance_gray_workspace_bytes(n, H, W)) {
+    set_error("white balance (gray) workspace too small");
+    return WN_E_WORKSPACE;
+  }
+  uint8_t* ws = (uint8_t*)workspace;
+  const size_t pre_b = align_up(preprocess_workspace_bytes(n, H, W), 256), img_b = align_up((size_t)n * H * W * 3, 256);
+  uint8_t* rgb = ws + pre_b;
+  uint8_t* wb = rgb + img_b;
+  const size_t npix = (size_t)n * H * W;
+  gray_expand_kernel<<<1024, 256, 0, stream>>>(gray, rgb, npix);
+  WN_LAUNCH_CHECK(h);
+  int rc = preprocess_run(h, rgb, n, H, W, nullptr, nullptr, nullptr, nullptr, wb, nullptr, nullptr, nullptr, ws, pre_b, stream, 1);
+  if (rc) return rc;
+  gray_extract_kernel<<<1024, 256, 0, stream>>>(wb, out, npix);
+  WN_LAUNCH_CHECK(h);
+  return WN_OK;
+}
 
 int preprocess_u8(wn_handle* h, const uint8_t* rgb, int n, int H, int W, float* x, float* wb,
                   float* he, float* gc, uint8_t* wb_u8, uint8_t* he_u8, uint8_t* gc_u8,
@@ -513,7 +552,7 @@ int preprocess_u8_planes(wn_handle* h, const uint8_t* rgb, int n, int H, int W, 
 
 static int preprocess_run(wn_handle* h, const uint8_t* rgb, int n, int H, int W, float* x, float* wb,
                           float* he, float* gc, uint8_t* wb_u8, uint8_t* he_u8, uint8_t* gc_u8, uint4* planes,
-                          void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+                          void* workspace, size_t workspace_bytes, cudaStream_t stream, int gray) {
   if (workspace_bytes < preprocess_workspace_bytes(n, H, W)) {
     set_error("preprocess workspace too small: %zu < %zu", workspace_bytes,
               preprocess_workspace_bytes(n, H, W));
@@ -551,7 +590,7 @@ static int preprocess_run(wn_handle* h, const uint8_t* rgb, int n, int H, int W,
   {
   TimedScope ts(h, kSlotLuts, stream);
   luts_kernel<<<dim3(65, n), 256, 0, stream>>>(tile_hist, rgb_hist, H * W, g.clip, g.lut_scale,
-                                               clahe_lut, wb_lut);
+                                               clahe_lut, wb_lut, gray);
   WN_LAUNCH_CHECK(h);
   }
   ApplyOut ao;

@@ -57,13 +57,6 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank)
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(rank));
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
-// ... with cluster-scope release: what was written before (shared-memory data another SM's issuer hands to the
-// tensor cores) is ordered before the arrival
-__device__ __forceinline__ void mbar_arrive_remote_release(uint64_t* bar, uint32_t rank) {
-  uint32_t remote;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(rank));
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
-}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -316,7 +309,12 @@ template <int KS, int CIN_PAD, int NPAD, int S, int AS, int CONCAT = 0, int NBLK
 struct UmmaCfg {
   static constexpr int K2 = NPAD * NBLK;                                 // tail GEMM K = this layer's output channels
   static constexpr int A2_COLS = TN ? K2 : 0;                            // TMEM columns per sub-tile: K2/2 hi pairs | K2/2 lo pairs
-  static constexpr int WT_TAP = TN * 48;                                 // per K=16 step and rank: [k8][TN | TN/2 rows][16 B]
+  // tail weights per K=16 step and rank.  One block (NBLK == 1), CONCAT form: [k8][TN | TN/2 rows][16 B] (a_hi x [w_hi|w_lo],
+  // a_lo x w_hi).  Block-diagonal (the three refiners): TN / NBLK columns per block, three passes into the same
+  // columns, [hi|lo][k8][TN / NBLK / 2 rows][16 B]
+  static constexpr bool TAIL_BLK = NBLK > 1;
+  static constexpr int TNB = TN / NBLK;                                  // tail output columns per block
+  static constexpr int WT_TAP = TAIL_BLK ? TNB * 32 : TN * 48;
   static constexpr int WT_BYTES = TN ? (K2 / 16) * WT_TAP : 0;
   static constexpr int TAIL_BYTES = (WT_BYTES + 1023) / 1024 * 1024;
 
@@ -368,7 +366,7 @@ struct UmmaCfg {
   static_assert(NA >= 1, "halo tile does not fit in shared memory");
   static_assert(TMEM_COLS_USED <= 512, "accumulators do not fit in TMEM");
   static_assert(NPAD % 16 == 0 && NPAD >= 16 && NPAD <= 256, "invalid UMMA N");
-  static_assert(TN == 0 || (CG == 2 && AS >= 2 && !WRAP && TN % 32 == 0 && 2 * TN <= SUB_COLS),
+  static_assert(TN == 0 || (CG == 2 && AS >= 2 && !WRAP && TNB % 32 == 0 && (TAIL_BLK ? 1 : 2) * TN <= SUB_COLS),
                 "tail layer: CTA pairs, multi-buffered accumulators, and its accumulators fit the drained columns");
 };
 
@@ -689,44 +687,77 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
           if (++acc == AS) { acc = 0; tphase ^= 1; }
         }
       } else {
-      // ---- fused tail layer (UmmaCfg TN): the second GEMM of a tile is issued while the NEXT tile's main loop
-      // runs -- as soon as the epilogue has put the tile's activations into shared memory (a2_full), at the
-      // latest before the next tile's last chunk, so that the epilogue's second pass (which releases the
-      // accumulator stage the tile after next needs) never waits for the issuer.
+      // ---- fused tail layer (UmmaCfg TN): the second GEMM of a tile is issued early in the NEXT tile's main loop:
+      // polled for at the first weight stages, waited for before stage kTailForceAt.  MMAs execute in issue order,
+      // so a tail GEMM issued behind a deep queue of the next tile's MMAs would hold the (single-buffered) bf16 copy
+      // of its tile -- and with it the epilogue's next first pass -- for the whole queue; issued after two stages it
+      // runs ~2 stages after its tile completed, while those two stages keep the tensor pipe busy during the
+      // epilogue's first pass.  (ncu, conv7 + tap-stacked conv8: 12.4k -> ~8.6k cycles per tile.)
+#ifndef WN_TAIL_FORCE_AT
+#define WN_TAIL_FORCE_AT 2
+#endif
+      constexpr int kTailForceAt = C::NCHUNK * C::NSTAGE_PER_CHUNK > WN_TAIL_FORCE_AT ? WN_TAIL_FORCE_AT
+                                                                                     : C::NCHUNK * C::NSTAGE_PER_CHUNK - 1;
       int pend_acc = -1;            // accumulator stage whose tail GEMM is still to be issued
-      uint32_t pend_mask = 0;       // ... sub-tiles not yet issued
       uint32_t a2phase = 0;
       auto tail_step = [&](bool force) {
         if constexpr (TN > 0) {
           if (pend_acc < 0) return;
+          // All sub-tiles of the tile go in ONE batch: a tcgen05.mma that takes A from tensor memory starts only
+          // after the MMAs in flight have drained (~1.5-1.8k cycles of idle tensor pipe per batch, ncu), so a tile
+          // pays that once, not once per sub-tile.  The decision is warp-uniform (lane 0 probes): the lanes must
+          // stay converged for the election below.
+          if (!force) {
+            int ready = 1;
 #pragma unroll
-          for (int sb = 0; sb < S; sb++) {
-            if (!(pend_mask & (1u << sb))) continue;
-            // a warp-uniform decision (lane 0 probes): the lanes must stay converged for the election below
-            if (!force && __shfl_sync(0xffffffffu, (int)mbar_try(&a2_full[sb], a2phase), 0) == 0) continue;
-            mbar_wait(&a2_full[sb], a2phase);
-            tc_fence_after();
-            if (elect_one_sync()) {
-              constexpr uint32_t idesc_t1 = make_idesc(128 * CG, 2 * TN);   // a_hi x [w_hi | w_lo]
-              constexpr uint32_t idesc_t2 = make_idesc(128 * CG, TN);       // a_lo x w_hi
+            for (int sb = 0; sb < S; sb++) ready &= (int)mbar_try(&a2_full[sb], a2phase);
+            if (__shfl_sync(0xffffffffu, ready, 0) == 0) return;
+          }
+#pragma unroll
+          for (int sb = 0; sb < S; sb++) mbar_wait(&a2_full[sb], a2phase);
+          tc_fence_after();
+          if (elect_one_sync()) {
+#pragma unroll
+            for (int sb = 0; sb < S; sb++) {
               constexpr uint32_t wt_hi32 = (128u >> 4) | (1u << 14);
               const uint32_t d2 = (uint32_t)((pend_acc * S + sb) * C::SUB_COLS);
               const uint32_t a2 = (uint32_t)(C::A2_COL0 + sb * C::A2_COLS);  // K = 16 bf16 = 8 columns per step
-              const uint32_t wt_lo32 = (smem_u32(wt_smem) >> 4) | ((uint32_t)(TN * 24 >> 4) << 16);
+              if constexpr (C::TAIL_BLK) {
+                // block-diagonal tail (three refiners): block b = channels [K2/NBLK * b, ...) -> columns [TNB * b, ...),
+                // three bf16 passes per K = 16 step into the same columns
+                constexpr uint32_t idesc_b = make_idesc(128 * CG, C::TNB);
+                constexpr int SPB = C::K2 / 16 / NBLK;  // K = 16 steps per block
+                const uint32_t wt_lo32 = (smem_u32(wt_smem) >> 4) | ((uint32_t)(C::TNB * 8 >> 4) << 16);  // LBO: k8 halves
 #pragma unroll
-              for (int j = 0; j < C::K2 / 16; j++)
-                umma_issue_ts<CG>(d2, a2 + (uint32_t)(8 * j), wt_lo32 + (uint32_t)(j * (C::WT_TAP >> 4)), wt_hi32, idesc_t1,
-                                  j == 0 ? 0u : 1u);
+                for (int blk = 0; blk < NBLK; blk++)
 #pragma unroll
-              for (int j = 0; j < C::K2 / 16; j++)
-                umma_issue_ts<CG>(d2, a2 + (uint32_t)(C::K2 / 2 + 8 * j), wt_lo32 + (uint32_t)(j * (C::WT_TAP >> 4)) + (uint32_t)TN,
-                                  wt_hi32, idesc_t2, 1u);
-              if (pend_mask == (1u << sb)) umma_done<CG>(&t2_full[pend_acc]);  // the last sub-tile of the tile
+                  for (int j = 0; j < SPB; j++) {
+                    const int step = blk * SPB + j;
+                    const uint32_t w = wt_lo32 + (uint32_t)(step * (C::WT_TAP >> 4));
+                    const uint32_t d = d2 + (uint32_t)(blk * C::TNB);
+                    umma_issue_ts<CG>(d, a2 + (uint32_t)(8 * step), w, wt_hi32, idesc_b, j == 0 ? 0u : 1u);                     // a_hi x w_hi
+                    umma_issue_ts<CG>(d, a2 + (uint32_t)(C::K2 / 2 + 8 * step), w, wt_hi32, idesc_b, 1u);                       // a_lo x w_hi
+                    umma_issue_ts<CG>(d, a2 + (uint32_t)(8 * step), w + (uint32_t)(C::TNB * 16 >> 4), wt_hi32, idesc_b, 1u);    // a_hi x w_lo
+                  }
+              } else {
+                constexpr uint32_t idesc_t1 = make_idesc(128 * CG, 2 * TN);   // a_hi x [w_hi | w_lo]
+                constexpr uint32_t idesc_t2 = make_idesc(128 * CG, TN);       // a_lo x w_hi
+                const uint32_t wt_lo32 = (smem_u32(wt_smem) >> 4) | ((uint32_t)(TN * 24 >> 4) << 16);
+#pragma unroll
+                for (int j = 0; j < C::K2 / 16; j++)
+                  umma_issue_ts<CG>(d2, a2 + (uint32_t)(8 * j), wt_lo32 + (uint32_t)(j * (C::WT_TAP >> 4)), wt_hi32, idesc_t1,
+                                    j == 0 ? 0u : 1u);
+#pragma unroll
+                for (int j = 0; j < C::K2 / 16; j++)
+                  umma_issue_ts<CG>(d2, a2 + (uint32_t)(C::K2 / 2 + 8 * j), wt_lo32 + (uint32_t)(j * (C::WT_TAP >> 4)) + (uint32_t)TN,
+                                    wt_hi32, idesc_t2, 1u);
+              }
             }
-            __syncwarp();
-            pend_mask &= ~(1u << sb);
+            umma_done<CG>(&t2_full[pend_acc]);
           }
-          if (pend_mask == 0) { pend_acc = -1; a2phase ^= 1; }
+          __syncwarp();
+          pend_acc = -1;
+          a2phase ^= 1;
         }
       };
       if constexpr (TN > 0) {  // the tail weights of both CTAs are in place
@@ -748,7 +779,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
           const int blk = NBLK > 1 ? c / C::CPB : 0;
           const uint32_t d_base = d_tile + (uint32_t)(blk * C::BLK_COLS);
           for (int tg = 0; tg < C::NSTAGE_PER_CHUNK; tg++) {
-            tail_step(c == C::NCHUNK - 1 && tg == C::NSTAGE_PER_CHUNK - 1);
+            tail_step(c * C::NSTAGE_PER_CHUNK + tg == kTailForceAt);
             if (!b_ready) mbar_wait(&b_full[bstage], bphase);
             if constexpr (CG == 2) mbar_wait(&b_full_peer[bstage], bphase);
             tc_fence_after();
@@ -800,7 +831,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
           }
           if (++astage == C::NA) { astage = 0; aphase ^= 1; }
         }
-        if constexpr (TN > 0) { pend_acc = acc; pend_mask = (1u << S) - 1; }
+        if constexpr (TN > 0) pend_acc = acc;
         if (++acc == AS) { acc = 0; tphase ^= 1; }
       }
       tail_step(true);  // the last tile's tail GEMM
@@ -833,7 +864,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
         // pass 1: this layer's activations (bias, ReLU, bf16 hi/lo) -> tensor memory as packed bf16 pairs
         //         (K2/2 columns of hi parts, K2/2 of lo parts); then "sub-tile ready" to the issuer
         constexpr int GC = 32, NG = NBLK * NPAD / GC, STEP = S == 1 ? 2 : 1;
-        static_assert(S <= 2 && NBLK == 1 && (NBLK * NPAD) % GC == 0 && NG % STEP == 0, "tail layer: tile shape");
+        static_assert(S <= 2 && !DUAL && (NBLK * NPAD) % GC == 0, "tail layer: tile shape (one accumulator per channel)");
 #pragma unroll 1
         for (int s = (S == 1 ? 0 : egroup); s < S; s += 2) {
           const uint32_t t_addr = tmem_base + lane_base + (uint32_t)((acc * S + s) * C::SUB_COLS);
@@ -848,12 +879,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
             }
           };
           const int first = S == 1 ? egroup : 0;
-          issue1(first * GC, vb[0], wb[0]);
+          const int cnt = (NG - first + STEP - 1) / STEP;   // S == 1: the two epilogue groups take alternate channel groups
+          if (cnt > 0) issue1(first * GC, vb[0], wb[0]);
 #pragma unroll
-          for (int k = 0; k < NG / STEP; k++) {
+          for (int k = 0; k < (NG + STEP - 1) / STEP; k++) {
+            if (k >= cnt) break;
             const int c0 = (first + k * STEP) * GC;
             tmem_ld_wait();
-            if (k + 1 < NG / STEP) issue1(c0 + STEP * GC, vb[(k + 1) & 1], wb[(k + 1) & 1]);
+            if (k + 1 < cnt) issue1(c0 + STEP * GC, vb[(k + 1) & 1], wb[(k + 1) & 1]);
             uint32_t hi[GC / 2], lo[GC / 2];   // bf16 pairs (channel c in the low half, c + 1 in the high half)
 #pragma unroll
             for (int j = 0; j < GC; j += 2) {
@@ -871,7 +904,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
           tc_fence_before();
           __syncwarp();
           if (lane == 0) {
-            if constexpr (CG == 2) mbar_arrive_remote_release(&a2_full[s], 0);
+            // plain arrival: what is handed over lives in tensor memory (tcgen05.st + wait::st + fence above), not in
+            // generic memory -- a cluster-scope release here compiles to MEMBAR.ALL.GPU and waits ~1 us for the previous
+            // tile's global stores, on the path every tail GEMM waits for (ncu source page: ERRBAR / MEMBAR stalls)
+            if constexpr (CG == 2) mbar_arrive_remote(&a2_full[s], 0);
             else mbar_arrive(&a2_full[s]);
           }
         }
@@ -879,7 +915,6 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
         mbar_wait(&t2_full[acc], tphase);
         tc_fence_after();
         constexpr int NG2 = TN / GC;
-        static_assert(S == 2 || NG2 % 2 == 0, "S == 1 splits the tail's channel groups over the two epilogue groups");
         static_assert(TEPI == kTailAct || !OUT8, "the tap-stacked tail stores raw sums");
 #pragma unroll 1
         for (int s = (S == 1 ? 0 : egroup); s < S; s += 2) {
@@ -889,20 +924,29 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
           const size_t pix = (size_t)gy * g.W + gx;
           const size_t hw = (size_t)g.H * g.W;
 #pragma unroll
-          for (int k = (S == 1 ? egroup : 0); k < NG2; k += STEP) {
+          for (int k = 0; k < NG2; k++) {
+            if (S == 1 && (k & 1) != egroup) continue;   // S == 1: alternate channel groups per epilogue group
             const int c0 = k * GC;
-            uint32_t v[GC], w[GC];
+            uint32_t v[GC], w[C::TAIL_BLK ? 1 : GC];
 #pragma unroll
             for (int q = 0; q < GC; q += 16) tmem_ld16(t_addr + (uint32_t)(c0 + q), v + q);
+            if constexpr (!C::TAIL_BLK) {   // CONCAT form: the a_hi x w_lo products sit TN columns further
 #pragma unroll
-            for (int q = 0; q < GC; q += 16) tmem_ld16(t_addr + (uint32_t)(TN + c0 + q), w + q);
+              for (int q = 0; q < GC; q += 16) tmem_ld16(t_addr + (uint32_t)(TN + c0 + q), w + q);
+            }
             tmem_ld_wait();
-            if (!inside || c0 >= g.cout) continue;
-            if constexpr (TEPI == kTailTaps) {
-              float* o = g.out_f32 + ((size_t)n * g.cout + c0) * hw + pix;
+            if constexpr (!C::TAIL_BLK) {
 #pragma unroll
-              for (int j = 0; j < GC; j++)
-                if (c0 + j < g.cout) o[(size_t)j * hw] = __uint_as_float(v[j]) + __uint_as_float(w[j]);
+              for (int j = 0; j < GC; j++) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
+            }
+            if (!inside) continue;
+            if constexpr (TEPI == kTailTaps) {
+              // group k = one 3x3 layer with 3 output channels, tap-stacked: 27 of its 32 columns are in use
+              float* o = g.out_f32 + ((size_t)n * (NG2 * 27) + k * 27) * hw + pix;
+#pragma unroll
+              for (int j = 0; j < 27; j++) o[(size_t)j * hw] = __uint_as_float(v[j]);
+            } else if (c0 >= g.cout) {
+              continue;
             } else if constexpr (OUT8) {
 #pragma unroll
               for (int q = 0; q < GC; q += 16) {
@@ -914,7 +958,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
                   float x[4], r[4];
 #pragma unroll
                   for (int t = 0; t < 4; t++) {
-                    x[t] = fmaxf(__uint_as_float(v[q + j + t]) + __uint_as_float(w[q + j + t]) + s_bias2[ch + j + t], 0.f);
+                    x[t] = fmaxf(__uint_as_float(v[q + j + t]) + s_bias2[ch + j + t], 0.f);
                     vmax = fmaxf(vmax, x[t]);
                   }
 #pragma unroll
@@ -944,9 +988,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
                 uint32_t hi[4], lo[4];
 #pragma unroll
                 for (int j = 0; j < 8; j += 2)
-                  split_bf16x2(fmaxf(__uint_as_float(v[q + j]) + __uint_as_float(w[q + j]) + s_bias2[ch + j], 0.f),
-                               fmaxf(__uint_as_float(v[q + j + 1]) + __uint_as_float(w[q + j + 1]) + s_bias2[ch + j + 1], 0.f),
-                               hi[j >> 1], lo[j >> 1]);
+                  split_bf16x2(fmaxf(__uint_as_float(v[q + j]) + s_bias2[ch + j], 0.f),
+                               fmaxf(__uint_as_float(v[q + j + 1]) + s_bias2[ch + j + 1], 0.f), hi[j >> 1], lo[j >> 1]);
                 const ActDst& d = g.dst0;
                 uint4* p_hi = d.base + ((size_t)n * 2 * d.planes_half + (ch >> 3)) * hw + pix;
                 p_hi[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);

@@ -39,9 +39,13 @@ def _run(im, device=None):
 
 
 def white_balance_transform(im_rgb, device=None) -> np.ndarray:
-    """Simplest colour balance (reference ``data.py:6-58``, RGB branch)."""
-    if np.asarray(im_rgb).ndim == 2:
-        raise NotImplementedError("the grayscale branch (data.py:30-36) is unused by the hot path and not provided")
+    """Simplest colour balance (reference ``data.py:6-58``): HWC RGB, or a 2-D grayscale image (``data.py:30-36``)."""
+    arr = np.asarray(im_rgb)
+    if arr.ndim == 2:
+        if arr.dtype != np.uint8:
+            raise TypeError(f"expected a uint8 image, got {arr.dtype}")
+        eng = get_engine(device)
+        return eng.white_balance_gray(torch.from_numpy(np.ascontiguousarray(arr[None])).to(eng.device))[0].cpu().numpy()
     return _run(im_rgb, device)["wb_u8"]
 
 

@@ -64,7 +64,7 @@ class Engine:
         handle = ctypes.c_void_p()
         _lib.check(self.lib.wn_create(device.index, ctypes.byref(handle)), "wn_create")
         self.handle = handle
-        # bring-up / A-B switches of the conv pipeline (wn_debug_set_flags); bit 8 (256) = conv3 and conv4 as two launches
+        # bring-up / A-B switches of the conv pipeline (wn_debug_set_flags): 256 / 512 = conv3+conv4 / conv7+conv8 unfused
         flags = int(os.environ.get("WATERNET_B200_DEBUG_FLAGS", "0"), 0)
         if flags:
             _lib.check(self.lib.wn_debug_set_flags(handle, flags), "wn_debug_set_flags")
@@ -294,6 +294,22 @@ class Engine:
                                            ws.data_ptr(), ws.numel(), _stream_ptr(self.device))
         _lib.check(rc, "wn_preprocess_u8")
         return res
+
+    def white_balance_gray(self, gray_u8: torch.Tensor) -> torch.Tensor:
+        """Grayscale branch of ``white_balance_transform`` (data.py:30-36) on uint8 (N,H,W) CUDA tensors."""
+        if gray_u8.dtype != torch.uint8 or gray_u8.dim() != 3:
+            raise ValueError(f"expected uint8 (N,H,W), got {gray_u8.dtype} {tuple(gray_u8.shape)}")
+        g = gray_u8.to(self.device).contiguous()
+        out = torch.empty_like(g)
+        if g.numel() == 0:
+            return out
+        n, h, w = g.shape
+        ws = self._workspace("preprocess", self.lib.wn_white_balance_gray_workspace_bytes(n, h, w))
+        with torch.cuda.device(self.device):
+            rc = self.lib.wn_white_balance_gray_u8(self.handle, g.data_ptr(), out.data_ptr(), n, h, w, ws.data_ptr(),
+                                                   ws.numel(), _stream_ptr(self.device))
+        _lib.check(rc, "wn_white_balance_gray_u8")
+        return out
 
     def resize_batch(self, images, dst_h: int, dst_w: int, swap_rb: bool = False) -> torch.Tensor:
         """Batched ``cv2.resize(img, (dst_w, dst_h))`` (+ optional BGR<->RGB swap) of differently sized uint8 HWC

@@ -297,8 +297,14 @@ luts_kernel(const uint32_t* __restrict__ tile_hist, const uint32_t* __restrict__
 // ---------------------------------------------------------------------------
 // Pass 3: per-pixel apply.  grid = (ceil(H*W/256), N), 256 threads.
 // ---------------------------------------------------------------------------
-// pixels per CTA = 256 * kApplyIters: amortises the ~30 KB of LUT/table staging per CTA
-constexpr int kApplyIters = 16;
+// pixels per CTA = 256 * iters (x 4 in the vector path): amortises the ~30 KB of LUT/table staging per CTA.  16 for big
+// launches; fewer when the launch is small (one pass of 4 images), so that the grid still has ~8 CTAs per SM and the
+// single wave is balanced
+constexpr int kApplyItersMax = 16;
+static int apply_iters(long long pixels_per_thread_slot, int sm_count) {
+  long long it = pixels_per_thread_slot / (256ll * 8 * sm_count);
+  return it < 4 ? 4 : it > kApplyItersMax ? kApplyItersMax : (int)it;
+}
 
 struct ApplyOut {
   float* f32[4];    // x, wb, he, gc  -- NCHW planes, may be null
@@ -321,7 +327,7 @@ template <bool VEC4>
 __global__ void __launch_bounds__(256)
 apply_kernel(const uint8_t* __restrict__ rgb, int H, int W, int th, int tw,
              const Tables* __restrict__ tables, const uint8_t* __restrict__ clahe_lut,
-             const uint8_t* __restrict__ wb_lut, ApplyOut out) {
+             const uint8_t* __restrict__ wb_lut, ApplyOut out, int iters) {
   __shared__ __align__(16) uint8_t s_clahe[64 * 256];
   __shared__ __align__(16) uint8_t s_wb[768];
   __shared__ __align__(16) uint8_t s_gamma[256];
@@ -381,8 +387,8 @@ apply_kernel(const uint8_t* __restrict__ rgb, int H, int W, int th, int tw,
 
   if constexpr (VEC4) {
     // four consecutive pixels per thread: 12 input bytes as three 32-bit loads, one float4 store per plane
-    for (int it = 0; it < kApplyIters; it++) {
-      const int pix = ((blockIdx.x * kApplyIters + it) * 256 + tid) * 4;
+    for (int it = 0; it < iters; it++) {
+      const int pix = ((blockIdx.x * iters + it) * 256 + tid) * 4;
       if (pix >= plane) break;
       const uint32_t* p32 = reinterpret_cast<const uint32_t*>(rgb + ((size_t)n * plane + pix) * 3);
       const uint32_t w0 = p32[0], w1 = p32[1], w2 = p32[2];
@@ -419,8 +425,8 @@ apply_kernel(const uint8_t* __restrict__ rgb, int H, int W, int th, int tw,
       }
     }
   } else {
-    for (int it = 0; it < kApplyIters; it++) {
-      const int pix = (blockIdx.x * kApplyIters + it) * 256 + tid;
+    for (int it = 0; it < iters; it++) {
+      const int pix = (blockIdx.x * iters + it) * 256 + tid;
       if (pix >= plane) break;
       const uint8_t* p = rgb + ((size_t)n * plane + pix) * 3;
       int lv[12];
@@ -603,13 +609,15 @@ static int preprocess_run(wn_handle* h, const uint8_t* rgb, int n, int H, int W,
                     ((uintptr_t)wb % 16) == 0 && ((uintptr_t)he % 16) == 0 && ((uintptr_t)gc % 16) == 0 &&
                     ((uintptr_t)wb_u8 % 4) == 0 && ((uintptr_t)he_u8 % 4) == 0 && ((uintptr_t)gc_u8 % 4) == 0;
   if (vec4) {
-    const int per_cta = 256 * kApplyIters * 4;
+    const int iters = apply_iters((long long)n * H * W / 4, h->sm_count);
+    const int per_cta = 256 * iters * 4;
     apply_kernel<true><<<dim3((H * W + per_cta - 1) / per_cta, n), 256, 0, stream>>>(rgb, H, W, g.th, g.tw, h->d_tables,
-                                                                                   clahe_lut, wb_lut, ao);
+                                                                                   clahe_lut, wb_lut, ao, iters);
   } else {
-    const int per_cta = 256 * kApplyIters;
+    const int iters = apply_iters((long long)n * H * W, h->sm_count);
+    const int per_cta = 256 * iters;
     apply_kernel<false><<<dim3((H * W + per_cta - 1) / per_cta, n), 256, 0, stream>>>(rgb, H, W, g.th, g.tw, h->d_tables,
-                                                                                    clahe_lut, wb_lut, ao);
+                                                                                    clahe_lut, wb_lut, ao, iters);
   }
   WN_LAUNCH_CHECK(h);
   return WN_OK;

@@ -62,6 +62,8 @@ def parse_args():
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather", choices=["peer", "nccl"], default="peer",
+                    help="N > 1: how the uint8 output is all-gathered (peer = copy-engine pushes over NVLink)")
     return ap.parse_args()
 
 
@@ -263,7 +265,7 @@ def main():
 
     from waternet_b200 import _lib
     from waternet_b200.api import Enhancer
-    from waternet_b200.dist import PassGather
+    from waternet_b200.dist import PassGather, PeerGather
     from waternet_b200.net import WaterNet
 
     sd = bench_state_dict()  # random init of the reference architecture, the same tensors the reference arm loads
@@ -279,15 +281,24 @@ def main():
     dev_in = torch.from_numpy(host).to(device)
     dev_out = torch.empty_like(dev_in)
     nb = eng.chunk_images(B, H, W)
-    gather = PassGather((B, H, W, 3), torch.uint8, device) if world > 1 else None
+    gather = None
+    if world > 1:  # copy-engine pushes into peer memory (CUDA IPC); --gather nccl = all_gather per pass
+        gather = (PassGather((B, H, W, 3), torch.uint8, device) if args.gather == "nccl"
+                  else PeerGather.create((B, H, W, 3), torch.uint8, device))
     side = torch.cuda.Stream(device)
+
+    push_done = {}
 
     def step_resident():
         """One step with the batch resident in HBM: per pass, kernels on the compute stream and (N > 1) the
-        all-gather of that pass's output on a side stream, under the next pass's kernels."""
+        exchange of that pass's output on a side stream, under the next pass's kernels.  The compute stream never
+        waits for the exchange as such -- only, one step later, for the push that still reads the slice of `dev_out`
+        a pass is about to overwrite -- so the ranks are not lock-stepped by the per-step completion all-reduce."""
         cur = torch.cuda.current_stream(device)
         for a in range(0, B, nb):
             b = min(B, a + nb)
+            if gather is not None and a in push_done:
+                cur.wait_event(push_done[a])
             eng.enhance(dev_in[a:b], mode=mode, out_u8=dev_out[a:b])
             if gather is not None:
                 ev = torch.cuda.Event()
@@ -295,8 +306,12 @@ def main():
                 with torch.cuda.stream(side):
                     side.wait_event(ev)
                     gather.on_pass(dev_out[a:b], a, b)
+                    done = torch.cuda.Event()
+                    done.record(side)
+                    push_done[a] = done
         if gather is not None:
-            cur.wait_stream(side)
+            with torch.cuda.stream(side):
+                gather.finish()
 
     pins = [(torch.from_numpy(host).pin_memory(), torch.empty(host.shape, dtype=torch.uint8).pin_memory())
             for _ in range(2)]
@@ -335,6 +350,9 @@ def main():
         prev = None
         for i in range(steps):
             ticket = enh.submit(*pins[i % 2], on_pass=on_pass)
+            if gather is not None:
+                with torch.cuda.stream(enh._s_out):
+                    gather.finish()
             if prev is not None:
                 enh.wait(prev)
             prev = ticket
@@ -486,7 +504,10 @@ def main():
                                                 "frac": gbs / peaks["hbm_gbs"], "bytes_per_px": bpp}
         config = workload_config(args, world)  # identical in both arms
         detail = {"mode": args.mode, "images_per_pass": nb,
-                  "collective": "all_gather(uint8 output) per pass on a side stream (NCCL)" if world > 1 else "none"}
+                  "collective": ("none" if world == 1 else
+                                 "all-gather of the uint8 output per pass on a side stream: " +
+                                 ("copy-engine pushes into peer memory over NVLink (CUDA IPC) + one 1-element NCCL "
+                                  "all-reduce per step" if isinstance(gather, PeerGather) else "NCCL all_gather"))}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",

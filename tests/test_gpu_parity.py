@@ -710,21 +710,33 @@ def _nccl_worker(rank, world, port, ret):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
         from waternet_b200.api import Enhancer
-        from waternet_b200.dist import PassGather
+        from waternet_b200.dist import PassGather, PeerGather
         h, w, per = 64, 96, 3
         frames = np.stack([ofw.synthetic_image(500 + i, h, w, "smooth") for i in range(world * per)])
         m = _model(0, 3.0, "default")
         enh = Enhancer(m, cuda_graph=False)
-        m.engine().set_chunk_pixels(2 * h * w)  # 3 local images -> two passes, two collectives
-        local = torch.from_numpy(frames[rank * per:(rank + 1) * per].copy()).pin_memory()
-        out = torch.empty_like(local).pin_memory()
-        gather = PassGather(tuple(local.shape), torch.uint8, torch.device("cuda", rank))
-        enh.enhance_pinned(local, out, on_pass=gather.on_pass)
-        torch.cuda.synchronize()
-        m.engine().set_chunk_pixels(0)
         full = Enhancer(m, cuda_graph=False)(frames)            # every rank: all images on its own GPU
-        ok = gather.calls == 2 and np.array_equal(gather.result().cpu().numpy(), full)
-        ok = ok and np.array_equal(out.numpy(), full[rank * per:(rank + 1) * per])
+        m.engine().set_chunk_pixels(2 * h * w)  # 3 local images -> two passes, two exchanges
+        local = torch.from_numpy(frames[rank * per:(rank + 1) * per].copy()).pin_memory()
+        ok = True
+        dev = torch.device("cuda", rank)
+        # both exchange forms: NCCL all_gather per pass, and copy-engine pushes into peer memory over CUDA IPC
+        for make in (lambda: PassGather(tuple(local.shape), torch.uint8, dev),
+                     lambda: PeerGather.create(tuple(local.shape), torch.uint8, dev)):
+            gather = make()
+            gather.result().zero_()
+            torch.cuda.synchronize()
+            dist.barrier()                      # nobody pushes into a buffer that is still being cleared
+            out = torch.empty_like(local).pin_memory()
+            enh.enhance_pinned(local, out, on_pass=gather.on_pass)
+            gather.finish()
+            torch.cuda.synchronize()
+            dist.barrier()
+            ok = ok and gather.calls == 2 and np.array_equal(gather.result().cpu().numpy(), full)
+            ok = ok and np.array_equal(out.numpy(), full[rank * per:(rank + 1) * per])
+            dist.barrier()
+        ok = ok and isinstance(gather, PeerGather)   # on one NVSwitch node the IPC path must be available
+        m.engine().set_chunk_pixels(0)
         ret[rank] = bool(ok)
     finally:
         dist.destroy_process_group()

@@ -120,6 +120,24 @@ struct TimedScope {
   }
 };
 
+// K-packed first-layer planes (umma_conv.cuh, UmmaCfg KP): rows of W + 1 columns, column x + 1 = pixel x.  `o` points at
+// the pixel's own column in plane 0; plane 1 (one `plane` further) holds per column [c8..11 @ x | c8..11 @ x + 1]: the
+// pixel writes its c8..11 into the first half of its own column and the second half of the column to its left; the
+// image's first / last pixel also write the zero halves and the zero column that padding needs.
+#ifdef __CUDACC__
+__device__ __forceinline__ void store_kp_pixel(uint4* o, size_t plane, int x, int W, uint4 c0_7, uint2 c8_11) {
+  o[0] = c0_7;
+  uint2* p1 = reinterpret_cast<uint2*>(o + plane);
+  p1[0] = c8_11;        // first half of column x + 1
+  p1[-1] = c8_11;       // second half of column x
+  if (x == 0) {
+    o[-1] = make_uint4(0u, 0u, 0u, 0u);   // plane 0, column 0 = the pixel left of the image
+    p1[-2] = make_uint2(0u, 0u);          // plane 1, column 0, first half = c8..11 of that pixel
+  }
+  if (x == W - 1) p1[1] = make_uint2(0u, 0u);   // second half of the last column = c8..11 of the pixel right of the image
+}
+#endif
+
 // preprocess.cu
 size_t preprocess_workspace_bytes(int n, int h, int w);
 int preprocess_u8(wn_handle* h, const uint8_t* rgb, int n, int height, int width, float* x,
@@ -134,8 +152,9 @@ int resize_u8(wn_handle* h, const uint8_t* const* src, const int* src_h, const i
               int dst_h, int dst_w, int swap_rb, cudaStream_t stream);
 // transform + cat[x, wb, he, gc] straight into the first layer's operand planes: planes[n][2][H*W] of 16 B
 // (8 bf16 levels 0..255: plane 0 = x.rgb wb.rgb he.rg, plane 1 = he.b gc.rgb 0 0 0 0)
+// kp != 0: the K-packed layout (planes[n][2][H][W + 1], see store_kp_pixel)
 int preprocess_u8_planes(wn_handle* h, const uint8_t* rgb, int n, int height, int width, uint4* planes,
-                         void* workspace, size_t workspace_bytes, cudaStream_t stream);
+                         void* workspace, size_t workspace_bytes, cudaStream_t stream, int kp = 0);
 
 // conv_simt.cu
 int simt_pack_weights(wn_handle* h, const float* const* params, cudaStream_t stream);
@@ -165,6 +184,7 @@ struct FwdOpts {
   float* dbg_dst = nullptr;
   bool packed = false;         // act0 already holds the 16-channel operand planes of this batch
   bool hi_only = false;        // ... as exact 8-bit levels, hi planes only (written by the preprocess kernel)
+  bool kpack = false;          // act0 is in the K-packed first-layer layout (inference; UmmaCfg KP)
   const int* run_if = nullptr; // every launch is conditional on *run_if != 0 (ConvArgs::run_if)
   uint8_t* out_u8 = nullptr;   // the last launch also writes ten2arr(out) as uint8 NHWC
   int stack = kStackAll;       // kStackCmg: stop after the confidence maps; kStackRefiners: refiners only

@@ -39,8 +39,10 @@ struct PackInArgs {
   const float* p[4];
   long long s[4][4];
 };
+// kp != 0: the K-packed first layer's layout (UmmaCfg KP): planes are W + 1 columns wide, column x + 1 = pixel x, and
+// plane 1 holds [c8..11 @ x | c8..11 @ x + 1] (each pixel writes its four channels into two half rows).
 __global__ void __launch_bounds__(256) pack_inputs_kernel(PackInArgs a, uint4* __restrict__ out, int H, int W,
-                                                          int* __restrict__ exact_flag) {
+                                                          int* __restrict__ exact_flag, int kp) {
   const int n = blockIdx.y;
   const int pix = blockIdx.x * 256 + threadIdx.x;
   const int hw = H * W;
@@ -64,11 +66,18 @@ __global__ void __launch_bounds__(256) pack_inputs_kernel(PackInArgs a, uint4* _
     for (int j = 0; j < 16; j += 2) {
       split_bf16x2(v[j], v[j + 1], hi[j >> 1], lo[j >> 1]);
     }
+    if (kp) {
+      const size_t plane = (size_t)H * (W + 1);
+      uint4* o = out + (size_t)n * 4 * plane + (size_t)y * (W + 1) + x + 1;   // planes: hi0, hi1, lo0, lo1
+      store_kp_pixel(o, plane, x, W, make_uint4(hi[0], hi[1], hi[2], hi[3]), make_uint2(hi[4], hi[5]));
+      store_kp_pixel(o + 2 * plane, plane, x, W, make_uint4(lo[0], lo[1], lo[2], lo[3]), make_uint2(lo[4], lo[5]));
+    } else {
     uint4* o = out + (size_t)n * 4 * hw + pix;  // planes: hi0, hi1, lo0, lo1
     o[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
     o[hw] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
     o[2 * (size_t)hw] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
     o[3 * (size_t)hw] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+    }
   }
   if (!__syncthreads_and(exact) && threadIdx.x == 0) atomicExch(exact_flag, 0);
 }
@@ -223,6 +232,8 @@ gather_sigmoid_kernel(const float* __restrict__ taps, const float* __restrict__ 
 }
 
 // layers that have an fp8-correction form (UmmaCfg FMT bit 0): the tensor-bound CTA-pair layers
+// halo-stage geometry of the first layer's kernel (S = 1: 8 + 6 columns, 16 + 6 rows), in 16-byte units
+static constexpr int kL1HaloW = 14, kL1PlaneUnits = 14 * 22;
 static bool has_f8_form(int li) { return li == kC2 || li == kC3 || li == kC5 || li == kC6 || li == kC7 || li == kR2; }
 static size_t stage8_bytes_total(const UmmaLayerSpec& s) {
   return (size_t)2 * (s.cinpad / 16) * s.ks * s.ks * (s.npad / 2) * 64;  // two per-rank images
@@ -230,6 +241,7 @@ static size_t stage8_bytes_total(const UmmaLayerSpec& s) {
 struct UmmaWeights {
   uint8_t* stages8[kNumUmmaLayers];  // fp8-correction weight images (has_f8_form layers)
   float* scale8[kNumUmmaLayers];     // {ws, 2^-9 / ws, max|w|, -}
+  uint8_t* stages_l1k;               // the first layer K-packed (UmmaCfg KP): two per-rank images of kKpSteps stages of 224 x 32 B
   uint8_t* tailr3;                   // the three refiners' conv3 tap-stacked (block-diagonal, 3 x 27 columns) as the tail of their conv2
   uint8_t* tail8;                    // cmg.conv8 tap-stacked (27 = 9 taps x 3 channels columns) as the tail layer of conv7
   uint8_t* tail4;                    // cmg.conv4 as the tail layer of conv3: two per-rank images, CG=2 CONCAT layout
@@ -258,6 +270,7 @@ int umma_pack_weights(wn_handle* h, const float* const* params, cudaStream_t str
   }
   if (!h->umma->dense) WN_CUDA(cudaMalloc(&h->umma->dense, (size_t)224 * 128 * 49 * sizeof(float)));
   if (!h->umma->tail4) WN_CUDA(cudaMalloc(&h->umma->tail4, (size_t)2 * 8 * 64 * 48));
+  if (!h->umma->stages_l1k) WN_CUDA(cudaMalloc(&h->umma->stages_l1k, (size_t)kKpSteps * 224 * 32 * 2));
   if (!h->umma->tail8) WN_CUDA(cudaMalloc(&h->umma->tail8, (size_t)2 * 4 * 32 * 48));
   if (!h->umma->tailr3) WN_CUDA(cudaMalloc(&h->umma->tailr3, (size_t)2 * 6 * 32 * 32));
   if (!h->umma->overflow_dev) WN_CUDA(cudaMalloc(&h->umma->overflow_dev, sizeof(int)));
@@ -304,6 +317,10 @@ int umma_pack_weights(wn_handle* h, const float* const* params, cudaStream_t str
       pack_stages_kernel<<<256, 256, 0, stream>>>(u->dense, (__nv_bfloat16*)u->stages[li], s.npad, s.cinpad, kk,
                                                   s.concat, s.nblk);
     WN_LAUNCH_CHECK(h);
+    if (li == kL1) {  // the K-packed form of the first layer (inference): K steps pair arbitrary halo rows (l1k_table)
+      pack_l1k_kernel<<<256, 256, 0, stream>>>(u->dense, (__nv_bfloat16*)u->stages_l1k, s.npad, l1k_table(kL1HaloW, kL1PlaneUnits));
+      WN_LAUNCH_CHECK(h);
+    }
     if (li == kC4) {  // the same weights as conv3's fused tail layer (UmmaCfg TN): per rank [chunk][k8][64 | 32 rows][8]
       pack_stages_cg2_kernel<<<256, 256, 0, stream>>>(u->dense, (__nv_bfloat16*)u->tail4, s.npad, s.cinpad, kk, 1, 1);
       WN_LAUNCH_CHECK(h);
@@ -350,6 +367,7 @@ void umma_free(wn_handle* h) {
   }
   if (h->umma->dense) cudaFree(h->umma->dense);
   if (h->umma->tail4) cudaFree(h->umma->tail4);
+  if (h->umma->stages_l1k) cudaFree(h->umma->stages_l1k);
   if (h->umma->tail8) cudaFree(h->umma->tail8);
   if (h->umma->tailr3) cudaFree(h->umma->tailr3);
   if (h->umma->overflow_dev) cudaFree(h->umma->overflow_dev);
@@ -376,7 +394,8 @@ int umma_chunk_images(const wn_handle* h, int n, int height, int width) {
 }
 
 size_t umma_forward_workspace_bytes(int n, int h, int w) {
-  return (size_t)umma_chunk(0, n, h, w) * h * w * kUmmaBytesPerPixel + 4096;
+  const size_t nb = (size_t)umma_chunk(0, n, h, w);
+  return nb * h * w * kUmmaBytesPerPixel + nb * h * 64 + 4096;
 }
 
 // taps per weight stage of the layers where it is a tuning knob (A/B builds override with -D)
@@ -420,9 +439,22 @@ size_t umma_forward_workspace_bytes(int n, int h, int w) {
 #endif
 
 template <int KS, int CIN_PAD, int NPAD, int S, int AS, int EPI, int CONCAT = 0, int NBLK = 1, int TPS = 1, int CG = 1,
-          int FMT = 0, int TN = 0, int TEPI = 0>
+          int FMT = 0, int TN = 0, int TEPI = 0, int KP = 0>
 static int launch_umma(wn_handle* h, int li, void* in_base, ConvArgs a, cudaStream_t stream) {
   const UmmaLayerSpec& spec = kSpecs[li];
+  if constexpr (KP != 0) {  // K-packed first layer: its own weight images and the table of K steps
+    using C = UmmaCfg<KS, CIN_PAD, NPAD, S, AS, CONCAT, NBLK, TPS, CG, FMT, TN, KP>;
+    static_assert(C::HALO_W == kL1HaloW && C::PLANE_BYTES / 16 == kL1PlaneUnits, "l1k_table geometry");
+    if (li != kL1 || spec.npad != NPAD || spec.cg != CG) {
+      set_error("internal: K-packed launch configuration does not match the first layer");
+      return WN_E_STATE;
+    }
+    if constexpr ((FMT & kFmtOut8) != 0) a.f8_overflow = h->umma->overflow_dev;
+    const KpTable t = l1k_table(kL1HaloW, kL1PlaneUnits);
+    for (int i = 0; i < kKpSteps; i++) { a.kp_off[i] = t.off[i]; a.kp_lbo[i] = t.lbo[i]; }
+    return launch_conv<KS, CIN_PAD, NPAD, S, AS, EPI, CONCAT, NBLK, TPS, CG, FMT, TN, TEPI, KP>(
+        h, spec.slot, h->umma->stages_l1k, h->umma->bias[li], in_base, a, stream);
+  } else {
   if constexpr ((FMT & kFmtOut8) != 0) a.f8_overflow = h->umma->overflow_dev;
   if constexpr ((FMT & kFmtIn8) != 0) {  // fp8-correction form: its own weight images, [hi | fp8] layout, CTA pairs
     if (spec.ks != KS || spec.cinpad != CIN_PAD || spec.npad != NPAD || spec.nblk != NBLK || !has_f8_form(li)) {
@@ -441,6 +473,7 @@ static int launch_umma(wn_handle* h, int li, void* in_base, ConvArgs a, cudaStre
   static_assert(TN == 0 || (FMT & kFmtIn8) != 0, "the fused tail layer exists for the fp8-correction form only");
   return launch_conv<KS, CIN_PAD, NPAD, S, AS, EPI, CONCAT, NBLK, TPS, CG, FMT>(h, spec.slot, h->umma->stages[li],
                                                                        h->umma->bias[li], in_base, a, stream);
+  }
 }
 
 // bf16 hi/lo planes -> fp32 NCHW (test aid)
@@ -489,7 +522,7 @@ int umma_forward_layers(wn_handle* h, const float* const in[4], const int64_t st
     }
     TimedScope ts(h, kSlotPack, stream);
     WN_CUDA(cudaMemsetAsync(b.exact_flag, 1, sizeof(int), stream));  // nonzero = "all inputs are 8-bit levels"
-    pack_inputs_kernel<<<dim3((H * W + 255) / 256, n), 256, 0, stream>>>(pa, b.act0, H, W, b.exact_flag);
+    pack_inputs_kernel<<<dim3((H * W + 255) / 256, n), 256, 0, stream>>>(pa, b.act0, H, W, b.exact_flag, o.kpack ? 1 : 0);
     WN_LAUNCH_CHECK(h);
   }
   ConvArgs a;
@@ -525,7 +558,9 @@ int umma_forward_layers(wn_handle* h, const float* const in[4], const int64_t st
     act(b.a[1], 128, b.r[1], 96);
     a.skip_lo = b.exact_flag;
     a.a_hi_only = o.hi_only ? 1 : 0;
-    if ((rc = launch_umma<7, 16, 224, 1, 2, kEpiAct, 0, 1, 7, 2, OUT8>(h, kL1, b.act0, a, stream))) return rc;
+    if (o.kpack) {
+      if ((rc = launch_umma<7, 16, 224, 1, 2, kEpiAct, 0, 1, 5, 2, OUT8, 0, 0, 1>(h, kL1, b.act0, a, stream))) return rc;
+    } else if ((rc = launch_umma<7, 16, 224, 1, 2, kEpiAct, 0, 1, 7, 2, OUT8>(h, kL1, b.act0, a, stream))) return rc;
     a.skip_lo = nullptr;
     a.a_hi_only = 0;
     if (dump(0, b.a[1], 128, 1) || dump(8, b.r[1], 96, 1)) return WN_OK;
@@ -624,7 +659,9 @@ int umma_forward_layers(wn_handle* h, const float* const in[4], const int64_t st
   act(b.a[1], 128, b.r[1], 96);
   a.skip_lo = b.exact_flag;
   a.a_hi_only = o.hi_only ? 1 : 0;
-  if ((rc = launch_umma<7, 16, 224, WN_L1_S, WN_L1_S == 1 ? 2 : 1, kEpiAct, 0, 1, WN_CG_L1R2 == 2 ? 7 : WN_L1_TPS, WN_CG_L1R2>(h, kL1, b.act0, a, stream))) return rc;
+  if (o.kpack) {
+    if ((rc = launch_umma<7, 16, 224, 1, 2, kEpiAct, 0, 1, 5, 2, 0, 0, 0, 1>(h, kL1, b.act0, a, stream))) return rc;
+  } else if ((rc = launch_umma<7, 16, 224, WN_L1_S, WN_L1_S == 1 ? 2 : 1, kEpiAct, 0, 1, WN_CG_L1R2 == 2 ? 7 : WN_L1_TPS, WN_CG_L1R2>(h, kL1, b.act0, a, stream))) return rc;
   a.skip_lo = nullptr;
   a.a_hi_only = 0;
   if (dump(0, b.a[1], 128) || dump(8, b.r[1], 96)) return WN_OK;
@@ -668,7 +705,7 @@ static FwdBuffers carve(void* workspace, int n, int H, int W) {
   uint4* refAB[2];
   FwdBuffers b;
   memset(&b, 0, sizeof(b));
-  b.act0 = (uint4*)ws;     ws += px * 64;
+  b.act0 = (uint4*)ws;     ws += (px + (size_t)n * H) * 64;   // + one column per row: the K-packed layout is W + 1 wide
   cmgAB[0] = (uint4*)ws;   ws += px * 512;
   cmgAB[1] = (uint4*)ws;   ws += px * 512;
   refAB[0] = (uint4*)ws;   ws += px * 384;
@@ -710,6 +747,7 @@ int umma_debug_layer(wn_handle* h, const float* const in[4], const int64_t in_st
   o.scheme = scheme;
   o.dbg_layer = layer;
   o.dbg_dst = dst;
+  o.kpack = !(h->dbg_flags & 2048);
   return umma_forward_layers(h, in, in_strides, nullptr, n, H, W, carve(workspace, n, H, W), stream, o);
 }
 
@@ -747,6 +785,7 @@ int umma_forward(wn_handle* h, const float* const in[4], const int64_t in_stride
     FwdOpts o;
     o.scheme = scheme;
     o.stack = stack;
+    o.kpack = !(h->dbg_flags & 2048);
     float* dst = out + (size_t)n0 * 3 * H * W;
     if (stack == kStackCmg) b.cm = dst;                                   // the maps are the result
     if (stack == kStackRefiners) { b.refined = refined + (size_t)n0 * 9 * H * W; dst = nullptr; }
@@ -787,12 +826,14 @@ int umma_enhance_u8(wn_handle* h, const uint8_t* rgb, uint8_t* out_u8, float* ou
     const int cur = n - n0 < nb ? n - n0 : nb;
     FwdBuffers b = carve(fwd_ws, cur, H, W);
     WN_CUDA(cudaMemsetAsync(b.exact_flag, 1, sizeof(int), stream));
-    rc = preprocess_u8_planes(h, rgb + (size_t)n0 * H * W * 3, cur, H, W, b.act0, pre_ws, pre_b, stream);
+    const bool kpack = !(h->dbg_flags & 2048);
+    rc = preprocess_u8_planes(h, rgb + (size_t)n0 * H * W * 3, cur, H, W, b.act0, pre_ws, pre_b, stream, kpack ? 1 : 0);
     if (rc) return rc;
     FwdOpts o;
     o.scheme = scheme;
     o.packed = true;
     o.hi_only = true;
+    o.kpack = kpack;
     o.out_u8 = out_u8 + (size_t)n0 * H * W * 3;
     rc = umma_pass(h, no_in, none, out_f32 ? out_f32 + (size_t)n0 * 3 * H * W : nullptr, cur, H, W, b, stream, o);
     if (rc) return rc;

@@ -311,10 +311,19 @@ struct ApplyOut {
   uint8_t* u8[3];   // wb, he, gc     -- NHWC, may be null
   uint4* planes;    // may be null: [n][2][H*W] x 16 B, the first conv layer's operand planes (8 bf16 levels each):
                     // torch.cat([x, wb, he, gc], 1) (net.py:46) as plane 0 = x.rgb wb.rgb he.rg, plane 1 = he.b gc.rgb 0 0 0 0
+  int kp;           // planes in the K-packed layout instead: [n][2][H][W + 1], plane 1 = [c8..11 @ x | c8..11 @ x + 1] (common.cuh)
 };
 // bf16 bit patterns of two integer levels 0..255 (exact: 8 significant bits), first level in the low half
 __device__ __forceinline__ uint32_t bf16_levels2(int a, int b) {
   return (__float_as_uint((float)a) >> 16) | (__float_as_uint((float)b) & 0xffff0000u);
+}
+__device__ __forceinline__ void store_level_planes_kp(uint4* planes, size_t n, int H, int W, int pix, const int* lv) {
+  const int y = pix / W, x = pix - y * W;
+  const size_t plane = (size_t)H * (W + 1);
+  store_kp_pixel(planes + n * 2 * plane + (size_t)y * (W + 1) + x + 1, plane, x, W,
+                 make_uint4(bf16_levels2(lv[0], lv[1]), bf16_levels2(lv[2], lv[3]), bf16_levels2(lv[4], lv[5]),
+                            bf16_levels2(lv[6], lv[7])),
+                 make_uint2(bf16_levels2(lv[8], lv[9]), bf16_levels2(lv[10], lv[11])));
 }
 __device__ __forceinline__ void store_level_planes(uint4* planes, size_t n, size_t plane, size_t pix, const int* lv) {
   uint4* p = planes + n * 2 * plane + pix;
@@ -410,7 +419,10 @@ apply_kernel(const uint8_t* __restrict__ rgb, int H, int W, int th, int tw,
       }
       if (out.planes) {
 #pragma unroll
-        for (int k = 0; k < 4; k++) store_level_planes(out.planes, n, plane, pix + k, lv[k]);
+        for (int k = 0; k < 4; k++) {
+          if (out.kp) store_level_planes_kp(out.planes, n, H, W, pix + k, lv[k]);
+          else store_level_planes(out.planes, n, plane, pix + k, lv[k]);
+        }
       }
       const size_t o8 = ((size_t)n * plane + pix) * 3;
 #pragma unroll
@@ -438,7 +450,10 @@ apply_kernel(const uint8_t* __restrict__ rgb, int H, int W, int th, int tw,
         float* q = out.f32[t] + o;
         q[0] = s_div[lv[t * 3]]; q[plane] = s_div[lv[t * 3 + 1]]; q[2 * (size_t)plane] = s_div[lv[t * 3 + 2]];
       }
-      if (out.planes) store_level_planes(out.planes, n, plane, pix, lv);
+      if (out.planes) {
+        if (out.kp) store_level_planes_kp(out.planes, n, H, W, pix, lv);
+        else store_level_planes(out.planes, n, plane, pix, lv);
+      }
       const size_t o8 = ((size_t)n * plane + pix) * 3;
 #pragma unroll
       for (int t = 0; t < 3; t++) {
@@ -507,7 +522,7 @@ size_t preprocess_workspace_bytes(int n, int, int) {
 
 static int preprocess_run(wn_handle* h, const uint8_t* rgb, int n, int H, int W, float* x, float* wb,
                           float* he, float* gc, uint8_t* wb_u8, uint8_t* he_u8, uint8_t* gc_u8, uint4* planes,
-                          void* workspace, size_t workspace_bytes, cudaStream_t stream, int gray = 0);
+                          void* workspace, size_t workspace_bytes, cudaStream_t stream, int gray = 0, int kp = 0);
 
 // grayscale branch of white_balance_transform (data.py:30-36, 38-58 with p = 1): the 2-D image runs through the RGB
 // machinery as r = g = b with the branch's fixed saturation levels; channel 0 of the result is the answer
@@ -551,14 +566,14 @@ int preprocess_u8(wn_handle* h, const uint8_t* rgb, int n, int H, int W, float* 
 }
 
 int preprocess_u8_planes(wn_handle* h, const uint8_t* rgb, int n, int H, int W, uint4* planes, void* workspace,
-                         size_t workspace_bytes, cudaStream_t stream) {
+                         size_t workspace_bytes, cudaStream_t stream, int kp) {
   return preprocess_run(h, rgb, n, H, W, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, planes,
-                        workspace, workspace_bytes, stream);
+                        workspace, workspace_bytes, stream, 0, kp);
 }
 
 static int preprocess_run(wn_handle* h, const uint8_t* rgb, int n, int H, int W, float* x, float* wb,
                           float* he, float* gc, uint8_t* wb_u8, uint8_t* he_u8, uint8_t* gc_u8, uint4* planes,
-                          void* workspace, size_t workspace_bytes, cudaStream_t stream, int gray) {
+                          void* workspace, size_t workspace_bytes, cudaStream_t stream, int gray, int kp) {
   if (workspace_bytes < preprocess_workspace_bytes(n, H, W)) {
     set_error("preprocess workspace too small: %zu < %zu", workspace_bytes,
               preprocess_workspace_bytes(n, H, W));
@@ -603,6 +618,7 @@ static int preprocess_run(wn_handle* h, const uint8_t* rgb, int n, int H, int W,
   ao.f32[0] = x; ao.f32[1] = wb; ao.f32[2] = he; ao.f32[3] = gc;
   ao.u8[0] = wb_u8; ao.u8[1] = he_u8; ao.u8[2] = gc_u8;
   ao.planes = planes;
+  ao.kp = kp;
   TimedScope ts(h, kSlotApply, stream);
   // vector path: 4 pixels per thread needs 4-pixel groups that do not straddle images (and aligned bases)
   const bool vec4 = (H * W) % 4 == 0 && ((uintptr_t)rgb % 4) == 0 && ((uintptr_t)x % 16) == 0 &&

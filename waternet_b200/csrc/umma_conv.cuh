@@ -304,9 +304,19 @@ constexpr int kFmtIn8 = 1, kFmtOut8 = 2;
 //        the accumulator columns the epilogue has just drained, and a second epilogue pass stores the tail layer's
 //        output.  cmg.conv3 -> conv4 (net.py:20-27): conv3's 512 B/px write, conv4's 512 B/px read and its launch
 //        disappear; no shared memory is spent on the intermediate tile.
+// KP     K-packed first layer (inference).  The 12 input channels fill only 12 of a K = 16 step's 16 slots.  A UMMA
+//        descriptor addresses the two 8-element K halves of a step independently (start address + LBO), so a step
+//        can pair ANY two 16-byte rows of the halo tile: channels 0-7 of one tap (plane 0), or a row of plane 1 that
+//        holds channels 8-11 of TWO neighbouring pixels [c8..11 @ x | c8..11 @ x+1] and so serves two taps of a
+//        kernel row at once.  A 7-tap row needs 7 + 4 = 11 halves instead of 14: 77 halves = 39 (padded: kKpSteps =
+//        40) K-steps per tile instead of 49.  The pairs and their LBOs come from a table (ConvArgs::kp_off / kp_lbo;
+//        l1k_table()); the weights are packed to match.  Plane 1's "next pixel" half makes the planes one column
+//        wider: column x + 1 holds pixel x, so that TMA zero fill left of the image stays correct.
+constexpr int kKpSteps = 40;
 template <int KS, int CIN_PAD, int NPAD, int S, int AS, int CONCAT = 0, int NBLK = 1, int TPS = 1, int CG = 1,
-          int FMT = 0, int TN = 0>
+          int FMT = 0, int TN = 0, int KP = 0>
 struct UmmaCfg {
+  static constexpr int KSTEPS = KP ? kKpSteps : KS * KS;   // weight "taps" (K = 16 steps per chunk) per tile
   static constexpr int K2 = NPAD * NBLK;                                 // tail GEMM K = this layer's output channels
   static constexpr int A2_COLS = TN ? K2 : 0;                            // TMEM columns per sub-tile: K2/2 hi pairs | K2/2 lo pairs
   // tail weights per K=16 step and rank.  One block (NBLK == 1), CONCAT form: [k8][TN | TN/2 rows][16 B] (a_hi x [w_hi|w_lo],
@@ -332,8 +342,9 @@ struct UmmaCfg {
   static constexpr int B_STAGE = TPS * B_TAP;
   // WRAP: TPS does not divide the tap count (single-chunk layers only): weight stages are groups of TPS
   // consecutive taps of the endless tap stream (tile after tile), so a group may straddle two tiles
-  static constexpr bool WRAP = (KS * KS) % TPS != 0;
-  static constexpr int NSTAGE_PER_CHUNK = KS * KS / TPS;
+  static constexpr bool WRAP = KSTEPS % TPS != 0;
+  static constexpr int NSTAGE_PER_CHUNK = KSTEPS / TPS;
+  static_assert(!KP || (KS == 7 && CIN_PAD == 16 && CG == 2 && !CONCAT && TN == 0), "K-packing: the 7x7 first layer");
   static constexpr int BUDGET = 225 * 1024 - 2048 - TAIL_BYTES;
   // halo ring: enough stages to prefetch the next chunk (or the next tile when there is one chunk)
   // (a 1x1 layer is HBM-bound and its stages are small: keep more loads in flight)
@@ -409,6 +420,9 @@ struct ConvArgs {
   // split_c / cout then describe the TAIL layer's output
   const uint8_t* wtail;
   const float* bias2;
+  // K-packed first layer (UmmaCfg KP): per K step the start offset (16-byte units inside the halo stage) of its
+  // lower half and the distance to the other one
+  uint16_t kp_off[kKpSteps], kp_lbo[kKpSteps];
   // conditional launch: when non-null and *run_if == 0 the kernel returns at once (the bf16x3 re-run of a
   // batch is enqueued unconditionally behind the fp8-correction pass and only does work if the flag is up)
   const int* run_if;
@@ -439,10 +453,10 @@ __device__ __forceinline__ void split_bf16x2(float f0, float f1, uint32_t& hi, u
 //        contribution to output pixel q - shift(tap) -- and a small gather kernel adds the nine shifted planes.
 enum TailEpilogue { kTailAct = 0, kTailTaps = 1 };
 template <int KS, int CIN_PAD, int NPAD, int S, int AS, int EPI, int CONCAT, int NBLK, int TPS, int CG = 1, int FMT = 0,
-          int TN = 0, int TEPI = kTailAct>
+          int TN = 0, int TEPI = kTailAct, int KP = 0>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) {
-  using C = UmmaCfg<KS, CIN_PAD, NPAD, S, AS, CONCAT, NBLK, TPS, CG, FMT, TN>;
+  using C = UmmaCfg<KS, CIN_PAD, NPAD, S, AS, CONCAT, NBLK, TPS, CG, FMT, TN, KP>;
   static_assert(TN == 0 || EPI == kEpiAct, "a tail layer follows an activation layer");
   constexpr bool F8IN = C::F8IN, DUAL = C::DUAL, OUT8 = (FMT & kFmtOut8) != 0;
   static_assert(!OUT8 || EPI == kEpiAct, "fp8 planes are written by the activation epilogue only");
@@ -524,7 +538,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
         const int n = tile / (g.tiles_x * g.tiles_y);
         const int rem = tile - n * g.tiles_x * g.tiles_y;
         const int ty = rem / g.tiles_x, tx = rem - ty * g.tiles_x;
-        const int x0 = tx * C::TILE_W - KS / 2, y0 = ty * C::TILE_H - KS / 2;
+        const int x0 = tx * C::TILE_W - KS / 2 + (KP ? 1 : 0), y0 = ty * C::TILE_H - KS / 2;  // KP: column x + 1 = pixel x
         for (int c = 0; c < C::NCHUNK; c++) {
           mbar_wait(&a_empty[stage], phase ^ 1);
           uint8_t* dst = a_stages + stage * C::A_STAGE;
@@ -795,7 +809,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
                 const int tap = tg * TPS + t;
                 const int ky = tap / KS, kx = tap - ky * KS;
                 const uint32_t b_lo32 = b_stage32 + (uint32_t)(t * (C::B_TAP >> 4));
-                const uint32_t a_tap = a_lo32 + (uint32_t)(ky * C::HALO_W + kx);
+                // K-packed: "tap" is a K step whose two halves are any two rows of the stage (table-driven)
+                const uint32_t a_tap = KP ? (a_lo32 & 0xffffu) + (uint32_t)g.kp_off[tap] + ((uint32_t)g.kp_lbo[tap] << 16)
+                                          : a_lo32 + (uint32_t)(ky * C::HALO_W + kx);
                 const uint32_t first = ((NBLK > 1 ? c % C::CPB : c) | tap) == 0 ? 0u : 1u;
                 // pass-major order: consecutive MMAs target different accumulators
 #pragma unroll
@@ -1353,6 +1369,73 @@ static __global__ void pack_stages_f8_cg2_kernel(const float* __restrict__ dense
 }
 
 // ------------------------------------------------------------------------------------------
+// K-packed first layer (UmmaCfg KP): the table of K steps and the matching weight images
+// ------------------------------------------------------------------------------------------
+// One 8-element K half: plane 0 row = channels 0-7 of tap (ky, kx); plane 1 row = channels 8-11 of taps (ky, kx) and
+// (ky, kx + 1); type 2 = padding (zero weights).
+struct KpHalf {
+  int8_t type, ky, kx;
+};
+struct KpTable {
+  KpHalf half[2 * kKpSteps];   // half[2 * step + k8]: the step's lower-address / higher-address half
+  uint16_t off[kKpSteps], lbo[kKpSteps];
+};
+// halo_w, plane_units: geometry of the halo stage (16-byte units).  Halves in kernel-row order: plane 0 at kx = 0..6,
+// plane 1 at kx = 0, 2, 4, 6 (77 halves), padded to 80; consecutive halves pair up, lower address first.
+static KpTable l1k_table(int halo_w, int plane_units) {
+  KpTable t;
+  KpHalf seq[2 * kKpSteps];
+  int n = 0;
+  for (int ky = 0; ky < 7; ky++) {
+    for (int kx = 0; kx < 7; kx++) seq[n++] = KpHalf{0, (int8_t)ky, (int8_t)kx};
+    for (int kx = 0; kx < 7; kx += 2) seq[n++] = KpHalf{1, (int8_t)ky, (int8_t)kx};
+  }
+  // padding halves: distinct valid rows (their weights are zero)
+  seq[n++] = KpHalf{2, 0, 0};
+  seq[n++] = KpHalf{2, 0, 1};
+  seq[n++] = KpHalf{2, 0, 2};
+  auto addr = [&](const KpHalf& hf) { return (hf.type == 1 ? plane_units : 0) + hf.ky * halo_w + hf.kx; };
+  for (int s = 0; s < kKpSteps; s++) {
+    KpHalf a = seq[2 * s], b = seq[2 * s + 1];
+    if (addr(a) > addr(b)) { KpHalf tmp = a; a = b; b = tmp; }
+    t.half[2 * s] = a;
+    t.half[2 * s + 1] = b;
+    t.off[s] = (uint16_t)addr(a);
+    t.lbo[s] = (uint16_t)(addr(b) - addr(a));
+  }
+  return t;
+}
+// dense fp32 [npad rows][16 channels][49 taps] -> per rank [step][hi|lo][k8][npad/2 rows][8] bf16 (the CG=2 non-CONCAT
+// stage layout with K steps in place of taps)
+static __global__ void pack_l1k_kernel(const float* __restrict__ dense, __nv_bfloat16* __restrict__ out, int npad,
+                                       const KpTable t) {
+  const int rows = npad / 2;
+  const size_t per_rank = (size_t)kKpSteps * 2 * 2 * rows * 8;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < 2 * per_rank; i += (size_t)gridDim.x * blockDim.x) {
+    const int rank = (int)(i / per_rank);
+    size_t r = i % per_rank;
+    const int e = (int)(r % 8); r /= 8;
+    const int q = (int)(r % rows); r /= rows;
+    const int k8 = (int)(r % 2); r /= 2;
+    const int part = (int)(r % 2); r /= 2;
+    const int step = (int)r;
+    const KpHalf hf = t.half[2 * step + k8];
+    int ch = -1, tap = 0;
+    if (hf.type == 0) { ch = e; tap = hf.ky * 7 + hf.kx; }
+    else if (hf.type == 1) {
+      ch = 8 + (e & 3);
+      const int kx = hf.kx + (e >> 2);
+      tap = hf.ky * 7 + kx;
+      if (kx > 6) ch = -1;
+    }
+    float w = 0.f;
+    if (ch >= 0) w = dense[((size_t)(rank * rows + q) * 16 + ch) * 49 + tap];
+    const __nv_bfloat16 hi = __float2bfloat16_rn(w);
+    out[i] = part == 0 ? hi : __float2bfloat16_rn(w - __bfloat162float(hi));
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // Host helpers
 // ------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -1391,14 +1474,14 @@ static int make_tmap(CUtensorMap* tm, void* base, int planes_total, int N, int H
 
 // Launch one convolution.  `slot` is the timing slot (common.cuh).
 template <int KS, int CIN_PAD, int NPAD, int S, int AS, int EPI, int CONCAT = 0, int NBLK = 1, int TPS = 1, int CG = 1,
-          int FMT = 0, int TN = 0, int TEPI = 0>
+          int FMT = 0, int TN = 0, int TEPI = 0, int KP = 0>
 static int launch_conv(wn_handle* h, int slot, const uint8_t* wpk, const float* bias, void* in_base, ConvArgs a,
                        cudaStream_t stream) {
-  using C = UmmaCfg<KS, CIN_PAD, NPAD, S, AS, CONCAT, NBLK, TPS, CG, FMT, TN>;
+  using C = UmmaCfg<KS, CIN_PAD, NPAD, S, AS, CONCAT, NBLK, TPS, CG, FMT, TN, KP>;
   int rc = get_encoder();
   if (rc) return rc;
   CUtensorMap tm;
-  rc = make_tmap(&tm, in_base, (a.a_hi_only ? 1 : 2) * (CIN_PAD / 8), a.N, a.H, a.W, C::HALO_W, C::HALO_H);
+  rc = make_tmap(&tm, in_base, (a.a_hi_only ? 1 : 2) * (CIN_PAD / 8), a.N, a.H, a.W + (KP ? 1 : 0), C::HALO_W, C::HALO_H);
   if (rc) return rc;
   a.wpk = wpk;
   a.bias = bias;
@@ -1407,7 +1490,7 @@ static int launch_conv(wn_handle* h, int slot, const uint8_t* wpk, const float* 
   a.tiles_x = (a.W + C::TILE_W - 1) / C::TILE_W;
   a.tiles_y = (a.H + C::TILE_H - 1) / C::TILE_H;
   const long long tiles = (long long)a.tiles_x * a.tiles_y * a.N;
-  auto kern = conv_umma_kernel<KS, CIN_PAD, NPAD, S, AS, EPI, CONCAT, NBLK, TPS, CG, FMT, TN, TEPI>;
+  auto kern = conv_umma_kernel<KS, CIN_PAD, NPAD, S, AS, EPI, CONCAT, NBLK, TPS, CG, FMT, TN, TEPI, KP>;
   WN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
   TimedScope ts(h, slot, stream);
   if constexpr (CG == 2) {  // clusters of two CTAs (one TPC each); every pair takes two adjacent tiles at a time

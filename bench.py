@@ -442,6 +442,11 @@ def main():
                 macs_by_slot[2] += macs_by_slot[3]
                 macs_by_slot[3] = 0
                 names_by_slot[2] = "cmg.conv3+conv4"
+            if mode != _lib.MODE_BF16X3 and not flags & 1024:  # refiner conv3 tap-stacked behind conv2 + gather/gate kernel
+                macs_by_slot[9] += macs_by_slot[10]
+                macs_by_slot[10] = 0
+                names_by_slot[9] = "refiner.conv2x3+conv3x3(taps)"
+                names_by_slot[10] = "refiner.conv3.gather+gate"
             if mode != _lib.MODE_BF16X3 and not flags & 512:   # conv8 tap-stacked behind conv7 + a gather kernel
                 macs_by_slot[6] += macs_by_slot[7]
                 macs_by_slot[7] = 0

@@ -193,8 +193,9 @@ int wn_debug_forward_layer(wn_handle* h, const float* x, const float* wb, const 
  * stores, bit 1: weight-stage refetch, bit 2: the lo passes).  RESULTS ARE WRONG with any of bits 0-7 set;
  * 0 restores normal operation.  Used by tools/pipeline_attribution.py only.  Bits 8-10 are A/B switches with
  * correct results: 256 = cmg.conv3 and conv4 as two launches (instead of conv4 as conv3's fused tail layer),
- * 512 = cmg.conv7 and conv8 as two launches (instead of conv8 tap-stacked behind conv7 + gather), 1024 = (an
- * experiment that measured slower, hence opt-in) the refiners' conv3 + gate tap-stacked behind their conv2.
+ * 512 = cmg.conv7 and conv8 as two launches (instead of conv8 tap-stacked behind conv7 + gather), 1024 = the
+ * refiners' conv2 and conv3 + gate as two launches (instead of conv3 tap-stacked behind conv2 + gather/gate),
+ * 2048 = the plain 49-tap first layer (instead of the K-packed one).
  */
 int wn_debug_set_flags(wn_handle* h, int flags);
 

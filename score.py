@@ -23,6 +23,8 @@ def main():
     ap.add_argument("--height", type=int, default=112)
     ap.add_argument("--width", type=int, default=112)
     ap.add_argument("--seed", type=int, default=None)
+    ap.add_argument("--epochs", type=int, default=400, help="accepted for command-line compatibility with the reference's "
+                                                            "score.py (:96); scoring runs one validation pass")
     ap.add_argument("--synthetic", action="store_true")
     args = ap.parse_args()
     assert args.weights is not None, "No weights specified in --weights!"

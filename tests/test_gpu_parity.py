@@ -914,9 +914,8 @@ def test_fused_tail_layers_equal_separate_launches():
         cu = [t.cuda() for t in ins]
         res = {}
         with torch.no_grad():
-            # 256: conv3 / conv4 as two launches; 512: conv7 / conv8 as two launches; 1024: (opt-in experiment) the
-            # refiners' conv3 + gate tap-stacked behind their conv2; 768: nothing fused
-            for flags in (0, 256, 512, 1024, 768):
+            # 256: conv3 / conv4 as two launches; 512: conv7 / conv8; 1024: refiner conv2 / conv3 + gate; 1792: nothing fused
+            for flags in (0, 256, 512, 1024, 1792):
                 eng.set_debug_flags(flags)
                 try:
                     res[flags] = (m(*cu).cpu().numpy(),
@@ -932,7 +931,7 @@ def test_fused_tail_layers_equal_separate_launches():
         # float64 oracle the parity bar
         ref64 = ofw.waternet_forward(sd, *ins, dtype=torch.float64).numpy()
         for flags in (0, 256, 512, 1024):
-            for got, want in zip(res[flags], res[768]):
+            for got, want in zip(res[flags], res[1792]):
                 _assert_close(got, want, tol=3e-4)
             _assert_close(res[flags][0], ref64)
 

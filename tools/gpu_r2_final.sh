@@ -19,7 +19,7 @@ for f in ("default", "bf16x3", "reference"):
     print(f, "value", d.get("value"), "e2e", d.get("e2e", {}).get("value"), "ms", d.get("ms_per_step"), d.get("clocks"))
     if f == "default": print(d.get("kernel_ms_per_step")); print(d.get("parity")); print(d["roofline"]["frac"], d["roofline"]["achieved"], d["gpu_launches"])
 PY
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"conv_umma|gather_sigmoid" -s 19 -c 19 -o /tmp/prof_r2_fwd \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"conv_umma|gather_" -s 19 -c 19 -o /tmp/prof_r2_fwd \
   python tools/profile_forward.py 1 1080 1920 default > gpurun_out/ncu_full.log 2>&1; echo "ncu full exit $?"
 python tools/summarize_ncu.py full /tmp/prof_r2_fwd.ncu-rep gpurun_out/r2_umma_kernels_1080p_n1.csv > /dev/null
 timeout 600 ncu --set full --clock-control none -k regex:"apply_kernel|stats_kernel|luts_kernel" -s 3 -c 3 -o /tmp/prof_r2_pre \

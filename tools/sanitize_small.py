@@ -18,8 +18,8 @@ big = torch.randint(0, 256, (1, 130, 200, 3), dtype=torch.uint8, device="cuda") 
 eng.set_chunk_pixels(130 * 200)
 out = eng.enhance(torch.cat([big, big]), mode=_lib.MODE_DEFAULT)                    # two passes, fused tails
 eng.set_chunk_pixels(0)
-eng.set_debug_flags(1024)
-out = eng.enhance(big, mode=_lib.MODE_DEFAULT)                                      # refiner tap-stack experiment
+eng.set_debug_flags(1792 + 2048)
+out = eng.enhance(big, mode=_lib.MODE_DEFAULT)                                      # the unfused / plain-first-layer forms
 eng.set_debug_flags(0)
 res = eng.resize_batch([big[0], rgb[0]], 48, 64, swap_rb=True)
 gray = eng.white_balance_gray(rgb[..., 0].contiguous())

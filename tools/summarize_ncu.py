@@ -91,7 +91,8 @@ LAYER_OF_KERNEL = [
     ("conv_umma_kernel<3, 64, 64", "cmg.conv7"),         # "+conv8(taps)" with a tail of 32 columns
     ("conv_umma_kernel<3, 64, 16", "cmg.conv8"),
     ("gather_sigmoid_kernel", "cmg.conv8.gather+sigmoid"),
-    ("conv_umma_kernel<5, 96, 32", "refiner.conv2x3"),
+    ("conv_umma_kernel<5, 96, 32", "refiner.conv2x3"),   # "+conv3x3(taps)" with a tail of 96 columns
+    ("gather_gate_kernel", "refiner.conv3.gather+gate"),
     ("conv_umma_kernel<3, 96, 16", "refiner.conv3x3+gate"),
 ]
 
@@ -105,6 +106,8 @@ def layer_name(kernel):
                 return "cmg.conv3+conv4"
             if name == "cmg.conv7" and len(args) >= 12 and args[11] == "32":
                 return "cmg.conv7+conv8(taps)"
+            if name == "refiner.conv2x3" and len(args) >= 12 and args[11] == "96":
+                return "refiner.conv2x3+conv3x3(taps)"
             return name
     return None
 

@@ -425,11 +425,30 @@ size_t umma_forward_workspace_bytes(int n, int h, int w) {
 #ifndef WN_F8_C56_S
 #define WN_F8_C56_S 2
 #endif
+#ifndef WN_F8_C5_S
+#define WN_F8_C5_S 4   // conv5 (7x7): 22.5 -> 22.0 ms per batch with four sub-tiles; conv6 (5x5) is slower that way (11.6 -> 11.9)
+#endif
+// taps per weight stage of the refiners' conv2 (5 = one kernel row, 25 = a whole chunk)
+#ifndef WN_F8_R2_TPS
+#define WN_F8_R2_TPS 5
+#endif
+// refiner conv2 with the tap-stacked conv3 tail: S=2, AS=2 = 384 accumulator columns + ONE 96-column bf16 operand
+// region the two sub-tiles take turns on (UmmaCfg::A2_SHARED); -DWN_R23_S=1 -DWN_R23_AS=3: one-sub-tile tiles
+#ifndef WN_R23_S
+#define WN_R23_S 2
+#endif
 #ifndef WN_R23_AS
-#define WN_R23_AS 3   // refiner conv2 with the tap-stacked conv3 tail: one sub-tile = 96 accumulator columns per stage + 96 for its bf16 copy
+#define WN_R23_AS 2
+#endif
+// where the tail GEMM's A operand lives: 1 = kTailTaps (tensor memory), 3 = kTailTaps | kTailSmem (shared memory)
+#ifndef WN_C78_TEPI
+#define WN_C78_TEPI 1   // measured equal to the shared-memory form; the tensor-memory form keeps conv7's halo ring at 6 stages
+#endif
+#ifndef WN_R23_TEPI
+#define WN_R23_TEPI 3
 #endif
 #ifndef WN_C78_AS
-#define WN_C78_AS 3   // conv7 with the tap-stacked conv8 tail: 2 x 64 accumulator columns per stage + 2 x 64 for the bf16 tiles
+#define WN_C78_AS 3   // conv7 with the tap-stacked conv8 tail: 2 x 64 accumulator columns per stage (+ 2 x 64 for the bf16 tiles in the tensor-memory form)
 #endif
 #ifndef WN_C7_TPS
 #define WN_C7_TPS 9
@@ -594,7 +613,7 @@ int umma_forward_layers(wn_handle* h, const float* const in[4], const int64_t st
       }
       if (dump(3, a4, 64, 1)) return WN_OK;
       act(a5, 64, nullptr, 0);
-      if ((rc = launch_umma<7, 64, 64, WN_F8_C56_S, 2, kEpiAct, 0, 1, 7, 2, IN8 | OUT8>(h, kC5, a4, a, stream))) return rc;
+      if ((rc = launch_umma<7, 64, 64, WN_F8_C5_S, 2, kEpiAct, 0, 1, 7, 2, IN8 | OUT8>(h, kC5, a4, a, stream))) return rc;
       if (dump(4, a5, 64, 1)) return WN_OK;
       act(a6, 64, nullptr, 0);
       if ((rc = launch_umma<5, 64, 64, WN_F8_C56_S, 2, kEpiAct, 0, 1, 5, 2, IN8 | OUT8>(h, kC6, a5, a, stream))) return rc;
@@ -610,7 +629,7 @@ int umma_forward_layers(wn_handle* h, const float* const in[4], const int64_t st
         a.cout = 27;
         a.wtail = h->umma->tail8;
         a.bias2 = h->umma->bias[kC8];  // unused by the tap-stacked epilogue (the gather adds the bias)
-        if ((rc = launch_umma<3, 64, 64, 2, WN_C78_AS, kEpiAct, 0, 1, 9, 2, IN8, 32, kTailTaps>(h, kC7, a6, a, stream))) return rc;
+        if ((rc = launch_umma<3, 64, 64, 2, WN_C78_AS, kEpiAct, 0, 1, 9, 2, IN8, 32, WN_C78_TEPI>(h, kC7, a6, a, stream))) return rc;
         a.wtail = nullptr;
         a.bias2 = nullptr;
         {
@@ -628,19 +647,19 @@ int umma_forward_layers(wn_handle* h, const float* const in[4], const int64_t st
       if (dbg_layer == 7) return WN_OK;
     }
     if (!want_ref) return WN_OK;
-    if (dbg_layer != 9 && (h->dbg_flags & 1024)) {
-      // EXPERIMENT, off by default (flag bit 10): the refiners' conv2 with their conv3 (3x3, 32 -> 3 each) tap-stacked
-      // as a block-diagonal fused tail layer: 81 partial-sum planes (324 B/px) instead of 96 channels (384 B/px);
-      // gather_gate_kernel adds the nine shifted planes per output, bias, ReLU and the gated sum (net.py:65-70,
-      // 104-108).  Correct (tests), but measured SLOWER than the two launches: 22.4 + gather vs 15.7 + 6.2 ms per
-      // batch -- the one-sub-tile tile this needs (TMEM: 96 accumulator + 96 operand columns per sub-tile) pays the
-      // tensor-memory-operand drain once per 128 pixels, and the refiners' conv2 is already bound by its operand
-      // reads (profiles/r2_ab_fused_tails.log).
+    if (dbg_layer != 9 && !(h->dbg_flags & 1024)) {
+      // the refiners' conv2 with their conv3 (3x3, 32 -> 3 each) tap-stacked as a block-diagonal fused tail layer:
+      // 81 partial-sum planes (324 B/px, in the buffer conv2's activations would have taken) instead of 96 channels
+      // (384 B/px); gather_gate_kernel adds the nine shifted planes per output, bias, ReLU and the gated sum
+      // (net.py:65-70, 104-108).  The tail GEMM's operand goes through shared memory here (kTailSmem: the refiners'
+      // small rings leave 96 KB free).  Same-box: 16.0 + 6.3 -> 19.8 + 1.9 ms per batch, +0.8 % images/s
+      // (profiles/r2_ab_fused_tails.log) -- the tail costs the conv2 launch more than its 36 small MMAs per tile
+      // suggest, see DESIGN.md 4.2.
       float* taps = reinterpret_cast<float*>(b.r[2]);
       a.out_f32 = taps;
       a.wtail = h->umma->tailr3;
       a.bias2 = nullptr;
-      if ((rc = launch_umma<5, 96, 32, 1, WN_R23_AS, kEpiAct, 0, 3, 25, 2, IN8, 96, kTailTaps>(h, kR2, b.r[1], a, stream))) return rc;
+      if ((rc = launch_umma<5, 96, 32, WN_R23_S, WN_R23_AS, kEpiAct, 0, 3, WN_R23_S == 1 ? 25 : WN_F8_R2_TPS, 2, IN8, 96, WN_R23_TEPI>(h, kR2, b.r[1], a, stream))) return rc;
       a.wtail = nullptr;
       TimedScope ts(h, spec_slot(kR3), stream);
       gather_gate_kernel<<<dim3((W + 63) / 64, (H + 3) / 4, n), dim3(64, 4), 0, stream>>>(
@@ -649,7 +668,7 @@ int umma_forward_layers(wn_handle* h, const float* const in[4], const int64_t st
       return WN_OK;
     }
     act(b.r[2], 96, nullptr, 0);
-    if ((rc = launch_umma<5, 96, 32, 2, WN_F8_R2_AS, kEpiAct, 0, 3, 5, 2, IN8>(h, kR2, b.r[1], a, stream))) return rc;
+    if ((rc = launch_umma<5, 96, 32, 2, WN_F8_R2_AS, kEpiAct, 0, 3, WN_F8_R2_TPS, 2, IN8>(h, kR2, b.r[1], a, stream))) return rc;
     if (dump(9, b.r[2], 96)) return WN_OK;
     last();
     if ((rc = launch_umma<3, 96, 16, 4, 2, kEpiGate, 1, 1, 9>(h, kR3, b.r[2], a, stream))) return rc;

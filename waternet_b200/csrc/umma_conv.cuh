@@ -314,11 +314,15 @@ constexpr int kFmtIn8 = 1, kFmtOut8 = 2;
 //        wider: column x + 1 holds pixel x, so that TMA zero fill left of the image stays correct.
 constexpr int kKpSteps = 40;
 template <int KS, int CIN_PAD, int NPAD, int S, int AS, int CONCAT = 0, int NBLK = 1, int TPS = 1, int CG = 1,
-          int FMT = 0, int TN = 0, int KP = 0>
+          int FMT = 0, int TN = 0, int KP = 0, int A2S = 0>
 struct UmmaCfg {
   static constexpr int KSTEPS = KP ? kKpSteps : KS * KS;   // weight "taps" (K = 16 steps per chunk) per tile
   static constexpr int K2 = NPAD * NBLK;                                 // tail GEMM K = this layer's output channels
-  static constexpr int A2_COLS = TN ? K2 : 0;                            // TMEM columns per sub-tile: K2/2 hi pairs | K2/2 lo pairs
+  // the tail GEMM's A operand (bf16 hi/lo copy of the tile): in tensor memory (A2S == 0), K2 columns per sub-tile (K2/2
+  // hi pairs | K2/2 lo pairs), or in shared memory (A2S != 0), per sub-tile [hi|lo][k8 group][128 rows][16 B]
+  static constexpr int A2_COLS = (TN && !A2S) ? K2 : 0;
+  static constexpr int A2_SUB = 2 * (K2 / 8) * 2048;
+  static constexpr int A2_BYTES = (TN && A2S) ? S * A2_SUB : 0;
   // tail weights per K=16 step and rank.  One block (NBLK == 1), CONCAT form: [k8][TN | TN/2 rows][16 B] (a_hi x [w_hi|w_lo],
   // a_lo x w_hi).  Block-diagonal (the three refiners): TN / NBLK columns per block, three passes into the same
   // columns, [hi|lo][k8][TN / NBLK / 2 rows][16 B]
@@ -326,7 +330,7 @@ struct UmmaCfg {
   static constexpr int TNB = TN / NBLK;                                  // tail output columns per block
   static constexpr int WT_TAP = TAIL_BLK ? TNB * 32 : TN * 48;
   static constexpr int WT_BYTES = TN ? (K2 / 16) * WT_TAP : 0;
-  static constexpr int TAIL_BYTES = (WT_BYTES + 1023) / 1024 * 1024;
+  static constexpr int TAIL_BYTES = (A2_BYTES + WT_BYTES + 1023) / 1024 * 1024;
 
   static constexpr bool F8IN = (FMT & kFmtIn8) != 0;
   static constexpr bool DUAL = CONCAT != 0;  // two accumulator halves per block: [a x w_hi | a_hi x w_lo]
@@ -368,7 +372,11 @@ struct UmmaCfg {
   static constexpr int BLK_COLS = DUAL ? 2 * NPAD : NPAD;   // accumulator columns per block
   static constexpr int SUB_COLS = NBLK * BLK_COLS;         // accumulator columns per sub-tile
   static constexpr int A2_COL0 = AS * S * SUB_COLS;        // tail: first TMEM column of the activation tile(s)
-  static constexpr int TMEM_COLS_USED = AS * S * SUB_COLS + S * A2_COLS;
+  // A2_SHARED: no room for one bf16 copy per sub-tile -> the sub-tiles take turns on ONE region (sub-tile s writes it
+  // after the tail GEMM of sub-tile s - 1 has read it; barriers t2_sub[])
+  static constexpr bool A2_SHARED = TN != 0 && AS * S * SUB_COLS + S * A2_COLS > 512;
+  static constexpr int A2_REGIONS = A2_SHARED ? 1 : S;
+  static constexpr int TMEM_COLS_USED = AS * S * SUB_COLS + A2_REGIONS * A2_COLS;
   static_assert(NCHUNK % NBLK == 0, "chunks must split evenly over the diagonal blocks");
   static_assert(N1 % 16 == 0 && N1 <= 256, "invalid UMMA N for the a_hi pass");
   static constexpr int TMEM_COLS = TMEM_COLS_USED <= 32 ? 32 : TMEM_COLS_USED <= 64 ? 64
@@ -451,12 +459,18 @@ __device__ __forceinline__ void split_bf16x2(float f0, float f1, uint32_t& hi, u
 //        output channels (cmg.conv8: 64 -> 3) in "tap-stacked" form: its 9 x 3 = 27 (tap, channel) filters are 27
 //        output columns of a 1x1 tail GEMM on the UNSHIFTED tile -- column 3*tap + c of pixel q is tap's
 //        contribution to output pixel q - shift(tap) -- and a small gather kernel adds the nine shifted planes.
-enum TailEpilogue { kTailAct = 0, kTailTaps = 1 };
+//        Bit 1 (kTailSmem): the bf16 copy of the tile -- the tail GEMM's A operand -- goes through SHARED memory
+//        (UMMA K-major layout, st.shared + fence.proxy.async) instead of tensor memory.  A tcgen05.mma that takes A from
+//        TMEM costs ~150-200 cycles here whatever its N (same-box A/B, profiles/r2_ab_fused_tails.log), one from
+//        shared memory 36-64; layers whose operand rings leave 64-96 KB of shared memory free (conv7, the refiners'
+//        conv2) use this form, conv3 (rings need the space) the tensor-memory form.
+enum TailEpilogue { kTailAct = 0, kTailTaps = 1, kTailSmem = 2 };
 template <int KS, int CIN_PAD, int NPAD, int S, int AS, int EPI, int CONCAT, int NBLK, int TPS, int CG = 1, int FMT = 0,
           int TN = 0, int TEPI = kTailAct, int KP = 0>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) {
-  using C = UmmaCfg<KS, CIN_PAD, NPAD, S, AS, CONCAT, NBLK, TPS, CG, FMT, TN, KP>;
+  using C = UmmaCfg<KS, CIN_PAD, NPAD, S, AS, CONCAT, NBLK, TPS, CG, FMT, TN, KP, (TEPI & kTailSmem) != 0>;
+  constexpr bool A2SMEM = (TEPI & kTailSmem) != 0, TAPS = (TEPI & kTailTaps) != 0;
   static_assert(TN == 0 || EPI == kEpiAct, "a tail layer follows an activation layer");
   constexpr bool F8IN = C::F8IN, DUAL = C::DUAL, OUT8 = (FMT & kFmtOut8) != 0;
   static_assert(!OUT8 || EPI == kEpiAct, "fp8 planes are written by the activation epilogue only");
@@ -465,8 +479,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* a_stages = smem;
   uint8_t* b_stages = smem + C::NA * C::A_STAGE;
-  uint8_t* wt_smem = b_stages + C::NB * C::B_STAGE;     // tail layer: its weights, resident for the whole launch
-  uint8_t* tail = wt_smem + C::TAIL_BYTES;
+  uint8_t* a2_tiles = b_stages + C::NB * C::B_STAGE;    // tail layer, shared-memory form: the tile(s) in operand layout
+  uint8_t* wt_smem = a2_tiles + C::A2_BYTES;            // tail layer: its weights, resident for the whole launch
+  uint8_t* tail = a2_tiles + C::TAIL_BYTES;
   uint64_t* a_full = reinterpret_cast<uint64_t*>(tail);
   uint64_t* a_empty = a_full + C::NA;
   uint64_t* b_full = a_empty + C::NA;
@@ -477,12 +492,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
   uint64_t* b_full_peer = a_full_peer + C::NA;
   uint64_t* a2_full = b_full_peer + C::NB;     // [S] tail: "sub-tile s is back in TMEM as bf16 operand" (leader's barrier counts both CTAs)
   uint64_t* t2_full = a2_full + S;             // [AS] tail: "the tail GEMM of this accumulator stage has completed"
-  uint64_t* wt_full = t2_full + AS;            // tail weights landed (own CTA) / (leader) in the peer CTA
+  uint64_t* t2_sub = t2_full + AS;             // [S] tail, shared operand region: "the tail GEMM of sub-tile s has completed"
+  uint64_t* wt_full = t2_sub + S;              // tail weights landed (own CTA) / (leader) in the peer CTA
   uint64_t* wt_full_peer = wt_full + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wt_full_peer + 1);
   float* s_bias = reinterpret_cast<float*>(tail + 512);
   float* s_bias2 = s_bias + NBLK * NPAD;
-  static_assert(AS <= 4 && S <= 4 && (3 * 6 + 3 * 8 + 2 * AS + S + AS + 2) * 8 + 4 <= 512, "barrier area");
+  static_assert(AS <= 4 && S <= 4 && (3 * 6 + 3 * 8 + 2 * AS + S + AS + S + 2) * 8 + 4 <= 512, "barrier area");
   static_assert((NBLK * NPAD + TN) * 4 <= 2048 - 512, "bias area");
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -500,13 +516,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
     if constexpr (TN > 0) {
       for (int i = 0; i < S; i++) mbar_init(&a2_full[i], (S == 1 ? 8 : 4) * CG);
       for (int i = 0; i < AS; i++) mbar_init(&t2_full[i], 1);
+      for (int i = 0; i < S; i++) mbar_init(&t2_sub[i], 1);
       mbar_init(wt_full, 1);
       mbar_init(wt_full_peer, 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int i = tid; i < NBLK * NPAD; i += kThreads) s_bias[i] = g.bias[i];
-  if constexpr (TN > 0 && TEPI == kTailAct)
+  if constexpr (TN > 0 && !TAPS)
     for (int i = tid; i < TN; i += kThreads) s_bias2[i] = g.bias2[i];
   if (warp == kWarpTmem) {
     if constexpr (CG == 2) {
@@ -707,71 +724,100 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
       // of its tile -- and with it the epilogue's next first pass -- for the whole queue; issued after two stages it
       // runs ~2 stages after its tile completed, while those two stages keep the tensor pipe busy during the
       // epilogue's first pass.  (ncu, conv7 + tap-stacked conv8: 12.4k -> ~8.6k cycles per tile.)
-#ifndef WN_TAIL_FORCE_AT
-#define WN_TAIL_FORCE_AT 2
-#endif
-      constexpr int kTailForceAt = C::NCHUNK * C::NSTAGE_PER_CHUNK > WN_TAIL_FORCE_AT ? WN_TAIL_FORCE_AT
-                                                                                     : C::NCHUNK * C::NSTAGE_PER_CHUNK - 1;
+#ifndef WN_TAIL_FORCE_NUM
+#define WN_TAIL_FORCE_NUM 3   // the tail GEMM is polled for at every weight stage of the next tile and waited for only
+#endif                        // when NUM/4 of that tile's stages have been issued (a safety net, not the schedule)
+      constexpr int kStagesPerTile = C::NCHUNK * C::NSTAGE_PER_CHUNK;
+      constexpr int kTailForceAt = kStagesPerTile * WN_TAIL_FORCE_NUM / 4 < kStagesPerTile - 1 ? kStagesPerTile * WN_TAIL_FORCE_NUM / 4
+                                                                                              : kStagesPerTile - 1;
       int pend_acc = -1;            // accumulator stage whose tail GEMM is still to be issued
+      int pend_sub = 0;             // shared operand region: the next sub-tile of that tile
       uint32_t a2phase = 0;
-      auto tail_step = [&](bool force) {
+      // the tail GEMM of sub-tile sb of accumulator stage `acc`
+      auto tail_mmas = [&](int tacc, int sb) {
+        if constexpr (TN > 0) {
+          constexpr uint32_t wt_hi32 = (128u >> 4) | (1u << 14);
+          const uint32_t d2 = (uint32_t)((tacc * S + sb) * C::SUB_COLS);
+          // A operand of K step `step`, hi (lo = 0) or lo (lo = 1) parts.  Tensor-memory form: 8 columns per step
+          // (K = 16 bf16 pairs), lo parts K2/2 columns further.  Shared-memory form: a descriptor over
+          // [k8 group][128 rows][16 B] -- LBO (the step's second k8 group) 2048 B, SBO (8-row groups) 128 B.
+          const uint32_t a2_col = (uint32_t)(C::A2_COL0 + (C::A2_SHARED ? 0 : sb) * C::A2_COLS);
+          const uint32_t a2_desc = A2SMEM ? (smem_u32(a2_tiles + sb * C::A2_SUB) >> 4) | ((2048u >> 4) << 16) : 0u;
+          auto mma = [&](uint32_t d, int step, int lo, uint32_t w, uint32_t idesc, uint32_t accumulate) {
+            if constexpr (A2SMEM)
+              umma_issue<CG>(d, a2_desc + (uint32_t)((lo * (C::K2 / 8) * 2048 + step * 4096) >> 4), wt_hi32, w, wt_hi32, idesc,
+                             accumulate);
+            else
+              umma_issue_ts<CG>(d, a2_col + (uint32_t)(lo * (C::K2 / 2) + 8 * step), w, wt_hi32, idesc, accumulate);
+          };
+          if constexpr (C::TAIL_BLK) {
+            // block-diagonal tail (three refiners): block b = channels [K2/NBLK * b, ...) -> columns [TNB * b, ...),
+            // three bf16 passes per K = 16 step into the same columns
+            constexpr uint32_t idesc_b = make_idesc(128 * CG, C::TNB);
+            constexpr int SPB = C::K2 / 16 / NBLK;  // K = 16 steps per block
+            const uint32_t wt_lo32 = (smem_u32(wt_smem) >> 4) | ((uint32_t)(C::TNB * 8 >> 4) << 16);  // LBO: k8 halves
+#pragma unroll
+            for (int blk = 0; blk < NBLK; blk++)
+#pragma unroll
+              for (int j = 0; j < SPB; j++) {
+                const int step = blk * SPB + j;
+                const uint32_t w = wt_lo32 + (uint32_t)(step * (C::WT_TAP >> 4));
+                const uint32_t d = d2 + (uint32_t)(blk * C::TNB);
+                mma(d, step, 0, w, idesc_b, j == 0 ? 0u : 1u);                      // a_hi x w_hi
+                mma(d, step, 1, w, idesc_b, 1u);                                    // a_lo x w_hi
+                mma(d, step, 0, w + (uint32_t)(C::TNB * 16 >> 4), idesc_b, 1u);     // a_hi x w_lo
+              }
+          } else {
+            constexpr uint32_t idesc_t1 = make_idesc(128 * CG, 2 * TN);   // a_hi x [w_hi | w_lo]
+            constexpr uint32_t idesc_t2 = make_idesc(128 * CG, TN);       // a_lo x w_hi
+            const uint32_t wt_lo32 = (smem_u32(wt_smem) >> 4) | ((uint32_t)(TN * 24 >> 4) << 16);
+#pragma unroll
+            for (int j = 0; j < C::K2 / 16; j++) mma(d2, j, 0, wt_lo32 + (uint32_t)(j * (C::WT_TAP >> 4)), idesc_t1, j == 0 ? 0u : 1u);
+#pragma unroll
+            for (int j = 0; j < C::K2 / 16; j++)
+              mma(d2, j, 1, wt_lo32 + (uint32_t)(j * (C::WT_TAP >> 4)) + (uint32_t)TN, idesc_t2, 1u);
+          }
+        }
+      };
+      // stage_idx: index of the weight stage (of the NEXT tile's main loop) about to be issued; < 0 = flush
+      auto tail_step = [&](int stage_idx) {
         if constexpr (TN > 0) {
           if (pend_acc < 0) return;
-          // All sub-tiles of the tile go in ONE batch: a tcgen05.mma that takes A from tensor memory starts only
-          // after the MMAs in flight have drained (~1.5-1.8k cycles of idle tensor pipe per batch, ncu), so a tile
-          // pays that once, not once per sub-tile.  The decision is warp-uniform (lane 0 probes): the lanes must
-          // stay converged for the election below.
-          if (!force) {
-            int ready = 1;
-#pragma unroll
-            for (int sb = 0; sb < S; sb++) ready &= (int)mbar_try(&a2_full[sb], a2phase);
-            if (__shfl_sync(0xffffffffu, ready, 0) == 0) return;
-          }
-#pragma unroll
-          for (int sb = 0; sb < S; sb++) mbar_wait(&a2_full[sb], a2phase);
-          tc_fence_after();
-          if (elect_one_sync()) {
-#pragma unroll
-            for (int sb = 0; sb < S; sb++) {
-              constexpr uint32_t wt_hi32 = (128u >> 4) | (1u << 14);
-              const uint32_t d2 = (uint32_t)((pend_acc * S + sb) * C::SUB_COLS);
-              const uint32_t a2 = (uint32_t)(C::A2_COL0 + sb * C::A2_COLS);  // K = 16 bf16 = 8 columns per step
-              if constexpr (C::TAIL_BLK) {
-                // block-diagonal tail (three refiners): block b = channels [K2/NBLK * b, ...) -> columns [TNB * b, ...),
-                // three bf16 passes per K = 16 step into the same columns
-                constexpr uint32_t idesc_b = make_idesc(128 * CG, C::TNB);
-                constexpr int SPB = C::K2 / 16 / NBLK;  // K = 16 steps per block
-                const uint32_t wt_lo32 = (smem_u32(wt_smem) >> 4) | ((uint32_t)(C::TNB * 8 >> 4) << 16);  // LBO: k8 halves
-#pragma unroll
-                for (int blk = 0; blk < NBLK; blk++)
-#pragma unroll
-                  for (int j = 0; j < SPB; j++) {
-                    const int step = blk * SPB + j;
-                    const uint32_t w = wt_lo32 + (uint32_t)(step * (C::WT_TAP >> 4));
-                    const uint32_t d = d2 + (uint32_t)(blk * C::TNB);
-                    umma_issue_ts<CG>(d, a2 + (uint32_t)(8 * step), w, wt_hi32, idesc_b, j == 0 ? 0u : 1u);                     // a_hi x w_hi
-                    umma_issue_ts<CG>(d, a2 + (uint32_t)(C::K2 / 2 + 8 * step), w, wt_hi32, idesc_b, 1u);                       // a_lo x w_hi
-                    umma_issue_ts<CG>(d, a2 + (uint32_t)(8 * step), w + (uint32_t)(C::TNB * 16 >> 4), wt_hi32, idesc_b, 1u);    // a_hi x w_lo
-                  }
-              } else {
-                constexpr uint32_t idesc_t1 = make_idesc(128 * CG, 2 * TN);   // a_hi x [w_hi | w_lo]
-                constexpr uint32_t idesc_t2 = make_idesc(128 * CG, TN);       // a_lo x w_hi
-                const uint32_t wt_lo32 = (smem_u32(wt_smem) >> 4) | ((uint32_t)(TN * 24 >> 4) << 16);
-#pragma unroll
-                for (int j = 0; j < C::K2 / 16; j++)
-                  umma_issue_ts<CG>(d2, a2 + (uint32_t)(8 * j), wt_lo32 + (uint32_t)(j * (C::WT_TAP >> 4)), wt_hi32, idesc_t1,
-                                    j == 0 ? 0u : 1u);
-#pragma unroll
-                for (int j = 0; j < C::K2 / 16; j++)
-                  umma_issue_ts<CG>(d2, a2 + (uint32_t)(C::K2 / 2 + 8 * j), wt_lo32 + (uint32_t)(j * (C::WT_TAP >> 4)) + (uint32_t)TN,
-                                    wt_hi32, idesc_t2, 1u);
-              }
+          if constexpr (C::A2_SHARED) {
+            // one sub-tile at a time (they share the operand region): polled for at every stage, waited for from
+            // stage kTailForceAt on
+            const bool force = stage_idx < 0 || stage_idx >= kTailForceAt;
+            if (!force && __shfl_sync(0xffffffffu, (int)mbar_try(&a2_full[pend_sub], a2phase), 0) == 0) return;
+            mbar_wait(&a2_full[pend_sub], a2phase);
+            tc_fence_after();
+            if (elect_one_sync()) {
+              tail_mmas(pend_acc, pend_sub);
+              umma_done<CG>(&t2_sub[pend_sub]);
             }
-            umma_done<CG>(&t2_full[pend_acc]);
+            __syncwarp();
+            if (++pend_sub == S) { pend_sub = 0; pend_acc = -1; a2phase ^= 1; }
+          } else {
+            // All sub-tiles of the tile go in ONE batch.  The decision is warp-uniform (lane 0 probes): the lanes must
+            // stay converged for the election below.
+            const bool force = stage_idx < 0 || stage_idx >= kTailForceAt;
+            if (!force) {
+              int ready = 1;
+#pragma unroll
+              for (int sb = 0; sb < S; sb++) ready &= (int)mbar_try(&a2_full[sb], a2phase);
+              if (__shfl_sync(0xffffffffu, ready, 0) == 0) return;
+            }
+#pragma unroll
+            for (int sb = 0; sb < S; sb++) mbar_wait(&a2_full[sb], a2phase);
+            tc_fence_after();
+            if (elect_one_sync()) {
+#pragma unroll
+              for (int sb = 0; sb < S; sb++) tail_mmas(pend_acc, sb);
+              umma_done<CG>(&t2_full[pend_acc]);
+            }
+            __syncwarp();
+            pend_acc = -1;
+            a2phase ^= 1;
           }
-          __syncwarp();
-          pend_acc = -1;
-          a2phase ^= 1;
         }
       };
       if constexpr (TN > 0) {  // the tail weights of both CTAs are in place
@@ -793,7 +839,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
           const int blk = NBLK > 1 ? c / C::CPB : 0;
           const uint32_t d_base = d_tile + (uint32_t)(blk * C::BLK_COLS);
           for (int tg = 0; tg < C::NSTAGE_PER_CHUNK; tg++) {
-            tail_step(c * C::NSTAGE_PER_CHUNK + tg == kTailForceAt);
+            tail_step(c * C::NSTAGE_PER_CHUNK + tg);
+            if constexpr (TN > 0) {  // nothing of the previous tile may be left when this tile's main loop ends
+              if (c == C::NCHUNK - 1 && tg == C::NSTAGE_PER_CHUNK - 1)
+                while (pend_acc >= 0) tail_step(-1);
+            }
             if (!b_ready) mbar_wait(&b_full[bstage], bphase);
             if constexpr (CG == 2) mbar_wait(&b_full_peer[bstage], bphase);
             tc_fence_after();
@@ -850,7 +900,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
         if constexpr (TN > 0) pend_acc = acc;
         if (++acc == AS) { acc = 0; tphase ^= 1; }
       }
-      tail_step(true);  // the last tile's tail GEMM
+      while (pend_acc >= 0) tail_step(-1);  // the last tile's tail GEMM(s)
       }
     }
   } else if (warp < 8) {
@@ -858,6 +908,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
     // a warp may only touch TMEM lanes 32*(warp%4)..+31; the two groups take alternate sub-tiles
     int acc = 0;
     uint32_t tphase = 0;
+    uint32_t tile_phase = 0;   // fused tail, shared operand region: parity of the per-tile barriers t2_sub[]
     const int egroup = warp >> 2, quarter = warp & 3;
     const int row = quarter * 32 + lane;      // TMEM lane == pixel row of the sub-tile
     const int px = row & 7, py = row >> 3;
@@ -881,10 +932,18 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
         //         (K2/2 columns of hi parts, K2/2 of lo parts); then "sub-tile ready" to the issuer
         constexpr int GC = 32, NG = NBLK * NPAD / GC, STEP = S == 1 ? 2 : 1;
         static_assert(S <= 2 && !DUAL && (NBLK * NPAD) % GC == 0, "tail layer: tile shape (one accumulator per channel)");
+        static_assert(!C::A2_SHARED || S == 2, "shared operand region: one epilogue group per sub-tile");
 #pragma unroll 1
         for (int s = (S == 1 ? 0 : egroup); s < S; s += 2) {
           const uint32_t t_addr = tmem_base + lane_base + (uint32_t)((acc * S + s) * C::SUB_COLS);
-          const uint32_t a2_addr = tmem_base + lane_base + (uint32_t)(C::A2_COL0 + s * C::A2_COLS);
+          const uint32_t a2_addr = tmem_base + lane_base + (uint32_t)(C::A2_COL0 + (C::A2_SHARED ? 0 : s) * C::A2_COLS);
+          if constexpr (C::A2_SHARED) {
+            // the sub-tiles take turns on one operand region: wait until the tail GEMM of the previous user has
+            // read it -- sub-tile s - 1 of this tile, or (s == 0) the last sub-tile of the previous tile
+            if (s > 0) mbar_wait(&t2_sub[s - 1], tile_phase);
+            else if (pt != cid) mbar_wait(&t2_sub[S - 1], tile_phase ^ 1);
+            tc_fence_after();
+          }
           uint32_t vb[2][GC], wb[2][DUAL ? GC : 1];
           auto issue1 = [&](int ch0, uint32_t* v, uint32_t* w) {
 #pragma unroll
@@ -912,10 +971,22 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
                                     : __uint_as_float(vb[k & 1][j + 1]) + (DUAL ? __uint_as_float(wb[k & 1][DUAL ? j + 1 : 0]) : 0.f);
               split_bf16x2(fmaxf(a0 + s_bias[c0 + j], 0.f), fmaxf(a1 + s_bias[c0 + j + 1], 0.f), hi[j >> 1], lo[j >> 1]);
             }
-            tmem_st16(a2_addr + (uint32_t)(c0 >> 1), hi);
-            tmem_st16(a2_addr + (uint32_t)(C::K2 / 2 + (c0 >> 1)), lo);
+            if constexpr (A2SMEM) {
+              // [k8 group][row][16 B]: group g of this row holds channels 8g..8g+7 = four bf16 pairs
+              uint4* a2_hi = reinterpret_cast<uint4*>(a2_tiles + s * C::A2_SUB) + row;
+              uint4* a2_lo = a2_hi + (C::K2 / 8) * 128;
+#pragma unroll
+              for (int q = 0; q < GC / 8; q++) {
+                a2_hi[((c0 >> 3) + q) * 128] = make_uint4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
+                a2_lo[((c0 >> 3) + q) * 128] = make_uint4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
+              }
+            } else {
+              tmem_st16(a2_addr + (uint32_t)(c0 >> 1), hi);
+              tmem_st16(a2_addr + (uint32_t)(C::K2 / 2 + (c0 >> 1)), lo);
+            }
           }
-          tmem_st_wait();
+          if constexpr (A2SMEM) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> tensor core
+          else tmem_st_wait();
           // the tail GEMM reads the columns just written and overwrites the accumulator columns just read
           tc_fence_before();
           __syncwarp();
@@ -928,10 +999,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
           }
         }
         // pass 2: the tail layer's accumulators (CONCAT: [a x w_hi | a_hi x w_lo]) -> bias, ReLU -> planes in HBM
-        mbar_wait(&t2_full[acc], tphase);
+        if constexpr (C::A2_SHARED) mbar_wait(&t2_sub[S == 1 ? 0 : egroup], tile_phase);  // this group's sub-tile
+        else mbar_wait(&t2_full[acc], tphase);
         tc_fence_after();
         constexpr int NG2 = TN / GC;
-        static_assert(TEPI == kTailAct || !OUT8, "the tap-stacked tail stores raw sums");
+        static_assert(!TAPS || !OUT8, "the tap-stacked tail stores raw sums");
 #pragma unroll 1
         for (int s = (S == 1 ? 0 : egroup); s < S; s += 2) {
           const int gx = tx * C::TILE_W + s * kSubW + px;
@@ -956,7 +1028,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
               for (int j = 0; j < GC; j++) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
             }
             if (!inside) continue;
-            if constexpr (TEPI == kTailTaps) {
+            if constexpr (TAPS) {
               // group k = one 3x3 layer with 3 output channels, tap-stacked: 27 of its 32 columns are in use
               float* o = g.out_f32 + ((size_t)n * (NG2 * 27) + k * 27) * hw + pix;
 #pragma unroll
@@ -1198,6 +1270,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs g) 
         else mbar_arrive(&t_empty[acc]);
       }
       if (++acc == AS) { acc = 0; tphase ^= 1; }
+      tile_phase ^= 1;
     }
   }
 
@@ -1477,7 +1550,7 @@ template <int KS, int CIN_PAD, int NPAD, int S, int AS, int EPI, int CONCAT = 0,
           int FMT = 0, int TN = 0, int TEPI = 0, int KP = 0>
 static int launch_conv(wn_handle* h, int slot, const uint8_t* wpk, const float* bias, void* in_base, ConvArgs a,
                        cudaStream_t stream) {
-  using C = UmmaCfg<KS, CIN_PAD, NPAD, S, AS, CONCAT, NBLK, TPS, CG, FMT, TN, KP>;
+  using C = UmmaCfg<KS, CIN_PAD, NPAD, S, AS, CONCAT, NBLK, TPS, CG, FMT, TN, KP, (TEPI & kTailSmem) != 0>;
   int rc = get_encoder();
   if (rc) return rc;
   CUtensorMap tm;

@@ -62,8 +62,9 @@ def parse_args():
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--gather", choices=["peer", "nccl"], default="peer",
-                    help="N > 1: how the uint8 output is all-gathered (peer = copy-engine pushes over NVLink)")
+    ap.add_argument("--gather", choices=["fused", "peer", "nccl"], default="fused",
+                    help="N > 1: how the uint8 output is all-gathered (fused = NVLink stores from the kernel that "
+                         "writes the output; peer = copy-engine pushes per pass; nccl = NCCL all_gather per pass)")
     return ap.parse_args()
 
 
@@ -282,21 +283,29 @@ def main():
     dev_out = torch.empty_like(dev_in)
     nb = eng.chunk_images(B, H, W)
     gather = None
-    if world > 1:  # copy-engine pushes into peer memory (CUDA IPC); --gather nccl = all_gather per pass
+    if world > 1:  # peer memory over CUDA IPC (fused stores or copy-engine pushes); --gather nccl = all_gather per pass
         gather = (PassGather((B, H, W, 3), torch.uint8, device) if args.gather == "nccl"
                   else PeerGather.create((B, H, W, 3), torch.uint8, device))
+    fused = args.gather == "fused" and isinstance(gather, PeerGather)
     side = torch.cuda.Stream(device)
 
     push_done = {}
 
     def step_resident():
-        """One step with the batch resident in HBM: per pass, kernels on the compute stream and (N > 1) the
-        exchange of that pass's output on a side stream, under the next pass's kernels.  The compute stream never
-        waits for the exchange as such -- only, one step later, for the push that still reads the slice of `dev_out`
-        a pass is about to overwrite -- so the ranks are not lock-stepped by the per-step completion all-reduce."""
+        """One step with the batch resident in HBM.  N > 1, fused: the last kernel of every pass stores its output
+        into every rank's buffer; the completion signal follows the last pass on the compute stream, the wait for the
+        peers' signals sits on a side stream.  peer / nccl: the exchange of a pass's output on the side stream, under
+        the next pass's kernels.  The compute stream never waits for the exchange as such -- only, one step later, for
+        the previous step's completion (fused) or for the push that still reads the slice of `dev_out` a pass is about
+        to overwrite -- so the ranks are not lock-stepped."""
         cur = torch.cuda.current_stream(device)
+        if fused and "step" in push_done:
+            cur.wait_event(push_done["step"])  # peers have signalled the step before the previous one
         for a in range(0, B, nb):
             b = min(B, a + nb)
+            if fused:
+                eng.enhance(dev_in[a:b], mode=mode, out_u8=dev_out[a:b], peer_out=gather.addresses(a))
+                continue
             if gather is not None and a in push_done:
                 cur.wait_event(push_done[a])
             eng.enhance(dev_in[a:b], mode=mode, out_u8=dev_out[a:b])
@@ -309,13 +318,22 @@ def main():
                     done = torch.cuda.Event()
                     done.record(side)
                     push_done[a] = done
-        if gather is not None:
+        if fused:
+            gather.signal()
+            if "waited" in push_done:
+                push_done["step"] = push_done["waited"]
+            with torch.cuda.stream(side):
+                gather.wait()
+                done = torch.cuda.Event()
+                done.record(side)
+                push_done["waited"] = done
+        elif gather is not None:
             with torch.cuda.stream(side):
                 gather.finish()
 
     pins = [(torch.from_numpy(host).pin_memory(), torch.empty(host.shape, dtype=torch.uint8).pin_memory())
             for _ in range(2)]
-    on_pass = gather.on_pass if gather is not None else None
+    on_pass = gather.on_pass if gather is not None and not fused else None
 
     def barrier():
         if world > 1:
@@ -349,8 +367,8 @@ def main():
         cur = torch.cuda.current_stream(device)
         prev = None
         for i in range(steps):
-            ticket = enh.submit(*pins[i % 2], on_pass=on_pass)
-            if gather is not None:
+            ticket = enh.submit(*pins[i % 2], on_pass=on_pass, exchange=gather if fused else None)
+            if gather is not None and not fused:
                 with torch.cuda.stream(enh._s_out):
                     gather.finish()
             if prev is not None:
@@ -403,15 +421,20 @@ def main():
     # the collective's own cost: the same step without it, same box, right after
     nogather_ms = None
     if world > 1:
-        saved, gather = gather, None
+        saved, gather, fused = (gather, fused), None, False
         nogather_ms, _ = timed(run_resident, args.steps)
-        gather = saved
+        gather, fused = saved
 
     run_e2e(2)
     e2e_ms, e2e_per_rank = timed(run_e2e, args.steps)
-    if world > 1:  # what was gathered is what every rank computed: compare my block of rank 0's result with my own
-        mine = gather.gathered[rank]
-        same = torch.equal(mine, enh._slots[(enh._next - 1) % len(enh._slots)].dev_out)
+    if world > 1:  # what was gathered is what every rank computed: my own block bitwise, every rank's block by checksum
+        last_out = enh._slots[(enh._next - 1) % len(enh._slots)].dev_out
+        same = torch.equal(gather.gathered[rank], last_out)
+        own = torch.zeros(world, dtype=torch.int64, device=device)
+        own[rank] = last_out.view(-1).view(torch.int32).sum(dtype=torch.int64)
+        dist.all_reduce(own)                                   # own[r] = checksum of what rank r computed
+        got = torch.stack([gather.gathered[r].view(-1).view(torch.int32).sum(dtype=torch.int64) for r in range(world)])
+        same = same and torch.equal(own, got)
         flag = torch.tensor([1 if same else 0], device=device)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         gather_ok = bool(flag.item())
@@ -510,9 +533,12 @@ def main():
         config = workload_config(args, world)  # identical in both arms
         detail = {"mode": args.mode, "images_per_pass": nb,
                   "collective": ("none" if world == 1 else
-                                 "all-gather of the uint8 output per pass on a side stream: " +
-                                 ("copy-engine pushes into peer memory over NVLink (CUDA IPC) + one 1-element NCCL "
-                                  "all-reduce per step" if isinstance(gather, PeerGather) else "NCCL all_gather"))}
+                                 "all-gather of the uint8 output, pass by pass: " +
+                                 ("NVLink stores into every rank's buffer (CUDA IPC) from the kernel that writes the output"
+                                  if fused else "copy-engine pushes into peer memory over NVLink (CUDA IPC)"
+                                  if isinstance(gather, PeerGather) else "NCCL all_gather") +
+                                 ("; per step one flag word pushed to every peer and a stream wait-value on theirs "
+                                  "(no kernel)" if isinstance(gather, PeerGather) else ""))}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -547,6 +573,8 @@ def main():
             }
         print(json.dumps(line), flush=True)
     if world > 1:
+        if isinstance(gather, PeerGather):
+            gather.close()
         dist.destroy_process_group()
 
 

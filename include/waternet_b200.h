@@ -150,6 +150,21 @@ int wn_enhance_u8(wn_handle* h, const uint8_t* rgb, uint8_t* out_nhwc, float* ou
                   void* stream);
 
 /*
+ * wn_enhance_u8 with the all-gather of the output fused into the kernel that produces it (the one
+ * exchange of the sharded path): the launch that writes out_nhwc stores the same bytes to peer_out[0..n_peers) --
+ * addresses inside the other ranks' buffers, mapped with wn_peer_open (NVLink stores, 16 bytes each), each the
+ * start of where THIS batch belongs there and aligned like out_nhwc modulo 16.  In the default mode that launch is
+ * the HBM-bound gather/gate kernel at the end of every pass, so the exchange of a pass rides on a kernel that
+ * leaves the tensor cores and most of the power budget idle; the other modes (and the range guard's re-run)
+ * finish with a copy kernel.  Completion at the peers is the caller's business (wn_stream_write_value32 +
+ * wn_memcpy_async of the flag word + wn_stream_wait_value32, see below).
+ */
+#define WN_MAX_PEERS 15
+int wn_enhance_u8_peers(wn_handle* h, const uint8_t* rgb, uint8_t* out_nhwc, float* out_f32_or_null,
+                        uint8_t* const* peer_out, int n_peers, int n, int height, int width, int mode,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/*
  * Training step (reference train.py:100-133: out = model(...); loss.backward()).
  * wn_forward_train is wn_forward (tensor-core mode) that additionally keeps every activation in
  * `train_workspace`; wn_backward consumes that workspace and d(loss)/d(out) (fp32 contiguous NCHW)
@@ -221,6 +236,37 @@ int wn_set_chunk_pixels(wn_handle* h, long long max_pixels);
  * of the flag (0/1).
  */
 int wn_f8_overflowed(const wn_handle* h);
+
+/*
+ * Multi-GPU exchange without a kernel and without touching the peer device's contexts (the all-gather
+ * of the output batch, waternet_b200/dist.py PeerGather).  Two things a collective library does cost this path
+ * time, measured at N=2 (tools/probe_gather.py): (1) the convolution kernels are persistent and own every SM's shared
+ * memory, so a collective's kernel beside them takes an SM at a kernel boundary and stalls that SM's CTA pair while
+ * it waits for the peer; (2) work submitted to a context this process holds ON THE PEER GPU -- which is what a
+ * framework-level cross-device copy does to order itself against the destination's streams -- makes the peer GPU
+ * time-slice away from its owner process, ~0.4 ms per switch with these kernels resident.  Hence this plumbing;
+ * every call acts on the calling thread's current device, none launches a kernel:
+ *
+ *   wn_peer_alloc   cudaMalloc + zero fill + cudaIpcGetMemHandle: a buffer other ranks may map; handle_out
+ *                   receives WN_PEER_HANDLE_BYTES bytes to send to them (any transport).
+ *   wn_peer_open    cudaIpcOpenMemHandle in the CURRENT device's context (peer access enabled lazily): the
+ *                   returned pointer is valid for copies issued on this device's streams.  wn_peer_close unmaps.
+ *   wn_memcpy_async cudaMemcpyAsync(cudaMemcpyDefault): with a wn_peer_open'ed destination it is a copy-engine
+ *                   push over NVLink, ordered on `stream`, issued entirely from this device.
+ *   wn_stream_write_value32 / wn_stream_wait_value32
+ *                   the driver's stream memory operations (cuStreamWriteValue32 / cuStreamWaitValue32, executed by
+ *                   the stream's front end): store `value` to the 4-byte aligned device address when the stream
+ *                   reaches it / hold the stream until (int32)(*addr - value) >= 0.  A peer's copy engine may be
+ *                   the writer of a waited-on address.
+ */
+#define WN_PEER_HANDLE_BYTES 64
+int wn_peer_alloc(size_t bytes, void** ptr, unsigned char* handle_out);
+int wn_peer_open(const unsigned char* handle, void** ptr);
+int wn_peer_close(void* ptr);
+int wn_peer_free(void* ptr);
+int wn_memcpy_async(void* dst, const void* src, size_t bytes, void* stream);
+int wn_stream_write_value32(void* stream, void* addr, uint32_t value);
+int wn_stream_wait_value32(void* stream, void* addr, uint32_t value);
 
 #ifdef __cplusplus
 }

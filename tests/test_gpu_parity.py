@@ -702,6 +702,57 @@ def test_default_mode_margin_on_every_weight_set(weights):
     assert rel < 6e-4
 
 
+# ------------------------------------------------------------------ output stores fused with the exchange
+@pytest.mark.parametrize("precision", MODES)
+def test_peer_out_addresses_receive_the_bytes_of_the_output(precision):
+    """wn_enhance_u8_peers: every 'peer' address (here: other buffers of the same GPU, no IPC needed) ends up with
+    exactly the uint8 output, whichever launch writes it -- the gather/gate kernel (default mode: vector rows, ragged
+    rows, unaligned batches), the copy kernel behind the bf16x3 / fp32 chains -- and on multi-pass batches."""
+    m = _model(0, 3.0, precision)
+    eng = m.engine()
+    for (n, h, w), cap in (((3, 64, 96), 2 * 64 * 96), ((2, 33, 47), 0), ((1, 40, 64), 0)):
+        frames = torch.from_numpy(np.ascontiguousarray(
+            np.stack([ofw.synthetic_image(40 + i, h, w, "smooth") for i in range(n)]))).cuda()
+        want = eng.enhance(frames, mode=m._mode()).clone()
+        eng.set_chunk_pixels(cap)
+        try:
+            block = torch.zeros(3 * frames.numel() + 64, dtype=torch.uint8, device="cuda")
+            out = torch.zeros_like(frames)
+            k = out.data_ptr() % 16    # peers must be aligned like the output modulo 16
+            mirrors = [block[k + 16 + i * (frames.numel() + 16 - frames.numel() % 16):][:frames.numel()] for i in range(2)]
+            assert all(t.data_ptr() % 16 == k for t in mirrors)
+            eng.enhance(frames, mode=m._mode(), out_u8=out, peer_out=[t.data_ptr() for t in mirrors])
+            torch.cuda.synchronize()
+        finally:
+            eng.set_chunk_pixels(0)
+        assert torch.equal(out, want)
+        for t in mirrors:
+            assert torch.equal(t.view(frames.shape), want)
+    with pytest.raises(Exception):   # misaligned peer address
+        eng.enhance(frames, mode=m._mode(), out_u8=out, peer_out=[mirrors[0].data_ptr() + 1])
+    with pytest.raises(ValueError):  # an output tensor the kernels would fill in the wrong order
+        eng.enhance(frames, mode=m._mode(), out_u8=torch.empty((n, w, h, 3), dtype=torch.uint8, device="cuda").permute(0, 2, 1, 3))
+
+
+def test_peer_out_follows_the_range_guard_rerun():
+    from waternet_b200.net import WaterNet
+    m = WaterNet(precision="default")
+    m.load_state_dict(_scaled_refiner_sd(400.0), strict=True)
+    m = m.cuda().eval()
+    eng = m.engine()
+    frames = torch.from_numpy(np.ascontiguousarray(
+        np.stack([ofw.synthetic_image(5 + i, 40, 56, "smooth") for i in range(3)]))).cuda()
+    mirror = torch.zeros_like(frames)
+    out = eng.enhance(frames, mode=m._mode(), peer_out=[mirror.data_ptr()])   # trips the guard: re-run inside the call
+    torch.cuda.synchronize()
+    assert eng.f8_overflowed()
+    mb = WaterNet(precision="bf16x3")
+    mb.load_state_dict(_scaled_refiner_sd(400.0), strict=True)
+    mb = mb.cuda().eval()
+    want = mb.engine().enhance(frames, mode=mb._mode())
+    assert torch.equal(out, want) and torch.equal(mirror, want)
+
+
 # ------------------------------------------------------------------ 2 ranks on NCCL: sharded == single GPU, bitwise
 def _nccl_worker(rank, world, port, ret):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -735,7 +786,24 @@ def _nccl_worker(rank, world, port, ret):
             ok = ok and gather.calls == 2 and np.array_equal(gather.result().cpu().numpy(), full)
             ok = ok and np.array_equal(out.numpy(), full[rank * per:(rank + 1) * per])
             dist.barrier()
+            if isinstance(gather, PeerGather):
+                kept = gather
         ok = ok and isinstance(gather, PeerGather)   # on one NVSwitch node the IPC path must be available
+        if ok:  # third form: the exchange fused into the kernels that write the output (wn_enhance_u8_peers)
+            for precision, want in (("default", full), ("bf16x3", None)):
+                if want is None:
+                    want = Enhancer(m, precision=precision, cuda_graph=False)(frames)
+                kept.result().zero_()
+                torch.cuda.synchronize()
+                dist.barrier()
+                out = torch.empty_like(local).pin_memory()
+                Enhancer(m, precision=precision, cuda_graph=False).enhance_pinned(local, out, exchange=kept)
+                torch.cuda.synchronize()
+                dist.barrier()
+                ok = ok and np.array_equal(kept.result().cpu().numpy(), want)
+                ok = ok and np.array_equal(out.numpy(), want[rank * per:(rank + 1) * per])
+                dist.barrier()
+            kept.close()
         m.engine().set_chunk_pixels(0)
         ret[rank] = bool(ok)
     finally:

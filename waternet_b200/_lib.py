@@ -20,6 +20,8 @@ MODE_DEFAULT = -1
 NUM_PARAMS = 34
 NUM_TIMING_SLOTS = 23
 ABI_VERSION = 2
+PEER_HANDLE_BYTES = 64  # WN_PEER_HANDLE_BYTES
+MAX_PEERS = 15          # WN_MAX_PEERS
 
 # name -> (restype, argtypes); mirrors include/waternet_b200.h one to one
 _SIGNATURES = {
@@ -44,6 +46,8 @@ _SIGNATURES = {
     "wn_enhance_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "wn_enhance_u8": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                               c_void_p, c_size_t, c_void_p]),
+    "wn_enhance_u8_peers": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, POINTER(c_void_p), c_int, c_int, c_int, c_int,
+                                    c_int, c_void_p, c_size_t, c_void_p]),
     "wn_launch_count": (c_uint64, [c_void_p]),
     "wn_submodule_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "wn_confidence_maps": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, POINTER(c_int64), c_void_p,
@@ -53,6 +57,13 @@ _SIGNATURES = {
     "wn_forward_chunk_images": (c_int, [c_void_p, c_int, c_int, c_int]),
     "wn_set_chunk_pixels": (c_int, [c_void_p, ctypes.c_longlong]),
     "wn_f8_overflowed": (c_int, [c_void_p]),
+    "wn_peer_alloc": (c_int, [c_size_t, POINTER(c_void_p), c_void_p]),
+    "wn_peer_open": (c_int, [c_void_p, POINTER(c_void_p)]),
+    "wn_peer_close": (c_int, [c_void_p]),
+    "wn_peer_free": (c_int, [c_void_p]),
+    "wn_memcpy_async": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
+    "wn_stream_write_value32": (c_int, [c_void_p, c_void_p, ctypes.c_uint32]),
+    "wn_stream_wait_value32": (c_int, [c_void_p, c_void_p, ctypes.c_uint32]),
     "wn_debug_set_flags": (c_int, [c_void_p, c_int]),
     "wn_train_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "wn_forward_train": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, POINTER(c_int64), c_void_p,

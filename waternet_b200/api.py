@@ -80,12 +80,12 @@ class Enhancer:
         return out[0] if single else out
 
     # ---- kernels of one pass --------------------------------------------------------------------
-    def _run_kernels(self, eng: Engine, slot: _Slot, a: int, b: int, whole: bool) -> None:
+    def _run_kernels(self, eng: Engine, slot: _Slot, a: int, b: int, whole: bool, peer_out=()) -> None:
         """preprocess -> forward -> ten2arr of images [a, b) of the slot (graph replay when small)."""
         src, dst = slot.dev_in[a:b], slot.dev_out[a:b]
         shape = tuple(slot.dev_in.shape)
-        if not (self.cuda_graph and whole and shape[0] * shape[1] * shape[2] <= self.GRAPH_MAX_PIXELS):
-            eng.enhance(src, mode=self.mode, out_u8=dst)
+        if peer_out or not (self.cuda_graph and whole and shape[0] * shape[1] * shape[2] <= self.GRAPH_MAX_PIXELS):
+            eng.enhance(src, mode=self.mode, out_u8=dst, peer_out=peer_out)
             return
 
         def key():  # everything a captured launch sequence has baked in
@@ -105,13 +105,18 @@ class Enhancer:
 
     # ---- pipelined host-buffer path ---------------------------------------------------------------
     def submit(self, pin_in: torch.Tensor, pin_out: torch.Tensor,
-               on_pass: Optional[Callable[[torch.Tensor, int, int], None]] = None) -> _Slot:
+               on_pass: Optional[Callable[[torch.Tensor, int, int], None]] = None, exchange=None) -> _Slot:
         """Enqueue one batch: pinned uint8 NHWC host tensor -> pinned uint8 NHWC host tensor.
 
         The batch is processed in passes of ``engine.chunk_images`` images; pass k's H2D copy runs on the
         copy-in stream, its kernels on the current stream, and ``on_pass(dev_out[a:b], a, b)`` (e.g. the
         all-gather of that pass's output) followed by its D2H copy on the copy-out stream.  Returns a ticket
         for :meth:`wait`; neither ``pin_in`` nor ``pin_out`` may be touched before that.
+
+        ``exchange``: a :class:`waternet_b200.dist.PeerGather` -- the multi-GPU all-gather of the output fused into the
+        kernels: every pass's last launch stores its output into all ranks' buffers as well (``exchange.addresses``),
+        ``exchange.signal()`` follows the last pass on the compute stream and ``exchange.wait()`` the last D2H copy
+        on the copy-out stream.
         """
         if pin_in.dtype != torch.uint8 or pin_in.dim() != 4 or pin_in.shape[3] != 3 or pin_in.shape != pin_out.shape:
             raise ValueError(f"expected uint8 (N,H,W,3) pinned tensors of one shape, got {tuple(pin_in.shape)}")
@@ -142,7 +147,10 @@ class Enhancer:
                 ev_in = torch.cuda.Event()
                 ev_in.record(self._s_in)
             cur.wait_event(ev_in)
-            self._run_kernels(eng, slot, a, b, whole=(a == 0 and b == n))
+            self._run_kernels(eng, slot, a, b, whole=(a == 0 and b == n),
+                              peer_out=exchange.addresses(a) if exchange is not None else ())
+            if exchange is not None and b == n:
+                exchange.signal()
             ev_k = torch.cuda.Event()
             ev_k.record(cur)
             with torch.cuda.stream(self._s_out):
@@ -150,6 +158,8 @@ class Enhancer:
                 if on_pass is not None:
                     on_pass(slot.dev_out[a:b], a, b)
                 pin_out[a:b].copy_(slot.dev_out[a:b], non_blocking=True)
+                if exchange is not None and b == n:
+                    exchange.wait()
         slot.done = torch.cuda.Event()
         slot.done.record(self._s_out)
         return slot
@@ -158,7 +168,7 @@ class Enhancer:
         if ticket.done is not None:
             ticket.done.synchronize()
 
-    def enhance_pinned(self, pin_in: torch.Tensor, pin_out: torch.Tensor, on_pass=None) -> None:
+    def enhance_pinned(self, pin_in: torch.Tensor, pin_out: torch.Tensor, on_pass=None, exchange=None) -> None:
         """Pinned uint8 NHWC host tensor -> pinned uint8 NHWC host tensor; returns when ``pin_out`` is complete."""
-        self.wait(self.submit(pin_in, pin_out, on_pass=on_pass))
+        self.wait(self.submit(pin_in, pin_out, on_pass=on_pass, exchange=exchange))
         torch.cuda.current_stream(self.engine.device).wait_stream(self._s_out)

@@ -257,6 +257,26 @@ size_t wn_enhance_workspace_bytes(int n, int h, int w, int mode) {
 int wn_enhance_u8(wn_handle* h, const uint8_t* rgb, uint8_t* out_nhwc, float* out_f32_or_null,
                   int n, int height, int width, int mode, void* workspace, size_t workspace_bytes,
                   void* stream) {
+  return wn_enhance_u8_peers(h, rgb, out_nhwc, out_f32_or_null, nullptr, 0, n, height, width, mode, workspace,
+                             workspace_bytes, stream);
+}
+
+int wn_enhance_u8_peers(wn_handle* h, const uint8_t* rgb, uint8_t* out_nhwc, float* out_f32_or_null,
+                        uint8_t* const* peer_out, int n_peers, int n, int height, int width, int mode,
+                        void* workspace, size_t workspace_bytes, void* stream) {
+  PeerOut peers = {};
+  if (n_peers < 0 || n_peers > WN_MAX_PEERS || (n_peers > 0 && !peer_out)) {
+    set_error("wn_enhance_u8_peers: 0..%d peer addresses", WN_MAX_PEERS);
+    return WN_E_INVALID;
+  }
+  for (int k = 0; k < n_peers; k++) {
+    if (!peer_out[k] || (((uintptr_t)peer_out[k] ^ (uintptr_t)out_nhwc) & 15)) {
+      set_error("wn_enhance_u8_peers: peer address %d is null or not aligned like out_nhwc (mod 16)", k);
+      return WN_E_INVALID;
+    }
+    peers.p[k] = peer_out[k];
+  }
+  peers.n = n_peers;
   if (!h || !rgb || !out_nhwc || !workspace) {
     set_error("wn_enhance_u8: null argument");
     return WN_E_INVALID;
@@ -280,7 +300,7 @@ int wn_enhance_u8(wn_handle* h, const uint8_t* rgb, uint8_t* out_nhwc, float* ou
   DeviceGuard guard(h->device);
   if (resolve_mode(mode) != WN_MODE_FP32_SIMT)  // tensor-core modes: folded path, nothing fp32 is materialised
     return umma_enhance_u8(h, rgb, out_nhwc, out_f32_or_null, n, height, width, workspace, workspace_bytes,
-                           (cudaStream_t)stream, resolve_mode(mode) == WN_MODE_BF16_FP8 ? 1 : 0);
+                           (cudaStream_t)stream, resolve_mode(mode) == WN_MODE_BF16_FP8 ? 1 : 0, peers);
   uint8_t* ws = (uint8_t*)(((uintptr_t)workspace + 255) / 256 * 256);
   const size_t tens = align256((size_t)n * 3 * height * width * sizeof(float));
   float* t[5];
@@ -302,7 +322,9 @@ int wn_enhance_u8(wn_handle* h, const uint8_t* rgb, uint8_t* out_nhwc, float* ou
   float* outf = out_f32_or_null ? out_f32_or_null : t[4];
   rc = wn_forward(h, t[0], t[1], t[2], t[3], st, outf, n, height, width, mode, fwd_ws, fwd_b, stream);
   if (rc) return rc;
-  return wn_postprocess_u8(h, outf, out_nhwc, n, height, width, stream);
+  rc = wn_postprocess_u8(h, outf, out_nhwc, n, height, width, stream);
+  if (rc) return rc;
+  return mirror_u8(h, out_nhwc, peers, (size_t)n * height * width * 3, nullptr, (cudaStream_t)stream);
 }
 
 // ---- the reference's callable sub-modules (net.py:45-56 ConfidenceMapGenerator.forward, :75-80 Refiner.forward)

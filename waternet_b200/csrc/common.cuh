@@ -178,6 +178,12 @@ struct FwdBuffers {
   float* refined; // optional: refined images after ReLU, fp32 [n][9][H][W]
   int* exact_flag;
 };
+// Peer copies of the uint8 output (multi-GPU all-gather fused into the kernel that produces the output: plain stores
+// to addresses mapped from the other ranks' buffers, wn_enhance_u8_peers)
+struct PeerOut {
+  uint8_t* p[WN_MAX_PEERS];
+  int n;
+};
 struct FwdOpts {
   int scheme = 0;              // 1 = fp8 correction passes (WN_MODE_BF16_FP8)
   int dbg_layer = -1;          // wn_debug_forward_layer: stop after this layer and decode it into dbg_dst
@@ -187,6 +193,7 @@ struct FwdOpts {
   bool kpack = false;          // act0 is in the K-packed first-layer layout (inference; UmmaCfg KP)
   const int* run_if = nullptr; // every launch is conditional on *run_if != 0 (ConvArgs::run_if)
   uint8_t* out_u8 = nullptr;   // the last launch also writes ten2arr(out) as uint8 NHWC
+  PeerOut peers = {};          // ... and the same bytes to every peer address (offsets as out_u8)
   int stack = kStackAll;       // kStackCmg: stop after the confidence maps; kStackRefiners: refiners only
 };
 int umma_forward_layers(wn_handle* h, const float* const in[4], const int64_t st[4][4], float* out, int n,
@@ -205,8 +212,10 @@ int umma_forward(wn_handle* h, const float* const in[4], const int64_t in_stride
                  int n, int height, int width, void* workspace, size_t workspace_bytes,
                  cudaStream_t stream, int scheme = 0, int stack = kStackAll, float* refined = nullptr);
 size_t umma_enhance_workspace_bytes(int n, int h, int w);
+int mirror_u8(wn_handle* h, const uint8_t* src, const PeerOut& peers, size_t bytes, const int* run_if, cudaStream_t stream);
 int umma_enhance_u8(wn_handle* h, const uint8_t* rgb, uint8_t* out_u8, float* out_f32, int n, int height,
-                    int width, void* workspace, size_t workspace_bytes, cudaStream_t stream, int scheme);
+                    int width, void* workspace, size_t workspace_bytes, cudaStream_t stream, int scheme,
+                    const PeerOut& peers = PeerOut());
 int umma_f8_overflowed(const wn_handle* h);
 
 // conv_bwd.cu

@@ -156,52 +156,111 @@ static __global__ void scatter_tapstack_kernel(const float* __restrict__ src, fl
 // HBM-bound: 324 B/px of partial sums read exactly once, 12 B/px of maps, 3..48 B/px written.
 static __global__ void __launch_bounds__(256)
 gather_gate_kernel(const float* __restrict__ taps, const float* __restrict__ bias, const float* __restrict__ cm,
-                   float* __restrict__ out_f32, uint8_t* __restrict__ out_u8, float* __restrict__ refined_out, int H, int W) {
+                   float* __restrict__ out_f32, uint8_t* __restrict__ out_u8, float* __restrict__ refined_out, int H, int W,
+                   PeerOut peers) {
   const int x = blockIdx.x * 64 + threadIdx.x, y = blockIdx.y * 4 + threadIdx.y, n = blockIdx.z;
-  if (x >= W || y >= H) return;
+  if (y >= H) return;  // warp-uniform (a warp is 32 consecutive x of one row)
+  const bool inside = x < W;
   const size_t hw = (size_t)H * W, pix = (size_t)y * W + x;
-  const float* t = taps + (size_t)n * 81 * hw;
-  float r[9];
+  uint32_t rgb = 0;  // this pixel's three output bytes
+  if (inside) {
+    const float* t = taps + (size_t)n * 81 * hw;
+    float r[9];
 #pragma unroll
-  for (int j = 0; j < 9; j++) r[j] = bias[j];
+    for (int j = 0; j < 9; j++) r[j] = bias[j];
 #pragma unroll
-  for (int ky = 0; ky < 3; ky++) {
-    const int yy = y + ky - 1;
-    if (yy < 0 || yy >= H) continue;
+    for (int ky = 0; ky < 3; ky++) {
+      const int yy = y + ky - 1;
+      if (yy < 0 || yy >= H) continue;
 #pragma unroll
-    for (int kx = 0; kx < 3; kx++) {
-      const int xx = x + kx - 1;
-      if (xx < 0 || xx >= W) continue;
-      const float* p = t + (size_t)((ky * 3 + kx) * 3) * hw + (size_t)yy * W + xx;
+      for (int kx = 0; kx < 3; kx++) {
+        const int xx = x + kx - 1;
+        if (xx < 0 || xx >= W) continue;
+        const float* p = t + (size_t)((ky * 3 + kx) * 3) * hw + (size_t)yy * W + xx;
 #pragma unroll
-      for (int rr = 0; rr < 3; rr++)
+        for (int rr = 0; rr < 3; rr++)
 #pragma unroll
-        for (int c = 0; c < 3; c++) r[3 * rr + c] += p[(size_t)(27 * rr + c) * hw];
+          for (int c = 0; c < 3; c++) r[3 * rr + c] += p[(size_t)(27 * rr + c) * hw];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 9; j++) r[j] = fmaxf(r[j], 0.f);
+    if (refined_out) {
+#pragma unroll
+      for (int j = 0; j < 9; j++) refined_out[((size_t)n * 9 + j) * hw + pix] = r[j];
+    }
+    if (cm) {
+      const size_t o = (size_t)n * 3 * hw + pix;
+      const float c0 = cm[o], c1 = cm[o + hw], c2 = cm[o + 2 * hw];
+      float v[3];
+#pragma unroll
+      for (int c = 0; c < 3; c++)
+        v[c] = __fadd_rn(__fadd_rn(__fmul_rn(r[c], c0), __fmul_rn(r[3 + c], c1)), __fmul_rn(r[6 + c], c2));
+      if (out_f32) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) out_f32[o + c * hw] = v[c];
+      }
+#pragma unroll
+      for (int c = 0; c < 3; c++)  // ten2arr (hubconf.py:24-34)
+        rgb |= (uint32_t)(int)__fmul_rn(fminf(fmaxf(v[c], 0.0f), 1.0f), 255.0f) << (8 * c);
     }
   }
+  if (!cm || !out_u8) return;
+  // uint8 NHWC: the warp's 32 pixels are 96 contiguous bytes.  Lane l < 24 assembles 32-bit word l of them from its
+  // neighbours' bytes, so a full segment leaves as one coalesced 96-byte store per destination -- out_u8 and the same
+  // offset of every peer address (the all-gather of the output fused here; NVLink wants whole sectors, not bytes)
+  const int lane = threadIdx.x & 31;
+  uint32_t word = 0;
 #pragma unroll
-  for (int j = 0; j < 9; j++) r[j] = fmaxf(r[j], 0.f);
-  if (refined_out) {
-#pragma unroll
-    for (int j = 0; j < 9; j++) refined_out[((size_t)n * 9 + j) * hw + pix] = r[j];
+  for (int j = 0; j < 4; j++) {
+    const int k = 4 * lane + j;  // byte k of the segment = component k % 3 of pixel k / 3 (lanes >= 24: unused)
+    word |= ((__shfl_sync(0xffffffffu, rgb, (k / 3) & 31) >> (8 * (k % 3))) & 0xffu) << (8 * j);
   }
-  if (cm) {
-    const size_t o = (size_t)n * 3 * hw + pix;
-    const float c0 = cm[o], c1 = cm[o + hw], c2 = cm[o + 2 * hw];
-    float v[3];
+  const int xw = x - lane;  // the warp's first pixel
+  const size_t off = ((size_t)n * hw + (size_t)y * W + xw) * 3;
+  if (xw + 32 <= W && (reinterpret_cast<uintptr_t>(out_u8 + off) & 3) == 0) {  // peers: aligned like out_u8 (host check)
+    if (lane < 24) {
+      reinterpret_cast<uint32_t*>(out_u8 + off)[lane] = word;
 #pragma unroll
-    for (int c = 0; c < 3; c++)
-      v[c] = __fadd_rn(__fadd_rn(__fmul_rn(r[c], c0), __fmul_rn(r[3 + c], c1)), __fmul_rn(r[6 + c], c2));
-    if (out_f32) {
-#pragma unroll
-      for (int c = 0; c < 3; c++) out_f32[o + c * hw] = v[c];
+      for (int i = 0; i < WN_MAX_PEERS; i++)  // unrolled: the addresses stay kernel parameters (no local copy)
+        if (i < peers.n) reinterpret_cast<uint32_t*>(peers.p[i] + off)[lane] = word;
     }
-    if (out_u8) {  // ten2arr (hubconf.py:24-34)
-      uint8_t* q = out_u8 + ((size_t)n * hw + pix) * 3;
+  } else if (inside) {
+    const size_t o = off + 3 * lane;
 #pragma unroll
-      for (int c = 0; c < 3; c++) q[c] = (uint8_t)(int)__fmul_rn(fminf(fmaxf(v[c], 0.0f), 1.0f), 255.0f);
+    for (int c = 0; c < 3; c++) {
+      const uint8_t q = (uint8_t)(rgb >> (8 * c));
+      out_u8[o + c] = q;
+#pragma unroll
+      for (int i = 0; i < WN_MAX_PEERS; i++)
+        if (i < peers.n) peers.p[i][o + c] = q;
     }
   }
+}
+// out -> every peer address (the paths whose uint8 output leaves a convolution epilogue: bf16x3 mode, the range guard's
+// re-run -- then conditional on *run_if like every launch of that chain -- and the A/B switches)
+static __global__ void __launch_bounds__(256)
+mirror_u8_kernel(const uint8_t* __restrict__ src, PeerOut peers, size_t bytes, const int* __restrict__ run_if) {
+  if (run_if && *run_if == 0) return;
+  const size_t stride = (size_t)gridDim.x * blockDim.x, i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t vecs = ((reinterpret_cast<uintptr_t>(src) & 15) == 0) ? bytes / 16 : 0;  // peers: same alignment (host check)
+  for (size_t i = i0; i < vecs; i += stride) {
+    const uint4 q = reinterpret_cast<const uint4*>(src)[i];
+#pragma unroll
+    for (int k = 0; k < WN_MAX_PEERS; k++)
+      if (k < peers.n) reinterpret_cast<uint4*>(peers.p[k])[i] = q;
+  }
+  for (size_t i = vecs * 16 + i0; i < bytes; i += stride) {
+#pragma unroll
+    for (int k = 0; k < WN_MAX_PEERS; k++)
+      if (k < peers.n) peers.p[k][i] = src[i];
+  }
+}
+int mirror_u8(wn_handle* h, const uint8_t* src, const PeerOut& peers, size_t bytes, const int* run_if, cudaStream_t stream) {
+  if (peers.n <= 0 || bytes == 0) return WN_OK;
+  mirror_u8_kernel<<<592, 256, 0, stream>>>(src, peers, bytes, run_if);
+  WN_LAUNCH_CHECK(h);
+  return WN_OK;
 }
 // cm[n][c][y][x] = sigmoid(bias[c] + sum over the 3x3 taps of taps[n][3 * tap + c][y + ky - 1][x + kx - 1]), zero outside
 // the image ("same" padding): the second half of the tap-stacked cmg.conv8 (net.py:40-43, 54).  HBM-bound: 108 B/px
@@ -663,7 +722,8 @@ int umma_forward_layers(wn_handle* h, const float* const in[4], const int64_t st
       a.wtail = nullptr;
       TimedScope ts(h, spec_slot(kR3), stream);
       gather_gate_kernel<<<dim3((W + 63) / 64, (H + 3) / 4, n), dim3(64, 4), 0, stream>>>(
-          taps, h->umma->bias[kR3], o.stack == kStackRefiners ? nullptr : b.cm, out, o.out_u8, b.refined, H, W);
+          taps, h->umma->bias[kR3], o.stack == kStackRefiners ? nullptr : b.cm, out, o.out_u8, b.refined, H, W,
+          o.out_u8 ? o.peers : PeerOut());
       WN_LAUNCH_CHECK(h);
       return WN_OK;
     }
@@ -672,7 +732,7 @@ int umma_forward_layers(wn_handle* h, const float* const in[4], const int64_t st
     if (dump(9, b.r[2], 96)) return WN_OK;
     last();
     if ((rc = launch_umma<3, 96, 16, 4, 2, kEpiGate, 1, 1, 9>(h, kR3, b.r[2], a, stream))) return rc;
-    return WN_OK;
+    return o.out_u8 ? mirror_u8(h, o.out_u8, o.peers, (size_t)n * H * W * 3, o.run_if, stream) : WN_OK;
   }
   // L1: 16 -> 128 (cmg) + 96 (refiners)
   act(b.a[1], 128, b.r[1], 96);
@@ -713,7 +773,7 @@ int umma_forward_layers(wn_handle* h, const float* const in[4], const int64_t st
   if (dump(9, b.r[2], 96)) return WN_OK;
   last();
   if ((rc = launch_umma<3, 96, 16, 4, 2, kEpiGate, 1, 1, 9>(h, kR3, b.r[2], a, stream))) return rc;
-  return WN_OK;
+  return o.out_u8 ? mirror_u8(h, o.out_u8, o.peers, (size_t)n * H * W * 3, o.run_if, stream) : WN_OK;
 }
 
 // Workspace carve-up of one pass (<= umma_chunk images).
@@ -823,7 +883,7 @@ size_t umma_enhance_workspace_bytes(int n, int h, int w) {
 }
 
 int umma_enhance_u8(wn_handle* h, const uint8_t* rgb, uint8_t* out_u8, float* out_f32, int n, int H, int W,
-                    void* workspace, size_t workspace_bytes, cudaStream_t stream, int scheme) {
+                    void* workspace, size_t workspace_bytes, cudaStream_t stream, int scheme, const PeerOut& peers) {
   if (!h->umma) {
     set_error("tensor-core weights have not been packed");
     return WN_E_STATE;
@@ -854,6 +914,8 @@ int umma_enhance_u8(wn_handle* h, const uint8_t* rgb, uint8_t* out_u8, float* ou
     o.hi_only = true;
     o.kpack = kpack;
     o.out_u8 = out_u8 + (size_t)n0 * H * W * 3;
+    o.peers.n = peers.n;
+    for (int k = 0; k < peers.n; k++) o.peers.p[k] = peers.p[k] + (size_t)n0 * H * W * 3;
     rc = umma_pass(h, no_in, none, out_f32 ? out_f32 + (size_t)n0 * 3 * H * W : nullptr, cur, H, W, b, stream, o);
     if (rc) return rc;
   }

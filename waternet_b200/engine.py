@@ -352,20 +352,31 @@ class Engine:
         return res
 
     def enhance(self, rgb_u8: torch.Tensor, mode: int = _lib.MODE_DEFAULT, out_u8: Optional[torch.Tensor] = None,
-                out_f32: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """preprocess -> forward -> postprocess on uint8 (N,H,W,3) CUDA input; returns uint8 NHWC."""
+                out_f32: Optional[torch.Tensor] = None, peer_out=()) -> torch.Tensor:
+        """preprocess -> forward -> postprocess on uint8 (N,H,W,3) CUDA input; returns uint8 NHWC.
+
+        ``peer_out``: device addresses (ints) inside other ranks' buffers (``dist.PeerGather.peer_addresses``) that
+        receive the same bytes as ``out_u8`` from the kernel that writes it (wn_enhance_u8_peers)."""
         if rgb_u8.dtype != torch.uint8 or rgb_u8.dim() != 4 or rgb_u8.shape[3] != 3:
             raise ValueError(f"expected uint8 (N,H,W,3), got {rgb_u8.dtype} {tuple(rgb_u8.shape)}")
         rgb_u8 = rgb_u8.to(self.device).contiguous()
         n, h, w, _ = rgb_u8.shape
         if out_u8 is None:
             out_u8 = torch.empty((n, h, w, 3), dtype=torch.uint8, device=self.device)
+        elif (out_u8.dtype != torch.uint8 or tuple(out_u8.shape) != (n, h, w, 3) or not out_u8.is_contiguous()
+              or out_u8.device != rgb_u8.device):
+            raise ValueError(f"out_u8 must be a contiguous uint8 {(n, h, w, 3)} tensor on {rgb_u8.device}, got "
+                             f"{out_u8.dtype} {tuple(out_u8.shape)} strides {out_u8.stride()} on {out_u8.device}")
+        if out_f32 is not None and (out_f32.dtype != torch.float32 or tuple(out_f32.shape) != (n, 3, h, w)
+                                    or not out_f32.is_contiguous() or out_f32.device != rgb_u8.device):
+            raise ValueError(f"out_f32 must be a contiguous float32 {(n, 3, h, w)} tensor on {rgb_u8.device}")
         if out_u8.numel() == 0:
             return out_u8
         ws = self._workspace("enhance", self.lib.wn_enhance_workspace_bytes(n, h, w, mode))
+        peers = (ctypes.c_void_p * max(1, len(peer_out)))(*peer_out)
         with torch.cuda.device(self.device):
-            rc = self.lib.wn_enhance_u8(self.handle, rgb_u8.data_ptr(), out_u8.data_ptr(),
-                                        None if out_f32 is None else out_f32.data_ptr(), n, h, w, mode,
-                                        ws.data_ptr(), ws.numel(), _stream_ptr(self.device))
-        _lib.check(rc, "wn_enhance_u8")
+            rc = self.lib.wn_enhance_u8_peers(self.handle, rgb_u8.data_ptr(), out_u8.data_ptr(),
+                                              None if out_f32 is None else out_f32.data_ptr(), peers, len(peer_out),
+                                              n, h, w, mode, ws.data_ptr(), ws.numel(), _stream_ptr(self.device))
+        _lib.check(rc, "wn_enhance_u8_peers")
         return out_u8

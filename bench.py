@@ -286,7 +286,7 @@ def main():
     if world > 1:  # peer memory over CUDA IPC (fused stores or copy-engine pushes); --gather nccl = all_gather per pass
         gather = (PassGather((B, H, W, 3), torch.uint8, device) if args.gather == "nccl"
                   else PeerGather.create((B, H, W, 3), torch.uint8, device))
-    fused = args.gather == "fused" and isinstance(gather, PeerGather)
+    fused_gather = args.gather == "fused" and isinstance(gather, PeerGather)
     side = torch.cuda.Stream(device)
 
     push_done = {}
@@ -299,11 +299,11 @@ def main():
         the previous step's completion (fused) or for the push that still reads the slice of `dev_out` a pass is about
         to overwrite -- so the ranks are not lock-stepped."""
         cur = torch.cuda.current_stream(device)
-        if fused and "step" in push_done:
+        if fused_gather and "step" in push_done:
             cur.wait_event(push_done["step"])  # peers have signalled the step before the previous one
         for a in range(0, B, nb):
             b = min(B, a + nb)
-            if fused:
+            if fused_gather:
                 eng.enhance(dev_in[a:b], mode=mode, out_u8=dev_out[a:b], peer_out=gather.addresses(a))
                 continue
             if gather is not None and a in push_done:
@@ -318,7 +318,7 @@ def main():
                     done = torch.cuda.Event()
                     done.record(side)
                     push_done[a] = done
-        if fused:
+        if fused_gather:
             gather.signal()
             if "waited" in push_done:
                 push_done["step"] = push_done["waited"]
@@ -333,7 +333,7 @@ def main():
 
     pins = [(torch.from_numpy(host).pin_memory(), torch.empty(host.shape, dtype=torch.uint8).pin_memory())
             for _ in range(2)]
-    on_pass = gather.on_pass if gather is not None and not fused else None
+    on_pass = gather.on_pass if gather is not None and not fused_gather else None
 
     def barrier():
         if world > 1:
@@ -367,8 +367,8 @@ def main():
         cur = torch.cuda.current_stream(device)
         prev = None
         for i in range(steps):
-            ticket = enh.submit(*pins[i % 2], on_pass=on_pass, exchange=gather if fused else None)
-            if gather is not None and not fused:
+            ticket = enh.submit(*pins[i % 2], on_pass=on_pass, exchange=gather if fused_gather else None)
+            if gather is not None and not fused_gather:
                 with torch.cuda.stream(enh._s_out):
                     gather.finish()
             if prev is not None:
@@ -421,9 +421,9 @@ def main():
     # the collective's own cost: the same step without it, same box, right after
     nogather_ms = None
     if world > 1:
-        saved, gather, fused = (gather, fused), None, False
+        saved, gather, fused_gather = (gather, fused_gather), None, False
         nogather_ms, _ = timed(run_resident, args.steps)
-        gather, fused = saved
+        gather, fused_gather = saved
 
     run_e2e(2)
     e2e_ms, e2e_per_rank = timed(run_e2e, args.steps)
@@ -535,7 +535,7 @@ def main():
                   "collective": ("none" if world == 1 else
                                  "all-gather of the uint8 output, pass by pass: " +
                                  ("NVLink stores into every rank's buffer (CUDA IPC) from the kernel that writes the output"
-                                  if fused else "copy-engine pushes into peer memory over NVLink (CUDA IPC)"
+                                  if fused_gather else "copy-engine pushes into peer memory over NVLink (CUDA IPC)"
                                   if isinstance(gather, PeerGather) else "NCCL all_gather") +
                                  ("; per step one flag word pushed to every peer and a stream wait-value on theirs "
                                   "(no kernel)" if isinstance(gather, PeerGather) else ""))}

@@ -228,6 +228,35 @@ def run_reference_arm(args):
               f"so images/s does not depend on the batch), "
               + ("unmodified reference: waternet.data.transform (numpy+cv2) + WaterNet.forward (torch CPU fp32)"
                  if ref.kind == "reference" else f"oracle port ({ref.note})"))
+    # how the reference itself would run on this box (inference.py:85,185-191: preprocess on the host, model and
+    # tensors on CUDA when available -- torch/cuDNN kernels, TF32 convolutions by default): reported beside the CPU
+    # arm, not instead of it; nothing of this repository is on that path either
+    on_gpu = None
+    if ref.kind == "reference" and torch.cuda.is_available():
+        try:
+            dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+            model = ref.model.to(dev)
+            pre_s = fwd_s = 0.0
+            for i in range(3):  # first pass = warm-up (cuDNN algorithm selection)
+                t0 = time.perf_counter()
+                wb, gc, he = ref.transform(frames[0])
+                ins = [ref.arr2ten(a).to(dev) for a in (frames[0], wb, he, gc)]
+                torch.cuda.synchronize(dev)
+                t1 = time.perf_counter()
+                with torch.no_grad():
+                    out = model(*ins)
+                arr = ref.ten2arr(out)
+                t2 = time.perf_counter()
+                if i:
+                    pre_s += (t1 - t0) / 2
+                    fwd_s += (t2 - t1) / 2
+            on_gpu = {"value": 1.0 / (pre_s + fwd_s), "unit": UNIT, "preprocess_ms_per_image": pre_s * 1e3,
+                      "forward_and_postprocess_ms_per_image": fwd_s * 1e3,
+                      "note": "unmodified reference, model.to(cuda) as inference.py does: transform on the host cores, "
+                              "forward by torch/cuDNN on one GPU (allow_tf32 default), ten2arr on the host"}
+            ref.model.to("cpu")
+        except Exception as e:  # informational only
+            on_gpu = {"unavailable": str(e)[:200]}
     config = workload_config(args, world)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
@@ -238,6 +267,7 @@ def run_reference_arm(args):
                          "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "reference_with_cuda_forward": on_gpu,
     }
     print(json.dumps(line), flush=True)
 

@@ -341,6 +341,33 @@ def test_native_backward_matches_fp64_autograd(shape):
     print(f"worst relative gradient error {worst:.2e}")
 
 
+def test_training_forward_runs_a_large_batch_as_slices(monkeypatch):
+    """A grad-enabled call beyond wn_forward_train's pixel limit (the reference's hub example calls the model
+    without no_grad) runs as several calls over slices of the batch: same output, same gradients (parameter
+    gradients added slice by slice), for parameters and input images."""
+    from waternet_b200.engine import Engine
+    n, h, w = 5, 24, 40
+    ins = [t.cuda() for t in _inputs_from_rgb([ofw.synthetic_image(70 + i, h, w, "smooth") for i in range(n)])]
+    target = torch.rand(n, 3, h, w, generator=torch.Generator().manual_seed(4)).cuda()
+
+    def run():
+        m = _model(5, 3.0, "default").train()
+        cu = [t.clone().requires_grad_(i == 1) for i, t in enumerate(ins)]
+        out = m(*cu)
+        torch.nn.functional.mse_loss(out, target).backward()
+        return out.detach(), [p.grad.clone() for p in m.parameters()], cu[1].grad.clone()
+
+    out1, g1, gi1 = run()
+    monkeypatch.setattr(Engine, "TRAIN_MAX_PIXELS", 2 * h * w)   # 5 images -> slices of 2, 2, 1
+    out2, g2, gi2 = run()
+    assert torch.equal(out1, out2) and torch.equal(gi1, gi2)     # per-image quantities: bitwise
+    for a, b in zip(g1, g2):                                      # sums over the batch: another order of additions
+        assert ((a - b).norm() / a.norm().clamp_min(1e-30)).item() < 1e-5
+    monkeypatch.setattr(Engine, "TRAIN_MAX_PIXELS", h * w - 1)
+    with pytest.raises(Exception):
+        run()
+
+
 def _input_grad_case(sd, needs, n=2, h=29, w=43):
     from waternet_b200.net import WaterNet
     m = WaterNet(precision="default")

@@ -223,41 +223,58 @@ class Engine:
     TRAIN_MAX_PIXELS = 8 << 20
 
     def forward_train(self, x, wb, he, gc):
-        """Tensor-core forward that keeps every activation.  Returns (out, saved-workspace tensor)."""
+        """Tensor-core forward that keeps every activation.  Returns (out, saved workspaces).
+
+        wn_forward_train takes at most TRAIN_MAX_PIXELS per call; a larger batch runs as several calls over slices
+        of the batch, each with its own workspace (~5.6 KB per pixel in total, like the reference's autograd graph)."""
         ins = self._check_inputs((x, wb, he, gc))
         n, _, h, w = ins[0].shape
         out = torch.empty((n, 3, h, w), dtype=torch.float32, device=self.device)
         if out.numel() == 0:
             return out, None
-        if n * h * w > self.TRAIN_MAX_PIXELS:
+        if h * w > self.TRAIN_MAX_PIXELS:
             raise _lib.WaterNetLibraryError(
-                f"a forward pass that keeps its activations for autograd holds ~5.6 KB per pixel: {n}x{h}x{w} exceeds "
-                f"the {self.TRAIN_MAX_PIXELS >> 20} Mi-pixel limit of wn_forward_train.  For inference wrap the call "
-                "in torch.no_grad() (the reference's autograd path would need the same memory)")
-        strides = (ctypes.c_int64 * 16)(*[s for t in ins for s in t.stride()])
-        ws = torch.empty(self.lib.wn_train_workspace_bytes(n, h, w), dtype=torch.uint8, device=self.device)
-        with torch.cuda.device(self.device):
-            rc = self.lib.wn_forward_train(self.handle, ins[0].data_ptr(), ins[1].data_ptr(), ins[2].data_ptr(),
-                                           ins[3].data_ptr(), strides, out.data_ptr(), n, h, w, ws.data_ptr(),
-                                           ws.numel(), _stream_ptr(self.device))
-        _lib.check(rc, "wn_forward_train")
-        return out, ws
+                f"a forward pass that keeps its activations for autograd holds ~5.6 KB per pixel: one {h}x{w} image "
+                f"exceeds the {self.TRAIN_MAX_PIXELS >> 20} Mi-pixel limit of wn_forward_train.  For inference wrap the "
+                "call in torch.no_grad()")
+        per = max(1, self.TRAIN_MAX_PIXELS // (h * w))
+        saved = []
+        for a in range(0, n, per):
+            b = min(n, a + per)
+            part = [t[a:b] for t in ins]
+            strides = (ctypes.c_int64 * 16)(*[s for t in part for s in t.stride()])
+            ws = torch.empty(self.lib.wn_train_workspace_bytes(b - a, h, w), dtype=torch.uint8, device=self.device)
+            with torch.cuda.device(self.device):
+                rc = self.lib.wn_forward_train(self.handle, part[0].data_ptr(), part[1].data_ptr(), part[2].data_ptr(),
+                                               part[3].data_ptr(), strides, out[a:b].data_ptr(), b - a, h, w,
+                                               ws.data_ptr(), ws.numel(), _stream_ptr(self.device))
+            _lib.check(rc, "wn_forward_train")
+            saved.append((a, b, ws))
+        return out, saved
 
-    def backward(self, grad_out: torch.Tensor, saved_ws: torch.Tensor, shapes, want_input_grads: bool = False):
-        """d(loss)/d(out) + the workspace of forward_train -> the 34 parameter gradients (state-dict order)
-        and, on request, the gradients of the four input images."""
+    def backward(self, grad_out: torch.Tensor, saved, shapes, want_input_grads: bool = False):
+        """d(loss)/d(out) + the workspaces of forward_train -> the 34 parameter gradients (state-dict order)
+        and, on request, the gradients of the four input images.  Batch slices are processed in order and their
+        parameter gradients added in that order (deterministic)."""
         g = grad_out.detach().to(self.device, torch.float32).contiguous()
         n, _, h, w = g.shape
-        grads = [torch.empty(tuple(s), dtype=torch.float32, device=self.device) for s in shapes]
-        arr = (ctypes.c_void_p * _lib.NUM_PARAMS)(*[t.data_ptr() for t in grads])
-        gin, gin_arr = None, None
+        saved = saved or []
+        make = torch.empty if saved else torch.zeros  # an empty batch has zero gradients
+        grads = [make(tuple(s), dtype=torch.float32, device=self.device) for s in shapes]
+        part = grads if len(saved) <= 1 else [torch.empty_like(t) for t in grads]
+        gin = None
         if want_input_grads:
             gin = [torch.empty((n, 3, h, w), dtype=torch.float32, device=self.device) for _ in range(4)]
-            gin_arr = (ctypes.c_void_p * 4)(*[t.data_ptr() for t in gin])
-        with torch.cuda.device(self.device):
-            rc = self.lib.wn_backward(self.handle, g.data_ptr(), arr, gin_arr, n, h, w, saved_ws.data_ptr(),
-                                      saved_ws.numel(), _stream_ptr(self.device))
-        _lib.check(rc, "wn_backward")
+        for i, (a, b, ws) in enumerate(saved):
+            dst = grads if i == 0 else part
+            arr = (ctypes.c_void_p * _lib.NUM_PARAMS)(*[t.data_ptr() for t in dst])
+            gin_arr = (ctypes.c_void_p * 4)(*[t[a:b].data_ptr() for t in gin]) if want_input_grads else None
+            with torch.cuda.device(self.device):
+                rc = self.lib.wn_backward(self.handle, g[a:b].data_ptr(), arr, gin_arr, b - a, h, w, ws.data_ptr(),
+                                          ws.numel(), _stream_ptr(self.device))
+            _lib.check(rc, "wn_backward")
+            if i > 0:
+                torch._foreach_add_(grads, part)
         return (grads, gin) if want_input_grads else grads
 
     # ---- preprocess / postprocess ----------------------------------------------

@@ -97,6 +97,13 @@ def test_postprocess_matches_ten2arr(eng):
 MODES = ["fp32", "bf16x3", "bf16_fp8"]
 
 
+def _assert_u8_close(got, want, share=0.01):
+    """uint8 images of two evaluations that differ by rounding: a truncating cast flips a level where the value sits
+    on a boundary -- one level at most, on a small share of the bytes."""
+    diff = np.abs(np.asarray(got).astype(int) - np.asarray(want).astype(int))
+    assert diff.max() <= 1 and (diff != 0).mean() < share, (diff.max(), (diff != 0).mean())
+
+
 def _model(seed, gain, precision):
     from waternet_b200.net import WaterNet
     m = WaterNet(precision=precision)
@@ -550,7 +557,8 @@ def test_multi_pass_batch_equals_per_image_and_oracle(precision):
     _assert_close(chunked.cpu().numpy(), ref.numpy())
     _assert_close(maps.cpu().numpy(), cm_ref.numpy())
     _assert_close(refined.cpu().numpy(), parts[2].numpy())
-    assert np.array_equal(u8.cpu().numpy(), opre.ten2arr(chunked.cpu().numpy())), "uint8 epilogue != ten2arr(fp32 output)"
+    _assert_close(f32.cpu().numpy(), ref.numpy())
+    assert np.array_equal(u8.cpu().numpy(), opre.ten2arr(f32.cpu().numpy())), "uint8 epilogue != ten2arr(fp32 output)"
 
 
 @pytest.mark.parametrize("precision", TC_MODES)
@@ -725,8 +733,15 @@ def test_default_mode_margin_on_every_weight_set(weights):
         out = m(*[t.cuda() for t in ins]).cpu().numpy()
     assert not m.engine().f8_overflowed()
     rel = _assert_close(out, ref)
-    print(f"default mode, {weights}: max rel err {rel:.2e}")
-    assert rel < 6e-4
+    # the folded uint8 path (wn_enhance_u8: the preprocess kernel writes the first layer's level planes)
+    frames = torch.from_numpy(np.ascontiguousarray(np.stack(rgbs))).cuda()
+    f32 = torch.empty(len(rgbs), 3, 112, 112, device="cuda")
+    u8 = m.engine().enhance(frames, mode=m._mode(), out_f32=f32)
+    assert not m.engine().f8_overflowed()
+    rel_folded = _assert_close(f32.cpu().numpy(), ref)
+    print(f"default mode, {weights}: max rel err {rel:.2e} (tensor inputs), {rel_folded:.2e} (folded uint8 path)")
+    assert rel < 6e-4 and rel_folded < 6e-4
+    _assert_u8_close(u8.cpu().numpy(), opre.ten2arr(ref), share=0.10)
 
 
 # ------------------------------------------------------------------ output stores fused with the exchange

@@ -154,7 +154,7 @@ static __global__ void scatter_tapstack_kernel(const float* __restrict__ src, fl
 //   out[c]        = refined[0][c] * cm[0] + refined[1][c] * cm[1] + refined[2][c] * cm[2]
 // written as fp32 NCHW and/or ten2arr'd uint8 NHWC; refined_out optionally receives the nine refined planes.
 // HBM-bound: 324 B/px of partial sums read exactly once, 12 B/px of maps, 3..48 B/px written.
-static __global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256, 8)  // 8 blocks = all 2048 threads of an SM: the kernel lives on loads in flight
 gather_gate_kernel(const float* __restrict__ taps, const float* __restrict__ bias, const float* __restrict__ cm,
                    float* __restrict__ out_f32, uint8_t* __restrict__ out_u8, float* __restrict__ refined_out, int H, int W,
                    PeerOut peers) {
@@ -206,24 +206,25 @@ gather_gate_kernel(const float* __restrict__ taps, const float* __restrict__ bia
     }
   }
   if (!cm || !out_u8) return;
-  // uint8 NHWC: the warp's 32 pixels are 96 contiguous bytes.  Lane l < 24 assembles 32-bit word l of them from its
-  // neighbours' bytes, so a full segment leaves as one coalesced 96-byte store per destination -- out_u8 and the same
-  // offset of every peer address (the all-gather of the output fused here; NVLink wants whole sectors, not bytes)
+  // uint8 NHWC: the warp's 32 pixels are 96 contiguous bytes.  With peer addresses (the all-gather of the output fused
+  // here) lane l < 24 assembles 32-bit word l of them from its neighbours' bytes, so a full segment leaves as one
+  // coalesced 96-byte store per destination: NVLink wants whole sectors, not bytes.  Without peers the three byte
+  // stores per pixel merge in L2 and cost less than the shuffles.
   const int lane = threadIdx.x & 31;
-  uint32_t word = 0;
-#pragma unroll
-  for (int j = 0; j < 4; j++) {
-    const int k = 4 * lane + j;  // byte k of the segment = component k % 3 of pixel k / 3 (lanes >= 24: unused)
-    word |= ((__shfl_sync(0xffffffffu, rgb, (k / 3) & 31) >> (8 * (k % 3))) & 0xffu) << (8 * j);
-  }
   const int xw = x - lane;  // the warp's first pixel
   const size_t off = ((size_t)n * hw + (size_t)y * W + xw) * 3;
-  if (xw + 32 <= W && (reinterpret_cast<uintptr_t>(out_u8 + off) & 3) == 0) {  // peers: aligned like out_u8 (host check)
+  if (peers.n > 0 && xw + 32 <= W && (reinterpret_cast<uintptr_t>(out_u8 + off) & 3) == 0) {  // warp-uniform
+    uint32_t word = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int k = 4 * lane + j;  // byte k of the segment = component k % 3 of pixel k / 3 (lanes >= 24: unused)
+      word |= ((__shfl_sync(0xffffffffu, rgb, (k / 3) & 31) >> (8 * (k % 3))) & 0xffu) << (8 * j);
+    }
     if (lane < 24) {
       reinterpret_cast<uint32_t*>(out_u8 + off)[lane] = word;
 #pragma unroll
       for (int i = 0; i < WN_MAX_PEERS; i++)  // unrolled: the addresses stay kernel parameters (no local copy)
-        if (i < peers.n) reinterpret_cast<uint32_t*>(peers.p[i] + off)[lane] = word;
+        if (i < peers.n) reinterpret_cast<uint32_t*>(peers.p[i] + off)[lane] = word;  // aligned like out_u8 (host check)
     }
   } else if (inside) {
     const size_t o = off + 3 * lane;

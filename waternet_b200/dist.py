@@ -133,17 +133,27 @@ class PeerGather:
         base = ctypes.c_void_p()
         handle = (ctypes.c_ubyte * _lib.PEER_HANDLE_BYTES)()
         with torch.cuda.device(self.device):
-            self._check(self._lib.wn_peer_alloc(self._bytes, ctypes.byref(base), handle), "wn_peer_alloc")
-            self._base = base.value
+            try:
+                self._check(self._lib.wn_peer_alloc(self._bytes, ctypes.byref(base), handle), "wn_peer_alloc")
+                self._base = base.value
+                mine = bytes(handle)
+            except Exception:
+                mine = None  # still take part in the handle exchange: the other ranks are waiting in it
             handles = [None] * self.world
-            dist.all_gather_object(handles, bytes(handle), group=group)
-            for r, hb in enumerate(handles):
-                if r == self.rank:
-                    continue
-                ptr = ctypes.c_void_p()
-                buf = (ctypes.c_ubyte * _lib.PEER_HANDLE_BYTES).from_buffer_copy(hb)
-                self._check(self._lib.wn_peer_open(buf, ctypes.byref(ptr)), "wn_peer_open")
-                self._peer_base[r] = ptr.value
+            dist.all_gather_object(handles, mine, group=group)
+            try:
+                if any(hb is None for hb in handles):
+                    raise _lib.WaterNetLibraryError("a rank could not allocate or export its peer buffer")
+                for r, hb in enumerate(handles):
+                    if r == self.rank:
+                        continue
+                    ptr = ctypes.c_void_p()
+                    buf = (ctypes.c_ubyte * _lib.PEER_HANDLE_BYTES).from_buffer_copy(hb)
+                    self._check(self._lib.wn_peer_open(buf, ctypes.byref(ptr)), "wn_peer_open")
+                    self._peer_base[r] = ptr.value
+            except Exception:
+                self.close(collective=False)  # nothing of a half-built exchange stays mapped or allocated
+                raise
         block = torch.as_tensor(_DeviceBlock(self._base, self._bytes), device=self.device)
         self._block = block
         self.gathered = block[:self.world * self.slot_bytes].view(dtype).view((self.world,) + self.local_shape)
@@ -222,9 +232,16 @@ class PeerGather:
     def result(self) -> torch.Tensor:
         return self.gathered.view((-1,) + tuple(self.gathered.shape[2:]))
 
+    def __del__(self):
+        try:
+            self.close(collective=False)
+        except Exception:  # interpreter shutdown: the driver reclaims the memory with the process
+            pass
+
     def close(self, collective: bool = True) -> None:
-        """Unmap the peers' blocks and free this rank's (after every rank has stopped pushing, when collective)."""
-        if self._base is None:
+        """Unmap the peers' blocks and free this rank's (after every rank has stopped pushing, when collective).
+        Tensors obtained from ``result()`` / ``gathered`` alias that memory: copy what must outlive the exchange."""
+        if getattr(self, "_base", None) is None and not getattr(self, "_peer_base", None):
             return
         with torch.cuda.device(self.device):
             torch.cuda.synchronize(self.device)
@@ -236,7 +253,8 @@ class PeerGather:
             if collective and dist.is_initialized():
                 dist.barrier(group=self.group)  # nobody still maps a block that is about to be freed
             self.gathered = self._block = None
-            self._lib.wn_peer_free(self._base)
+            if self._base is not None:
+                self._lib.wn_peer_free(self._base)
             self._base = None
 
 

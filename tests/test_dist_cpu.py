@@ -57,6 +57,14 @@ def _worker(rank, world, port, n, ret):
             pg.on_pass(mine[a:a + 2], a, min(per, a + 2))
         want = torch.cat([fn(batch[:per]) + r for r in range(world)])
         ok = ok and pg.calls == 2 and torch.equal(pg.result(), want)
+        # no CUDA, no peer memory: every rank must agree on the NCCL / gloo all-gather form instead of hanging
+        from waternet_b200.dist import PeerGather
+        fb = PeerGather.create(tuple(mine.shape), mine.dtype, mine.device)
+        ok = ok and isinstance(fb, PassGather)
+        for a in range(0, per, 2):
+            fb.on_pass(mine[a:a + 2], a, min(per, a + 2))
+        fb.finish()
+        ok = ok and torch.equal(fb.result(), want)
         ret[rank] = bool(ok)
     finally:
         dist.destroy_process_group()

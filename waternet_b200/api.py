@@ -134,6 +134,9 @@ class Enhancer:
         n, h, w, _ = shape
         cur = torch.cuda.current_stream(dev)
         if n * h * w == 0:
+            if exchange is not None:  # an empty local batch still takes part in the step's completion protocol
+                exchange.signal()
+                exchange.wait()
             slot.done = torch.cuda.Event()
             slot.done.record(cur)
             return slot

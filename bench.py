@@ -11,8 +11,9 @@ WB/GC/HE preprocess -> gated-fusion forward -> uint8 enhanced images
 `value` times that with the uint8 batch already resident in HBM; `e2e` times the
 public host-buffer call (pinned host uint8 in, uint8 out) with both copies inside
 the timed region (pipelined pass by pass on side streams).  At N>1 every rank
-processes its own batch (weak scaling) and all-gathers its uint8 output over NCCL,
-pass by pass under the next pass's kernels (waternet_b200.dist.PassGather).
+processes its own batch (weak scaling); the all-gather of the uint8 output is
+fused into the launch that writes it -- NVLink stores into every rank's IPC-mapped buffer
+(waternet_b200.dist.PeerGather; --gather peer / nccl: copy-engine pushes / NCCL per pass).
 Before timing, image 0 of the batch is checked against the CPU reference (the line
 carries `parity`; the run fails above the 1e-3 bar).  Rank 0 prints ONE JSON line.
 """

@@ -152,8 +152,9 @@ int wn_enhance_u8(wn_handle* h, const uint8_t* rgb, uint8_t* out_nhwc, float* ou
 /*
  * wn_enhance_u8 with the all-gather of the output fused into the kernel that produces it (the one
  * exchange of the sharded path): the launch that writes out_nhwc stores the same bytes to peer_out[0..n_peers) --
- * addresses inside the other ranks' buffers, mapped with wn_peer_open (NVLink stores, 16 bytes each), each the
- * start of where THIS batch belongs there and aligned like out_nhwc modulo 16.  In the default mode that launch is
+ * addresses inside the other ranks' buffers, mapped with wn_peer_open (NVLink stores), each the start of where THIS
+ * batch belongs there.  Any alignment works; 4-byte aligned rows leave as whole 96-byte segments (16-byte aligned
+ * buffers as 16-byte copies in the copy-kernel forms), anything else byte by byte.  In the default mode that launch is
  * the HBM-bound gather/gate kernel at the end of every pass, so the exchange of a pass rides on a kernel that
  * leaves the tensor cores and most of the power budget idle; the other modes (and the range guard's re-run)
  * finish with a copy kernel.  Completion at the peers is the caller's business (wn_stream_write_value32 +

@@ -748,8 +748,9 @@ def test_default_mode_margin_on_every_weight_set(weights):
 @pytest.mark.parametrize("precision", MODES)
 def test_peer_out_addresses_receive_the_bytes_of_the_output(precision):
     """wn_enhance_u8_peers: every 'peer' address (here: other buffers of the same GPU, no IPC needed) ends up with
-    exactly the uint8 output, whichever launch writes it -- the gather/gate kernel (default mode: vector rows, ragged
-    rows, unaligned batches), the copy kernel behind the bf16x3 / fp32 chains -- and on multi-pass batches."""
+    exactly the uint8 output, whichever launch writes it -- the gather/gate kernel (default mode: whole segments,
+    ragged rows, destinations of any alignment), the copy kernel behind the bf16x3 / fp32 chains -- and on multi-pass
+    batches.  (In a PeerGather block rank r's slot starts r * B * H * W * 3 bytes in: odd shapes misalign it.)"""
     m = _model(0, 3.0, precision)
     eng = m.engine()
     for (n, h, w), cap in (((3, 64, 96), 2 * 64 * 96), ((2, 33, 47), 0), ((1, 40, 64), 0)):
@@ -760,9 +761,9 @@ def test_peer_out_addresses_receive_the_bytes_of_the_output(precision):
         try:
             block = torch.zeros(3 * frames.numel() + 64, dtype=torch.uint8, device="cuda")
             out = torch.zeros_like(frames)
-            k = out.data_ptr() % 16    # peers must be aligned like the output modulo 16
-            mirrors = [block[k + 16 + i * (frames.numel() + 16 - frames.numel() % 16):][:frames.numel()] for i in range(2)]
-            assert all(t.data_ptr() % 16 == k for t in mirrors)
+            k = out.data_ptr() % 16    # one peer aligned like the output (the fast stores), one off by a byte
+            mirrors = [block[k + 16 + i * (frames.numel() + 17 - frames.numel() % 16):][:frames.numel()] for i in range(2)]
+            assert mirrors[0].data_ptr() % 16 == k and mirrors[1].data_ptr() % 16 == (k + 1) % 16
             eng.enhance(frames, mode=m._mode(), out_u8=out, peer_out=[t.data_ptr() for t in mirrors])
             torch.cuda.synchronize()
         finally:
@@ -770,8 +771,8 @@ def test_peer_out_addresses_receive_the_bytes_of_the_output(precision):
         assert torch.equal(out, want)
         for t in mirrors:
             assert torch.equal(t.view(frames.shape), want)
-    with pytest.raises(Exception):   # misaligned peer address
-        eng.enhance(frames, mode=m._mode(), out_u8=out, peer_out=[mirrors[0].data_ptr() + 1])
+    with pytest.raises(Exception):   # more peers than the ABI takes
+        eng.enhance(frames, mode=m._mode(), out_u8=out, peer_out=[mirrors[0].data_ptr()] * 16)
     with pytest.raises(ValueError):  # an output tensor the kernels would fill in the wrong order
         eng.enhance(frames, mode=m._mode(), out_u8=torch.empty((n, w, h, 3), dtype=torch.uint8, device="cuda").permute(0, 2, 1, 3))
 

@@ -270,8 +270,8 @@ int wn_enhance_u8_peers(wn_handle* h, const uint8_t* rgb, uint8_t* out_nhwc, flo
     return WN_E_INVALID;
   }
   for (int k = 0; k < n_peers; k++) {
-    if (!peer_out[k] || (((uintptr_t)peer_out[k] ^ (uintptr_t)out_nhwc) & 15)) {
-      set_error("wn_enhance_u8_peers: peer address %d is null or not aligned like out_nhwc (mod 16)", k);
+    if (!peer_out[k]) {
+      set_error("wn_enhance_u8_peers: peer address %d is null", k);
       return WN_E_INVALID;
     }
     peers.p[k] = peer_out[k];

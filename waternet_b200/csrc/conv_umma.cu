@@ -208,35 +208,32 @@ gather_gate_kernel(const float* __restrict__ taps, const float* __restrict__ bia
   if (!cm || !out_u8) return;
   // uint8 NHWC: the warp's 32 pixels are 96 contiguous bytes.  With peer addresses (the all-gather of the output fused
   // here) lane l < 24 assembles 32-bit word l of them from its neighbours' bytes, so a full segment leaves as one
-  // coalesced 96-byte store per destination: NVLink wants whole sectors, not bytes.  Without peers the three byte
-  // stores per pixel merge in L2 and cost less than the shuffles.
+  // coalesced 96-byte store per (4-byte aligned) destination: NVLink wants whole sectors, not bytes.  Without peers the
+  // three byte stores per pixel merge in L2 and cost less than the shuffles.
   const int lane = threadIdx.x & 31;
   const int xw = x - lane;  // the warp's first pixel
   const size_t off = ((size_t)n * hw + (size_t)y * W + xw) * 3;
-  if (peers.n > 0 && xw + 32 <= W && (reinterpret_cast<uintptr_t>(out_u8 + off) & 3) == 0) {  // warp-uniform
-    uint32_t word = 0;
+  const bool words = peers.n > 0 && xw + 32 <= W;  // warp-uniform
+  uint32_t word = 0;
+  if (words) {
 #pragma unroll
     for (int j = 0; j < 4; j++) {
       const int k = 4 * lane + j;  // byte k of the segment = component k % 3 of pixel k / 3 (lanes >= 24: unused)
       word |= ((__shfl_sync(0xffffffffu, rgb, (k / 3) & 31) >> (8 * (k % 3))) & 0xffu) << (8 * j);
     }
-    if (lane < 24) {
-      reinterpret_cast<uint32_t*>(out_u8 + off)[lane] = word;
-#pragma unroll
-      for (int i = 0; i < WN_MAX_PEERS; i++)  // unrolled: the addresses stay kernel parameters (no local copy)
-        if (i < peers.n) reinterpret_cast<uint32_t*>(peers.p[i] + off)[lane] = word;  // aligned like out_u8 (host check)
-    }
-  } else if (inside) {
-    const size_t o = off + 3 * lane;
-#pragma unroll
-    for (int c = 0; c < 3; c++) {
-      const uint8_t q = (uint8_t)(rgb >> (8 * c));
-      out_u8[o + c] = q;
-#pragma unroll
-      for (int i = 0; i < WN_MAX_PEERS; i++)
-        if (i < peers.n) peers.p[i][o + c] = q;
-    }
   }
+  auto put = [&](uint8_t* dst) {  // this warp's segment -> dst (the same for every lane)
+    if (words && (reinterpret_cast<uintptr_t>(dst + off) & 3) == 0) {
+      if (lane < 24) reinterpret_cast<uint32_t*>(dst + off)[lane] = word;
+    } else if (inside) {
+#pragma unroll
+      for (int c = 0; c < 3; c++) dst[off + 3 * lane + c] = (uint8_t)(rgb >> (8 * c));
+    }
+  };
+  put(out_u8);
+#pragma unroll
+  for (int i = 0; i < WN_MAX_PEERS; i++)  // unrolled: the addresses stay kernel parameters (no local copy)
+    if (i < peers.n) put(peers.p[i]);
 }
 // out -> every peer address (the paths whose uint8 output leaves a convolution epilogue: bf16x3 mode, the range guard's
 // re-run -- then conditional on *run_if like every launch of that chain -- and the A/B switches)
@@ -244,17 +241,14 @@ static __global__ void __launch_bounds__(256)
 mirror_u8_kernel(const uint8_t* __restrict__ src, PeerOut peers, size_t bytes, const int* __restrict__ run_if) {
   if (run_if && *run_if == 0) return;
   const size_t stride = (size_t)gridDim.x * blockDim.x, i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const size_t vecs = ((reinterpret_cast<uintptr_t>(src) & 15) == 0) ? bytes / 16 : 0;  // peers: same alignment (host check)
-  for (size_t i = i0; i < vecs; i += stride) {
-    const uint4 q = reinterpret_cast<const uint4*>(src)[i];
 #pragma unroll
-    for (int k = 0; k < WN_MAX_PEERS; k++)
-      if (k < peers.n) reinterpret_cast<uint4*>(peers.p[k])[i] = q;
-  }
-  for (size_t i = vecs * 16 + i0; i < bytes; i += stride) {
-#pragma unroll
-    for (int k = 0; k < WN_MAX_PEERS; k++)
-      if (k < peers.n) peers.p[k][i] = src[i];
+  for (int k = 0; k < WN_MAX_PEERS; k++) {
+    if (k >= peers.n) continue;
+    uint8_t* dst = peers.p[k];
+    // 16-byte copies where source and destination allow it (the batches of a 16-byte aligned buffer); bytes otherwise
+    const size_t vecs = (((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0) ? bytes / 16 : 0;
+    for (size_t i = i0; i < vecs; i += stride) reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(src)[i];
+    for (size_t i = vecs * 16 + i0; i < bytes; i += stride) dst[i] = src[i];
   }
 }
 int mirror_u8(wn_handle* h, const uint8_t* src, const PeerOut& peers, size_t bytes, const int* run_if, cudaStream_t stream) {
